@@ -1,0 +1,137 @@
+/*
+ * meld_b200.h -- C-ABI of libmeld_b200.so, the sm_100a engine behind
+ * meld.MELD().fit_transform / meld.utils.normalize_densities.
+ *
+ * The reference (KrishnaswamyLab/MELD) has no FFI of its own: its seam is the
+ * Python API plus the duck-typed graph protocol used by meld/filter.py
+ * (graph.estimate_lmax(), graph.lmax, graph.L, graph.N).  Each entry point below
+ * cites the reference call it stands in for; INTEGRATION.md shows the ctypes stub
+ * a maintainer would add to the reference.
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative meld_b200_status; the text
+ *    of the last failure on the calling thread is meld_b200_last_error().
+ *  - All array arguments are DEVICE pointers unless the name ends in `_host`.
+ *    The caller (PyTorch, as the device-memory container) owns every buffer it
+ *    passes in; the library owns only the opaque handles it creates.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Calls are asynchronous with respect to the host unless stated otherwise.
+ *  - A handle is not thread-safe.  No C++ exception crosses this boundary.
+ *  - There is no CPU fallback: without a CUDA device every compute call fails
+ *    with MELD_B200_ERR_CUDA.
+ */
+#ifndef MELD_B200_H_
+#define MELD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum meld_b200_status {
+  MELD_B200_OK = 0,
+  MELD_B200_ERR_INVALID = -1, /* bad argument (NULL, shape, range)            */
+  MELD_B200_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed          */
+  MELD_B200_ERR_NOMEM = -3,   /* device or host allocation failed             */
+  MELD_B200_ERR_UNSUPPORTED = -4, /* outside the engine-supported subset      */
+  MELD_B200_ERR_INTERNAL = -5
+} meld_b200_status;
+
+/* Opaque device graph: CSR of the combinatorial Laplacian L = D - W (float64
+ * values, int32 columns) for rows [row0, row0 + n_rows) of an n_cols-wide
+ * operator, plus the row-block partition the Chebyshev kernel stages by TMA. */
+typedef struct meld_b200_graph meld_b200_graph_t;
+
+/* ---- library ---------------------------------------------------------------- */
+int meld_b200_version(void);              /* major*10000 + minor*100 + patch     */
+const char *meld_b200_last_error(void);   /* thread-local, never NULL            */
+/* sm_count / cc_major / cc_minor of the current device (host pointers).        */
+int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+
+/* Launch-configuration knobs of the Chebyshev kernel, for bench sweeps and tests
+ * only (keys: blk_chunk, stage_cap, n_stage, threads, ctas_per_sm, group,
+ * use_graph).  Takes effect for graphs created afterwards.                       */
+int meld_b200_set_tuning(const char *key, int value);
+
+/* ---- graph construction ------------------------------------------------------ */
+
+/* Stands in for graphtools.Graph(X, knn, decay, thresh, anisotropy, use_pygsp=True)
+ * as reached from MELD.fit (reference meld/meld.py:117-118, :273): exact
+ * Euclidean kNN, alpha-decay kernel K_ij = exp(-(d_ij/eps_i)^decay) for every j
+ * with K_ij >= thresh, (K+K^T)/2, anisotropy K_ij/(q_i q_j)^a, W = K - diag,
+ * L = diag(W 1) - W.  X is (n, d) row-major float64 (the post-PCA data_nu).
+ * flags: bit0 keep the un-symmetrised kernel for meld_b200_graph_export_knn_kernel,
+ *        bit1 use the SIMT fp32 candidate search instead of the tcgen05 one
+ *        (test cross-check only).
+ * Synchronises the stream (row counts come back to size the CSR).               */
+#define MELD_B200_FLAG_KEEP_KNN_KERNEL 1
+#define MELD_B200_FLAG_SIMT_SEARCH 2
+int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay,
+                              double thresh, double anisotropy, double bandwidth_scale,
+                              int flags, void *stream, meld_b200_graph_t **graph_out);
+
+/* Parity / prebuilt-graph entry (reference: MELD.fit(graph) short-circuit,
+ * meld/benchmark.py:194-195): adopt a CSR Laplacian built elsewhere.  Rows
+ * [row0, row0+n_rows) of an operator with n_cols columns; indptr has n_rows+1
+ * int64 entries starting at 0.  The arrays are copied; the caller keeps its own. */
+int meld_b200_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz,
+                             const int64_t *indptr, const int32_t *indices, const double *data,
+                             void *stream, meld_b200_graph_t **graph_out);
+
+int meld_b200_graph_info(const meld_b200_graph_t *g, int64_t *n_rows_host, int64_t *n_cols_host,
+                         int64_t *row0_host, int64_t *nnz_host);
+/* Copies L out (caller-allocated: indptr n_rows+1 int64, indices nnz int32, data nnz f64). */
+int meld_b200_graph_export_csr(const meld_b200_graph_t *g, int64_t *indptr, int32_t *indices,
+                               double *data, void *stream);
+/* Un-symmetrised alpha-decay kernel (graphtools kNNGraph.build_kernel_to_data);
+ * only when built with MELD_B200_FLAG_KEEP_KNN_KERNEL.                           */
+int meld_b200_graph_knn_kernel_nnz(const meld_b200_graph_t *g, int64_t *nnz_host);
+int meld_b200_graph_export_knn_kernel(const meld_b200_graph_t *g, int64_t *indptr, int32_t *indices,
+                                      double *data, void *stream);
+/* Build statistics (host): [0] candidate-search passes run, [1] max candidates/row,
+ * [2] candidate capacity used, [3] rows that overflowed on the first emit pass,
+ * [4] search implementation (0 tcgen05, 1 SIMT), [5..7] reserved.                */
+int meld_b200_graph_build_stats(const meld_b200_graph_t *g, int64_t *stats8_host);
+int meld_b200_graph_destroy(meld_b200_graph_t *g);
+
+/* ---- filter ------------------------------------------------------------------- */
+
+/* Stands in for pygsp Graph.estimate_lmax() (reference meld/filter.py:39):
+ * Lanczos on L, returns 1.01 * largest Ritz value (the reference's 1.01 factor).
+ * Converged to `rel_tol` or `max_iters`, whichever first.  Synchronous.
+ * Only for full (row0 == 0, n_rows == n_cols) graphs.                            */
+int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol, void *stream,
+                            double *lmax_host, int *iters_host);
+
+/* Stands in for pygsp cheby_op(G, c, signal) as called by
+ * pygsp.filters.Filter.filter(method="chebyshev") from meld/filter.py:56-59.
+ * coeffs_host: m+1 Chebyshev coefficients (host).  S, R: (n, p) row-major float64
+ * device arrays, p <= 8 per call.  R may not alias S.                            */
+int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coeffs_host, int n_coeffs,
+                           const double *S, int p, double *R, void *stream);
+
+/* One term of the three-term recurrence on this graph's rows, for callers that
+ * exchange T between ranks after each step (row-partitioned multi-GPU):
+ *   y      = L[rows,:] @ T_cur                       (T_cur: n_cols x p, global rows)
+ *   T_new  = alpha * (y - shift * T_cur[row0+i]) - gamma * T_old[i]
+ *   R[i]   = (r_scale ? R[i] : 0) + c * T_new[i] + c_cur * T_cur[row0+i]
+ * T_old / T_new / R are (n_rows, p) local-row arrays; T_new may alias T_old;
+ * T_old may be NULL when gamma == 0, R may be NULL to skip the accumulation.    */
+int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double *T_old, double *T_new,
+                         double *R, int p, double alpha, double shift, double gamma, double c,
+                         double c_cur, int r_accumulate, void *stream);
+
+/* ---- small fused host-side helpers -------------------------------------------- */
+
+/* meld/meld.py:143-191 + :229-232: one-hot indicators from integer label codes
+ * (codes[i] in [0,p)), optionally column-normalised to sum 1.  S: (n, p) f64.   */
+int meld_b200_indicator_matrix(const int32_t *codes, int64_t n, int p, int sample_normalize, double *S,
+                               void *stream);
+/* meld/utils.py:35-47: row-wise L1 normalisation, zero rows stay zero.          */
+int meld_b200_l1_normalize_rows(const double *in, int64_t n, int p, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MELD_B200_H_ */

@@ -1,0 +1,121 @@
+// Shared internals of libmeld_b200.so (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <new>
+
+#include "../../include/meld_b200.h"
+
+namespace meld {
+
+// ---- error plumbing --------------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define MELD_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t err__ = (call);                                                                  \
+    if (err__ != cudaSuccess) {                                                                  \
+      meld::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+      return (err__ == cudaErrorMemoryAllocation) ? MELD_B200_ERR_NOMEM : MELD_B200_ERR_CUDA;    \
+    }                                                                                            \
+  } while (0)
+
+#define MELD_CHECK(expr)        \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+#define MELD_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      meld::set_error(__VA_ARGS__);    \
+      return MELD_B200_ERR_INVALID;    \
+    }                                  \
+  } while (0)
+
+#define MELD_LAUNCH_CHECK() MELD_CUDA(cudaGetLastError())
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+int sm_count();
+
+// Launch configuration of the Chebyshev SpMM kernel (see cheby.cu).  The defaults are
+// the shipped configuration; meld_b200_set_tuning changes them for bench sweeps.
+struct Tuning {
+  int blk_chunk = 1536;   // target CSR entries per row block (C)
+  int stage_cap = 2048;   // entries of shared memory per pipeline stage
+  int n_stage = 3;        // TMA pipeline depth per CTA
+  int threads = 128;      // threads per CTA
+  int ctas_per_sm = 3;    // persistent CTAs per SM
+  int group = 0;          // lanes per row (0 = choose from mean nnz/row)
+  int use_graph = 1;      // capture the m-step recurrence in a CUDA graph
+};
+Tuning &tuning();
+
+// ---- device buffer with explicit ownership -----------------------------------------
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      cudaGetLastError();
+      return MELD_B200_ERR_NOMEM;
+    }
+    n = count;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// Elements of padding appended to col/val so the 16-byte aligned TMA bulk copies of
+// a row block may start before / end after the block's own entries.
+constexpr int kCsrPad = 16;
+
+}  // namespace meld
+
+// The opaque handle of include/meld_b200.h.
+struct meld_b200_graph {
+  int64_t n_rows = 0, n_cols = 0, row0 = 0, nnz = 0;
+  // CSR of L (values f64, columns int32, row pointers int32: nnz < 2^31 per GPU).
+  meld::DevBuf<int32_t> row_ptr;  // n_rows + 1
+  meld::DevBuf<int32_t> col;      // nnz + kCsrPad
+  meld::DevBuf<double> val;       // nnz + kCsrPad
+  // Row-block partition for the TMA-staged SpMM: block b = rows [blk[b], blk[b+1]).
+  meld::DevBuf<int32_t> blk;  // n_blk + 1
+  int32_t n_blk = 0;
+  int32_t blk_chunk = 0;  // target nnz per block (C)
+  int32_t max_row_nnz = 0;
+  // Chebyshev / Lanczos workspace, grown on demand.
+  meld::DevBuf<double> work;
+  // Un-symmetrised kNN kernel kept for export (padded rows), optional.
+  meld::DevBuf<int32_t> knn_cnt;   // n
+  meld::DevBuf<int32_t> knn_col;   // n * knn_cap
+  meld::DevBuf<double> knn_val;    // n * knn_cap
+  int32_t knn_cap = 0;
+  int64_t knn_nnz = -1;
+  int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace meld {
+// Build the row-block partition (and max_row_nnz) of a graph whose row_ptr is final.
+int graph_finalize(meld_b200_graph *g, cudaStream_t stream);
+}  // namespace meld

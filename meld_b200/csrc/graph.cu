@@ -1,0 +1,212 @@
+// Graph handle management: adopt / export CSR Laplacians, row-block partition.
+#include "common.cuh"
+
+#include <string.h>
+#include <stdlib.h>
+
+namespace meld {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  cached = n;
+  return n;
+}
+
+// ---- tuning knobs (bench / tests only; defaults are the shipped configuration) ------
+Tuning g_tuning;
+
+Tuning &tuning() { return g_tuning; }
+
+// blk[b] = first row whose first entry is at or after b * chunk.
+__global__ void partition_rows_kernel(const int32_t *__restrict__ row_ptr, int64_t n_rows, int32_t chunk,
+                                      int32_t n_blk, int32_t *__restrict__ blk) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_blk) return;
+  if (b == n_blk) {
+    blk[b] = (int32_t)n_rows;
+    return;
+  }
+  int64_t target = (int64_t)b * chunk;
+  int64_t lo = 0, hi = n_rows;  // lower_bound over row_ptr[0..n_rows)
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)row_ptr[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  blk[b] = (int32_t)lo;
+}
+
+__global__ void max_row_nnz_kernel(const int32_t *__restrict__ row_ptr, int64_t n_rows, int32_t *out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t m = 0;
+  for (; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) m = max(m, row_ptr[i + 1] - row_ptr[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+int graph_finalize(meld_b200_graph *g, cudaStream_t stream) {
+  const int32_t chunk = tuning().blk_chunk;
+  g->blk_chunk = chunk;
+  g->n_blk = (int32_t)(g->nnz > 0 ? ceil_div(g->nnz, chunk) : 1);
+  MELD_CHECK(g->blk.alloc((size_t)g->n_blk + 1));
+  partition_rows_kernel<<<(unsigned)ceil_div(g->n_blk + 1, 256), 256, 0, stream>>>(g->row_ptr.p, g->n_rows, chunk,
+                                                                                  g->n_blk, g->blk.p);
+  MELD_LAUNCH_CHECK();
+  DevBuf<int32_t> mx;
+  MELD_CHECK(mx.alloc(1));
+  MELD_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int32_t), stream));
+  if (g->n_rows > 0) {
+    int grid = (int)(ceil_div(g->n_rows, 256) < 1184 ? ceil_div(g->n_rows, 256) : 1184);
+    max_row_nnz_kernel<<<grid, 256, 0, stream>>>(g->row_ptr.p, g->n_rows, mx.p);
+    MELD_LAUNCH_CHECK();
+  }
+  MELD_CUDA(cudaMemcpyAsync(&g->max_row_nnz, mx.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  MELD_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+__global__ void indptr64_to_32_kernel(const int64_t *__restrict__ in, int64_t n, int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)in[i];
+}
+__global__ void indptr32_to_64_kernel(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int64_t)in[i];
+}
+
+}  // namespace meld
+
+using namespace meld;
+
+extern "C" {
+
+int meld_b200_version(void) { return 100; /* 0.1.0 */ }
+
+const char *meld_b200_last_error(void) { return g_err; }
+
+int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host) {
+  int dev = 0;
+  MELD_CUDA(cudaGetDevice(&dev));
+  int sms = 0, maj = 0, min = 0;
+  MELD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  MELD_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  MELD_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count_host) *sm_count_host = sms;
+  if (cc_major_host) *cc_major_host = maj;
+  if (cc_minor_host) *cc_minor_host = min;
+  return 0;
+}
+
+int meld_b200_set_tuning(const char *key, int value) {
+  MELD_REQUIRE(key != nullptr, "set_tuning: NULL key");
+  Tuning &t = tuning();
+  if (!strcmp(key, "blk_chunk")) t.blk_chunk = value;
+  else if (!strcmp(key, "stage_cap")) t.stage_cap = value;
+  else if (!strcmp(key, "n_stage")) t.n_stage = value;
+  else if (!strcmp(key, "threads")) t.threads = value;
+  else if (!strcmp(key, "ctas_per_sm")) t.ctas_per_sm = value;
+  else if (!strcmp(key, "group")) t.group = value;
+  else if (!strcmp(key, "use_graph")) t.use_graph = value;
+  else {
+    set_error("set_tuning: unknown key '%s'", key);
+    return MELD_B200_ERR_INVALID;
+  }
+  return 0;
+}
+
+int meld_b200_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, const int64_t *indptr,
+                             const int32_t *indices, const double *data, void *stream_, meld_b200_graph_t **out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(out != nullptr, "graph_from_csr: graph_out is NULL");
+  *out = nullptr;
+  MELD_REQUIRE(n_rows >= 0 && n_cols > 0 && row0 >= 0 && row0 + n_rows <= n_cols,
+               "graph_from_csr: bad shape n_rows=%lld n_cols=%lld row0=%lld", (long long)n_rows, (long long)n_cols,
+               (long long)row0);
+  MELD_REQUIRE(nnz >= 0 && nnz < (int64_t)2147483647 - kCsrPad, "graph_from_csr: nnz=%lld out of range",
+               (long long)nnz);
+  MELD_REQUIRE(n_cols < (int64_t)2147483647, "graph_from_csr: n_cols too large for int32 columns");
+  MELD_REQUIRE(indptr && (nnz == 0 || (indices && data)), "graph_from_csr: NULL array");
+  meld_b200_graph *g = new (std::nothrow) meld_b200_graph();
+  if (!g) {
+    set_error("graph_from_csr: host allocation failed");
+    return MELD_B200_ERR_NOMEM;
+  }
+  g->n_rows = n_rows;
+  g->n_cols = n_cols;
+  g->row0 = row0;
+  g->nnz = nnz;
+  int rc = 0;
+  auto fail = [&](int code) {
+    delete g;
+    return code;
+  };
+  if ((rc = g->row_ptr.alloc((size_t)n_rows + 1))) return fail(rc);
+  if ((rc = g->col.alloc((size_t)nnz + kCsrPad))) return fail(rc);
+  if ((rc = g->val.alloc((size_t)nnz + kCsrPad))) return fail(rc);
+  indptr64_to_32_kernel<<<(unsigned)ceil_div(n_rows + 1, 256), 256, 0, stream>>>(indptr, n_rows + 1, g->row_ptr.p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->col.p + nnz, 0, kCsrPad * sizeof(int32_t), stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->val.p + nnz, 0, kCsrPad * sizeof(double), stream);
+  if (e == cudaSuccess && nnz > 0)
+    e = cudaMemcpyAsync(g->col.p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess && nnz > 0)
+    e = cudaMemcpyAsync(g->val.p, data, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) {
+    set_error("graph_from_csr: %s", cudaGetErrorString(e));
+    return fail(MELD_B200_ERR_CUDA);
+  }
+  if ((rc = graph_finalize(g, stream))) return fail(rc);
+  *out = g;
+  return 0;
+}
+
+int meld_b200_graph_info(const meld_b200_graph_t *g, int64_t *n_rows, int64_t *n_cols, int64_t *row0, int64_t *nnz) {
+  MELD_REQUIRE(g != nullptr, "graph_info: NULL graph");
+  if (n_rows) *n_rows = g->n_rows;
+  if (n_cols) *n_cols = g->n_cols;
+  if (row0) *row0 = g->row0;
+  if (nnz) *nnz = g->nnz;
+  return 0;
+}
+
+int meld_b200_graph_export_csr(const meld_b200_graph_t *g, int64_t *indptr, int32_t *indices, double *data,
+                               void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(g && indptr && indices && data, "graph_export_csr: NULL argument");
+  indptr32_to_64_kernel<<<(unsigned)ceil_div(g->n_rows + 1, 256), 256, 0, stream>>>(g->row_ptr.p, g->n_rows + 1,
+                                                                                  indptr);
+  MELD_LAUNCH_CHECK();
+  if (g->nnz > 0) {
+    MELD_CUDA(cudaMemcpyAsync(indices, g->col.p, (size_t)g->nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    MELD_CUDA(cudaMemcpyAsync(data, g->val.p, (size_t)g->nnz * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  }
+  return 0;
+}
+
+int meld_b200_graph_build_stats(const meld_b200_graph_t *g, int64_t *stats8_host) {
+  MELD_REQUIRE(g && stats8_host, "graph_build_stats: NULL argument");
+  memcpy(stats8_host, g->stats, sizeof(g->stats));
+  return 0;
+}
+
+int meld_b200_graph_destroy(meld_b200_graph_t *g) {
+  delete g;
+  return 0;
+}
+
+}  // extern "C"

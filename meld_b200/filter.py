@@ -1,0 +1,97 @@
+"""MELD graph filter on the GPU: same signature as the reference ``meld.filter.filter``.
+
+Reference: ``meld/filter.py:5-61`` -- estimate lmax, build the heat / laplacian
+kernel h(lambda / lmax), apply it with PyGSP's Chebyshev approximation
+(``compute_cheby_coeff`` + ``cheby_op``).  Here the m+1 coefficients are computed
+on the host (a few dozen numbers) and the three-term recurrence runs in
+libmeld_b200 (``meld_b200_cheby_filter``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nv
+from .graph import DeviceGraph, _as_device_f64
+
+MAX_P = 8  # signal columns per recurrence launch
+
+
+def filter_kernel(name, beta, offset=0, order=1):
+    """h(x) on normalised eigenvalues x = lambda / lmax (``meld/filter.py:42-53``)."""
+    name = name.lower()
+    if name == "laplacian":
+        return lambda x: 1 / (1 + (beta * np.abs(x - offset)) ** order)
+    if name == "heat":
+        return lambda x: np.exp(-beta * np.abs(x - offset) ** order)
+    raise NotImplementedError
+
+
+def cheby_coefficients(h, lmax, m):
+    """Chebyshev coefficients of h(lambda/lmax) on [0, lmax]: m+1 values from m+1 nodes.
+
+    Same quadrature as PyGSP ``compute_cheby_coeff`` (N = m+1 nodes, c_0 used halved).
+    """
+    n = m + 1
+    q = np.arange(n)
+    a = lmax / 2.0
+    hv = h((a * np.cos(np.pi * (q + 0.5) / n) + a) / lmax)
+    # one dot product per order, arguments formed as pi*o*(q+1/2)/n, so the few dozen
+    # coefficients round exactly like PyGSP's loop
+    return np.array([2.0 / n * np.dot(hv, np.cos(np.pi * o * (q + 0.5) / n)) for o in range(m + 1)])
+
+
+def filter(signal, graph, filter, beta, offset=0, order=1, solver="chebyshev", chebyshev_order=None):
+    """Low-pass filter ``signal`` (N, p) over ``graph``; returns an ndarray (or a CUDA tensor
+    when ``signal`` is one)."""
+    if not isinstance(graph, DeviceGraph):
+        raise TypeError("graph must be a meld_b200.DeviceGraph")
+    h = filter_kernel(filter, beta, offset, order)  # NotImplementedError for unknown kernels
+    if solver != "chebyshev":
+        raise NotImplementedError(
+            "solver='{}' is not available in the B200 engine (dense O(N^3) eigendecomposition); "
+            "use solver='chebyshev'".format(solver)
+        )
+    torch = nv.require_cuda()
+    lmax = graph.estimate_lmax()
+    coeffs = np.ascontiguousarray(cheby_coefficients(h, lmax, int(chebyshev_order)), dtype=np.float64)
+    on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
+    S = _as_device_f64(torch, signal)
+    squeeze = S.dim() == 1
+    if squeeze:
+        S = S[:, None]
+    R = cheby_apply(graph, lmax, coeffs, S)
+    if squeeze:
+        R = R[:, 0]
+    return R if on_device else R.cpu().numpy()
+
+
+def cheby_apply(graph, lmax, coeffs, S):
+    """R = sum_k c_k T_k(L) S on the device; S is an (N, p) float64 CUDA tensor."""
+    torch = nv.require_cuda()
+    N, p = S.shape
+    if N != graph.N:
+        raise ValueError("signal has {} rows, graph has {} nodes".format(N, graph.N))
+    cptr = coeffs.ctypes.data_as(C.POINTER(C.c_double))
+    if p <= MAX_P:
+        S = S.contiguous()
+        R = torch.empty_like(S)
+        nv.check(
+            nv.lib().meld_b200_cheby_filter(graph._h, float(lmax), cptr, len(coeffs), nv.ptr(S), p, nv.ptr(R),
+                                            nv.current_stream_ptr()),
+            "cheby_filter",
+        )
+        return R
+    R = torch.empty((N, p), dtype=torch.float64, device=S.device)
+    for j in range(0, p, MAX_P):
+        Sj = S[:, j:j + MAX_P].contiguous()
+        Rj = torch.empty_like(Sj)
+        nv.check(
+            nv.lib().meld_b200_cheby_filter(graph._h, float(lmax), cptr, len(coeffs), nv.ptr(Sj), Sj.shape[1],
+                                            nv.ptr(Rj), nv.current_stream_ptr()),
+            "cheby_filter",
+        )
+        R[:, j:j + MAX_P] = Rj
+    return R

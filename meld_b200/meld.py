@@ -1,0 +1,402 @@
+"""``MELD`` estimator with the reference's public API, driving the B200 engine.
+
+Mirrors ``meld/meld.py`` of KrishnaswamyLab/MELD (constructor defaults ``:94-107``,
+``set_params`` reset semantics ``:127-141``, label handling ``:143-191``,
+``transform`` ``:193-250``, ``fit_transform`` ``:252-274``) and the part of
+``graphtools.estimator.GraphEstimator`` it inherits (``fit``, graph parameters
+``knn=5, decay=40, n_pca=100, thresh=1e-4``).  Argument names, defaults, returned
+DataFrame layout and exception texts are the reference's; the graph build and the
+Chebyshev filter run in libmeld_b200 on the GPU.  There is no CPU path.
+"""
+
+from __future__ import annotations
+
+import numbers
+import time
+
+import numpy as np
+import pandas as pd
+
+from . import _native as nv
+from . import filter as _filter
+from . import utils
+from .graph import DeviceGraph, _as_device_f64
+
+_FILTER_PARAMS = ["beta", "offset", "order", "solver", "chebyshev_order", "lap_type", "filter"]
+_GRAPH_PARAMS = ["knn", "decay", "thresh", "n_pca", "distance", "anisotropy", "random_state", "bandwidth_scale"]
+
+
+def _check_positive(**params):
+    for p in params:
+        if not isinstance(params[p], numbers.Number) or params[p] <= 0:
+            raise ValueError("Expected {} > 0, got {}".format(p, params[p]))
+
+
+def _check_int(**params):
+    for p in params:
+        if not isinstance(params[p], numbers.Integral):
+            raise ValueError("Expected {} integer, got {}".format(p, params[p]))
+
+
+def _check_in(choices, **params):
+    for p in params:
+        if params[p] not in choices:
+            raise ValueError("{} value {} not recognized. Choose from {}".format(p, params[p], choices))
+
+
+class MELD(object):
+    """MELD operator for filtering sample-indicator signals over a cell-similarity graph.
+
+    Parameters
+    ----------
+    beta : int, optional, Default: 60
+        Amount of smoothing to apply.
+    offset : float, optional, Default: 0
+        Shift of the filter in the (normalised) eigenvalue spectrum, in [0, 1].
+    order : int, optional, Default: 1
+        Falloff / smoothness of the filter.
+    filter : str, optional, Default: 'heat'
+        'heat' or 'laplacian'.
+    solver : str, optional, Default: 'chebyshev'
+        Only 'chebyshev' runs on the B200 engine; 'exact' is validated but raises
+        NotImplementedError at transform time.
+    chebyshev_order : int, optional, Default: 50
+    lap_type : ('combinatorial', 'normalized'), Default: 'combinatorial'
+        Validated and stored; like the reference it is never forwarded to the graph,
+        whose Laplacian is always combinatorial.
+    sample_normalize : bool, optional, Default: True
+        Column-normalise the indicator vectors to sum 1.
+    anisotropy : float, optional, Default: 1
+    **kwargs : graph parameters (``knn=5, decay=40, n_pca=100, thresh=1e-4,
+        distance='euclidean', n_jobs=1, random_state=None, verbose=1,
+        bandwidth_scale=1.0``).
+    """
+
+    def __init__(self, beta=60, offset=0, order=1, filter="heat", solver="chebyshev", chebyshev_order=50,
+                 lap_type="combinatorial", sample_normalize=True, anisotropy=1, n_landmark=None, **kwargs):
+        self.graph = None
+        self.X = None
+        self.sample_densities = None
+        self.filt = None
+        self.beta = beta
+        self.offset = offset
+        self.order = order
+        self.solver = solver
+        self.chebyshev_order = chebyshev_order
+        self.lap_type = lap_type
+        self.filter = filter
+        self.sample_normalize = sample_normalize
+
+        kwargs.pop("use_pygsp", None)
+        self.knn = kwargs.pop("knn", 5)
+        self.decay = kwargs.pop("decay", 40)
+        self.n_pca = kwargs.pop("n_pca", 100)
+        self.thresh = kwargs.pop("thresh", 1e-4)
+        self.distance = kwargs.pop("distance", "euclidean")
+        self.n_jobs = kwargs.pop("n_jobs", 1)
+        self.random_state = kwargs.pop("random_state", None)
+        self.verbose = kwargs.pop("verbose", 1)
+        self.anisotropy = anisotropy
+        self.n_landmark = n_landmark
+        self.kwargs = kwargs  # remaining graphtools.Graph keywords, checked at fit time
+        self.timings_ = {}
+
+    # ---- validated parameters (graphtools.estimator.attribute equivalents) ---------------
+    beta = property(lambda self: self._beta)
+
+    @beta.setter
+    def beta(self, v):
+        _check_positive(beta=v)
+        self._beta = v
+
+    filter = property(lambda self: self._filter)
+
+    @filter.setter
+    def filter(self, v):
+        _check_in(["heat", "laplacian"], filter=v)
+        self._filter = v
+
+    solver = property(lambda self: self._solver)
+
+    @solver.setter
+    def solver(self, v):
+        _check_in(["chebyshev", "exact"], solver=v)
+        self._solver = v
+
+    chebyshev_order = property(lambda self: self._chebyshev_order)
+
+    @chebyshev_order.setter
+    def chebyshev_order(self, v):
+        _check_int(chebyshev_order=v)
+        _check_positive(chebyshev_order=v)
+        self._chebyshev_order = v
+
+    lap_type = property(lambda self: self._lap_type)
+
+    @lap_type.setter
+    def lap_type(self, v):
+        _check_in(["combinatorial", "normalized"], lap_type=v)
+        self._lap_type = v
+
+    knn = property(lambda self: self._knn)
+
+    @knn.setter
+    def knn(self, v):
+        _check_positive(knn=v)
+        _check_int(knn=v)
+        self._knn = v
+
+    decay = property(lambda self: self._decay)
+
+    @decay.setter
+    def decay(self, v):
+        if v is not None:
+            _check_positive(decay=v)
+        self._decay = v
+
+    # ---- cache invalidation ------------------------------------------------------------------
+    def _reset_graph(self):
+        self._reset_filter()
+
+    def _reset_filter(self):
+        self.filt = None
+        self.sample_densities = None
+
+    def set_params(self, **params):
+        """Set parameters; changing a filter parameter drops the cached densities, changing a
+        graph parameter drops the graph as well (reference ``meld/meld.py:127-141``)."""
+        for p in _FILTER_PARAMS:
+            if p in params and params[p] != getattr(self, p):
+                self._reset_filter()
+                setattr(self, p, params[p])
+                del params[p]
+            elif p in params:
+                del params[p]
+        reset_graph = False
+        for p in list(params):
+            if p in _GRAPH_PARAMS:
+                cur = getattr(self, p) if hasattr(self, p) else self.kwargs.get(p)
+                if params[p] != cur:
+                    reset_graph = True
+                    if hasattr(self, p):
+                        setattr(self, p, params[p])
+                    else:
+                        self.kwargs[p] = params[p]
+                del params[p]
+            elif p in ("n_jobs", "verbose", "sample_normalize", "n_landmark"):
+                setattr(self, p, params.pop(p))
+        if params:
+            raise ValueError("Invalid parameter(s) for MELD: {}".format(sorted(params)))
+        if reset_graph:
+            self.graph = None
+            self._reset_graph()
+        return self
+
+    # ---- fit ----------------------------------------------------------------------------------
+    def _log(self, msg):
+        if self.verbose:
+            print(msg, flush=True)
+
+    def _check_supported(self, extra):
+        if self.distance != "euclidean":
+            raise NotImplementedError("distance='{}': only 'euclidean' runs on the B200 engine".format(self.distance))
+        if self.decay is None:
+            raise NotImplementedError("decay=None (unweighted kNN kernel) is not available in the B200 engine")
+        if not (self.thresh > 0):
+            raise NotImplementedError("thresh=0 selects graphtools' dense exact graph; the B200 engine needs thresh > 0")
+        if self.n_landmark is not None:
+            raise NotImplementedError("landmark graphs are not available in the B200 engine")
+        known = {"bandwidth_scale"}
+        unsupported = sorted(k for k in extra if k not in known)
+        if unsupported:
+            raise NotImplementedError("graph keyword(s) {} are not available in the B200 engine".format(unsupported))
+
+    def _reduce_data(self, X):
+        """graphtools ``Data._reduce_data``: randomised PCA when n_pca < min(X.shape) (host sklearn
+        call, shared with the oracle; SURVEY 8a row B')."""
+        n_pca = self.n_pca
+        if n_pca is None or n_pca >= min(X.shape):
+            return X
+        torch = nv.require_cuda()
+        from sklearn.decomposition import PCA
+
+        t0 = time.perf_counter()
+        self._log("Calculating PCA...")
+        Xh = X.cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(getattr(X, "values", X), dtype=np.float64)
+        self.data_pca = PCA(n_pca, svd_solver="randomized", random_state=self.random_state)
+        out = self.data_pca.fit_transform(Xh)
+        self.timings_["pca"] = time.perf_counter() - t0
+        self._log("Calculated PCA in {:.2f} seconds.".format(self.timings_["pca"]))
+        return out
+
+    def fit(self, X, **kwargs):
+        """Build the kNN alpha-decay graph on ``X`` (array-like (N, D), CUDA tensor, or a prebuilt
+        ``DeviceGraph``).  Stands in for the inherited ``GraphEstimator.fit``."""
+        torch = nv.require_cuda()
+        nv.lib()
+        if isinstance(X, DeviceGraph):
+            self.graph = X
+            self.X = None
+            self._reset_graph()
+            return self
+        if hasattr(X, "tocsr") or hasattr(X, "todense"):
+            raise NotImplementedError("sparse input is not available in the B200 engine; pass a dense matrix")
+        extra = dict(self.kwargs)
+        extra.update(kwargs)
+        if extra.pop("sample_idx", None) is not None:
+            raise NotImplementedError("sample_idx (MNN graphs) is not available in the B200 engine")
+        extra.pop("use_pygsp", None)
+        self._check_supported(extra)
+        if self.graph is not None and self.X is not None and _same_data(torch, X, self.X):
+            return self  # same data, same parameters: keep the graph (set_params drops it otherwise)
+        shape = tuple(X.shape)
+        if len(shape) != 2:
+            raise ValueError("Expected a 2D matrix. Got shape {}".format(shape))
+        self._log("Building graph on {} samples and {} features.".format(shape[0], shape[1]))
+        t0 = time.perf_counter()
+        data_nu = self._reduce_data(X)
+        self._log("Calculating graph and diffusion operator...")
+        t1 = time.perf_counter()
+        self.graph = DeviceGraph.from_data(
+            data_nu, knn=self.knn, decay=self.decay, thresh=self.thresh, anisotropy=self.anisotropy,
+            bandwidth_scale=extra.get("bandwidth_scale", 1.0),
+        )
+        self.timings_["graph"] = time.perf_counter() - t1
+        self._log("Calculated graph and diffusion operator in {:.2f} seconds.".format(time.perf_counter() - t0))
+        self.X = X
+        self._reset_graph()
+        return self
+
+    # ---- labels -----------------------------------------------------------------------------
+    def _label_codes(self, sample_labels):
+        """Sorted unique labels (``np.unique`` order) and an int32 code per cell."""
+        labels = getattr(sample_labels, "values", sample_labels)
+        labels = np.asarray(labels)
+        if labels.ndim > 1:
+            if labels.shape[1] == 1:
+                labels = labels.reshape(-1)
+            else:
+                raise ValueError("sample_labels must be a single column. Got" "shape={}".format(labels.shape))
+        codes, uniques = pd.factorize(labels)  # hash pass; np.unique would sort N strings
+        uniques = np.asarray(uniques)
+        order = np.argsort(uniques, kind="stable")
+        rank = np.empty(len(order), dtype=np.int32)
+        rank[order] = np.arange(len(order), dtype=np.int32)
+        samples = uniques[order]
+        if labels.dtype.kind in "US":
+            samples = samples.astype(labels.dtype)
+        return samples, rank[codes]
+
+    def _create_sample_indicators(self, sample_labels):
+        """One-hot indicator DataFrame, columns in ``np.unique`` order (``meld/meld.py:143-191``)."""
+        self.sample_labels_ = sample_labels
+        self.samples, codes = self._label_codes(sample_labels)
+        self._codes = codes
+        p = len(self.samples)
+        ind = np.zeros((len(codes), p), dtype=int)
+        ind[np.arange(len(codes)), codes] = 1
+        index = getattr(self, "_labels_index", None) if p == 2 else None
+        self._indicators = pd.DataFrame(ind, index=index, columns=self.samples)
+        return self._indicators
+
+    @property
+    def sample_indicators(self):
+        """Indicator DataFrame (column-normalised when ``sample_normalize``), built on first use."""
+        if getattr(self, "_indicators", None) is None and getattr(self, "_codes", None) is not None:
+            p = len(self.samples)
+            ind = np.zeros((len(self._codes), p), dtype=int)
+            ind[np.arange(len(self._codes)), self._codes] = 1
+            df = pd.DataFrame(ind, index=self._labels_index if p == 2 else None, columns=self.samples)
+            if self.sample_normalize:
+                df = df / df.sum(axis=0)
+            self._indicators = df
+        return getattr(self, "_indicators", None)
+
+    @sample_indicators.setter
+    def sample_indicators(self, value):
+        self._indicators = value
+
+    # ---- transform --------------------------------------------------------------------------
+    def transform(self, sample_labels):
+        """Filter the sample indicators of ``sample_labels`` over the graph.
+
+        Returns a DataFrame (N, p) of sample densities, columns = sorted unique labels,
+        index = ``sample_labels.index`` when it has one.
+        """
+        torch = nv.require_cuda()
+        self.graph = utils._check_pygsp_graph(self.graph)
+        self._sample_labels = sample_labels
+
+        if sample_labels.shape[0] != self.graph.N:
+            raise ValueError(
+                "Input data ({}) and input graph ({}) "
+                "are not of the same size".format(sample_labels.shape, self.graph.N)
+            )
+        flat_check = getattr(sample_labels, "values", sample_labels)
+        if np.asarray(flat_check).ndim == 1 or np.asarray(flat_check).shape[1] == 1:
+            samples, codes = self._label_codes(sample_labels)
+            n_unique = len(samples)
+        else:
+            samples, codes = None, None
+            n_unique = len(np.unique(flat_check))
+        if n_unique == 1:
+            raise ValueError("Found only one unqiue sample label. Cannot estimate density " "of a single sample.")
+
+        if hasattr(sample_labels, "index"):
+            self._labels_index = sample_labels.index
+        else:
+            self._labels_index = None
+
+        if samples is None:
+            self._create_sample_indicators(sample_labels)  # raises the single-column ValueError
+        self.sample_labels_ = sample_labels
+        self.samples, self._codes = samples, codes
+        self._indicators = None  # rebuilt lazily by the sample_indicators property
+
+        _filter.filter_kernel(self.filter, self.beta, self.offset, self.order)
+        if self.solver != "chebyshev":
+            raise NotImplementedError(
+                "solver='{}' is not available in the B200 engine; use solver='chebyshev'".format(self.solver)
+            )
+        t0 = time.perf_counter()
+        p = len(samples)
+        dev = self.graph.device
+        d_codes = torch.from_numpy(codes).to(dev, non_blocking=True)
+        S = torch.empty((len(codes), p), dtype=torch.float64, device=dev)
+        nv.check(
+            nv.lib().meld_b200_indicator_matrix(nv.ptr(d_codes), len(codes), p, int(bool(self.sample_normalize)),
+                                                nv.ptr(S), nv.current_stream_ptr()),
+            "indicator_matrix",
+        )
+        densities = _filter.filter(
+            signal=S, graph=self.graph, filter=self.filter, beta=self.beta, offset=self.offset, order=self.order,
+            solver=self.solver, chebyshev_order=self.chebyshev_order,
+        )
+        self.sample_densities_device = densities
+        host = densities.cpu().numpy()
+        self.timings_["transform"] = time.perf_counter() - t0
+        self.sample_densities = pd.DataFrame(host, index=self._labels_index, columns=self.samples)
+        return self.sample_densities
+
+    def fit_transform(self, X, sample_labels, **kwargs):
+        """Build the graph on ``X`` and estimate the density of each sample in ``sample_labels``."""
+        self.fit(X, **kwargs)
+        return self.transform(sample_labels)
+
+
+def _same_data(torch, a, b):
+    if a is b:
+        return True
+    if isinstance(a, torch.Tensor) or isinstance(b, torch.Tensor):
+        return (
+            isinstance(a, torch.Tensor)
+            and isinstance(b, torch.Tensor)
+            and a.shape == b.shape
+            and a.device == b.device
+            and bool(torch.equal(a, b))
+        )
+    try:
+        a_, b_ = np.asarray(getattr(a, "values", a)), np.asarray(getattr(b, "values", b))
+        return a_.shape == b_.shape and bool(np.array_equal(a_, b_))
+    except Exception:
+        return False

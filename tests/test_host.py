@@ -1,0 +1,116 @@
+"""CPU-side tests: host logic, the oracle-independent parts of the API contract, and that the
+C-ABI library loads and exports every symbol include/meld_b200.h declares (no compute calls)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from meld_b200 import build
+
+    return build.build(verbose=False)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "meld_b200.h")).read()
+    declared = set(re.findall(r"\b(meld_b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(built_lib)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    from meld_b200 import _native
+
+    assert set(_native.SIGNATURES) == declared
+    assert _native.lib().meld_b200_version() >= 100
+    assert _native.lib().meld_b200_last_error() is not None
+
+
+def test_cuda_sass_is_sm100a_and_uses_tma(built_lib):
+    import subprocess
+
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    assert "cheby_step_kernel" in sass
+    assert "UBLKCP" in sass  # cp.async.bulk (1-D TMA) staging of the CSR row blocks
+
+
+def test_invalid_parameters_raise_reference_messages():
+    import meld_b200 as mb
+
+    with pytest.raises(ValueError, match=re.escape(
+            "lap_type value hello world not recognized. Choose from ['combinatorial', 'normalized']")):
+        mb.MELD(verbose=0, lap_type="hello world")
+    with pytest.raises(ValueError, match="Expected beta > 0"):
+        mb.MELD(beta=-1)
+    with pytest.raises(ValueError, match="Expected chebyshev_order integer"):
+        mb.MELD(chebyshev_order=2.5)
+    with pytest.raises(ValueError, match="solver value"):
+        mb.MELD(solver="cg")
+    op = mb.MELD()
+    assert (op.beta, op.chebyshev_order, op.knn, op.decay, op.thresh, op.n_pca, op.anisotropy) == (60, 50, 5, 40, 1e-4, 100, 1)
+
+
+def test_sample_labels_2d_message():
+    import meld_b200 as mb
+
+    labels = np.ones((10, 2))
+    with pytest.raises(ValueError, match=re.escape(
+            "sample_labels must be a single column. Got" "shape={}".format(labels.shape))):
+        mb.MELD()._create_sample_indicators(labels)
+
+
+def test_label_codes_follow_np_unique_order():
+    import meld_b200 as mb
+
+    rng = np.random.default_rng(0)
+    for labels in [rng.choice(["B", "A", "C"], size=200), rng.integers(0, 5, 100), rng.choice([2.5, -1.0], 50),
+                   rng.choice(["treatment", "control"], 64).reshape(-1, 1)]:
+        samples, codes = mb.MELD()._label_codes(labels)
+        uniq, inv = np.unique(labels, return_inverse=True)
+        assert np.array_equal(samples, uniq) and samples.dtype == uniq.dtype
+        assert np.array_equal(codes, inv.reshape(-1))
+    ind = mb.MELD()._create_sample_indicators(np.array(["x", "y", "x", "z"]))
+    assert list(ind.columns) == ["x", "y", "z"] and ind.values.tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1]]
+
+
+def test_cheby_coefficients_match_oracle():
+    from meld_b200 import filter as mf
+    from oracle import cheby
+
+    for name, kw in [("heat", dict(beta=60)), ("laplacian", dict(beta=20, offset=0.1, order=2))]:
+        for m in (1, 7, 50, 64):
+            a = mf.cheby_coefficients(mf.filter_kernel(name, **kw), 0.173, m)
+            b = cheby.cheby_coeff(cheby.filter_kernel(name, **kw), 0.173, m)
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-15)
+    with pytest.raises(NotImplementedError):
+        mf.filter_kernel("gaussian", 1)
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+    import meld_b200 as mb
+    from meld_b200._native import NativeError
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(NativeError, match="no CPU fallback"):
+        mb.MELD(verbose=0).fit_transform(np.zeros((20, 3)), np.arange(20) % 2)
+    with pytest.raises(NativeError):
+        mb.normalize_densities(np.ones((4, 2)))
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "meld_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
