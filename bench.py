@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: cells/s of MELD.fit_transform on the B200 engine + SpMV roofline.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference ...                     # the reference's CPU path (oracle port)
+
+A "step" is one full pass of the hot path (kNN alpha-decay graph build -> Laplacian -> lmax ->
+Chebyshev filter of the sample indicators) over one batch of synthetic cells.  Workload at N=1:
+BASELINE.json configs[3] -- 500k cells x 100 PCA dims, knn=15, Chebyshev order 64, 4 samples --
+the configuration the metric's roofline target is quoted on; it fits one GPU.  Prints ONE JSON line
+(rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cells/sec MELD.fit_transform"
+UNIT = "cells/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c4", help="synthetic config of meld_b200.synthetic (c1..c5)")
+    ap.add_argument("--cells", type=int, default=None, help="override the number of cells")
+    ap.add_argument("--cpu-cells", type=int, default=20000, help="cells in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_inputs(args, seed_offset=0):
+    from meld_b200 import synthetic
+
+    cfg = synthetic.CONFIGS[args.config]
+    n = args.cells or cfg["N"]
+    X, labels, kw = synthetic.make_config(args.config, seed=int(args.config[1:]) + seed_offset, N=n)
+    return X, labels, kw, cfg
+
+
+def workload_name(args, cfg, n):
+    return "{}: {} cells x {} dims, {} samples, {}".format(
+        args.config, n, cfg["D"], cfg["n_samples"], ", ".join("{}={}".format(k, v) for k, v in cfg["meld"].items()) or "defaults")
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_leg(args, n_cells, n_jobs):
+    """The reference's CPU path (oracle port: same sklearn / scipy calls) on a bounded sample."""
+    from oracle import meld as omeld  # test infrastructure; allowed here as the timed CPU baseline only
+    from meld_b200 import synthetic
+
+    cfg = synthetic.CONFIGS[args.config]
+    X, labels, kw = synthetic.make_config(args.config, N=n_cells)
+    t0 = time.perf_counter()
+    dens, g, lmax = omeld.fit_transform(X, labels, n_pca=None if cfg["D"] <= 100 else 100, random_state=0,
+                                        n_jobs=n_jobs, **kw)
+    dt = time.perf_counter() - t0
+    return n_cells / dt, dt, int(g["L"].nnz)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    from meld_b200 import synthetic
+
+    cfg = synthetic.CONFIGS[args.config]
+    n_full = args.cells or cfg["N"]
+    n = min(args.cpu_cells, n_full)
+    vals = []
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_leg(args, n, cores)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, dt, nnz = cpu_reference_leg(args, n, cores)
+        vals.append((v, dt))
+    total = time.perf_counter() - t_all
+    value = n * args.steps / total
+    sample = ("oracle port of the reference CPU path (sklearn ball-tree kNN n_jobs={}, scipy CSC matvecs 1 thread) on a "
+              "{}-cell sample of the workload generator; CPU kNN cost grows ~N^2 so cells/s at the full size is lower"
+              ).format(cores, n)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, cfg, n_full), "sample_cells": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import meld_b200
+    from meld_b200 import _native as nv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = nv.lib()
+
+    # each rank owns an independent batch of cells (no data-path collective): weak scaling
+    Xh, labels, kw, cfg = make_inputs(args, seed_offset=rank)
+    n, d = Xh.shape
+    p = cfg["n_samples"]
+    m = kw.get("chebyshev_order", 50)
+    samples, codes_h = np.unique(labels, return_inverse=True)
+    X_dev = torch.from_numpy(Xh).cuda()
+    codes_dev = torch.from_numpy(codes_h.astype(np.int32)).cuda()
+    X_pin = torch.from_numpy(Xh).pin_memory()
+    X_pin_np = X_pin.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(events=None):
+        op = meld_b200.MELD(verbose=0, **kw)
+        op.profile_events = events
+        op.fit(X_dev)
+        out = op.transform_device(codes_dev, p)
+        return op, out
+
+    def step_e2e():
+        op = meld_b200.MELD(verbose=0, **kw)
+        dens = op.fit_transform(X_pin_np, labels)  # host buffers in, DataFrame (host) out
+        return op, dens
+
+    # ---- device-resident arm ("value") + live SpMV timing
+    for _ in range(args.warmup):
+        op, out = step_device()
+    barrier()
+    events = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.meld_b200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        op, out = step_device(events)
+    e1.record()
+    barrier()
+    launches = lib.meld_b200_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    nnz = op.graph.nnz
+    lmax = op.graph.lmax
+    stats = op.graph.build_stats()
+    filt_ms = [a.elapsed_time(b) for a, b, _ in events]
+    launch_us = 1e3 * float(np.mean(filt_ms)) / m  # average duration of one cheby_step launch
+    bytes_step = nnz * 12 + (n + 1) * 4 + 5 * n * p * 8
+    achieved = bytes_step / (launch_us * 1e-6) / 1e9
+
+    # ---- end-to-end arm: host (pinned) inputs, DataFrame back on the host, copies inside the timed region
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e2e = time.perf_counter()
+    f0.record()
+    for _ in range(args.steps):
+        _, dens = step_e2e()
+    f1.record()
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t_e2e))
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    value = world * n * args.steps / (ms_total * 1e-3)
+    e2e_value = world * n * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args, cfg, n), "parallelism": "replicas x{}".format(world),
+                "nnz_L": int(nnz), "nnz_per_row": nnz / n, "lmax": lmax, "candidate_cap": stats["candidate_cap"],
+                "max_candidates": stats["max_candidates"], "search_passes": stats["search_passes"],
+                "l2_note": "inputs (X {} MB, L {} MB) exceed the 126 MB L2; no explicit flush".format(
+                    Xh.nbytes // 2**20, nnz * 12 // 2**20),
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Xh.nbytes + 4 * n),
+                    "d2h_bytes_per_step": int(8 * n * p), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "cheby_step_kernel (CSR SpMM + fused three-term update)", "bound": "hbm",
+                "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "bytes_per_launch": int(bytes_step),
+                "us_per_launch": launch_us, "launches_per_step": m,
+                "filter_share_of_step": float(np.mean(filt_ms)) / (ms_total / args.steps),
+            },
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            ncpu = min(args.cpu_cells, n)
+            v, dt, _ = cpu_reference_leg(args, ncpu, cores)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "oracle port (sklearn ball-tree kNN n_jobs={}, scipy matvecs) fit_transform on a {}-cell "
+                          "sample of the same generator, {:.1f} s".format(cores, ncpu, dt),
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,11 +46,13 @@ typedef struct meld_b200_graph meld_b200_graph_t;
 /* ---- library ---------------------------------------------------------------- */
 int meld_b200_version(void);              /* major*10000 + minor*100 + patch     */
 const char *meld_b200_last_error(void);   /* thread-local, never NULL            */
+/* Kernels this library has launched so far in this process (its own, not CUB's).  */
+int64_t meld_b200_launch_count(void);
 /* sm_count / cc_major / cc_minor of the current device (host pointers).        */
 int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
 
 /* Launch-configuration knobs of the Chebyshev kernel, for bench sweeps and tests
- * only (keys: blk_chunk, stage_cap, n_stage, threads, ctas_per_sm, group,
+ * only (keys: blk_chunk, stage_cap, row_cap, n_stage, threads, ctas_per_sm, group,
  * use_graph).  Takes effect for graphs created afterwards.                       */
 int meld_b200_set_tuning(const char *key, int value);
 
@@ -70,6 +72,13 @@ int meld_b200_set_tuning(const char *key, int value);
 int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay,
                               double thresh, double anisotropy, double bandwidth_scale,
                               int flags, void *stream, meld_b200_graph_t **graph_out);
+
+/* Test hook: run only the reduced-precision candidate search of knn_graph_build and return the
+ * per-row pass-2 key (float, s-space) and candidate count; used to cross-check the tcgen05 search
+ * against the SIMT one.  Synchronous.                                            */
+int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int knn, double decay,
+                                     double thresh, double bandwidth_scale, int flags, void *stream,
+                                     float *key2_out, int32_t *cnt_out, int64_t *cap_host);
 
 /* Parity / prebuilt-graph entry (reference: MELD.fit(graph) short-circuit,
  * meld/benchmark.py:194-195): adopt a CSR Laplacian built elsewhere.  Rows

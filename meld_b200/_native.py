@@ -25,9 +25,11 @@ _pi64, _pint, _pdbl = C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_do
 SIGNATURES = {
     "meld_b200_version": (C.c_int, []),
     "meld_b200_last_error": (C.c_char_p, []),
+    "meld_b200_launch_count": (C.c_int64, []),
     "meld_b200_device_info": (C.c_int, [_pint, _pint, _pint]),
     "meld_b200_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "meld_b200_knn_graph_build": (C.c_int, [_vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _vp, C.POINTER(_vp)]),
+    "meld_b200_debug_candidate_search": (C.c_int, [_vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _pi64]),
     "meld_b200_graph_from_csr": (C.c_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "meld_b200_graph_info": (C.c_int, [_vp, _pi64, _pi64, _pi64, _pi64]),
     "meld_b200_graph_export_csr": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

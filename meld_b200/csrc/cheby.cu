@@ -70,15 +70,24 @@ struct StepArgs {
   double *R;
   double alpha, shift, gamma, c, c_cur;
   int r_acc;
-  int cap;      // entries per stage
+  int cap;      // CSR entries per stage
+  int rcap;     // row pointers per stage
   int n_stage;  // pipeline depth
 };
 
-// Gather one P-wide signal row with the widest aligned loads available.
+// Gather one P-wide signal row with the widest aligned loads available: every distinct
+// 128-byte line touched by a warp-level load costs ~2 L1 wavefront cycles, so a 32-byte row
+// must be one 256-bit request, not two 128-bit ones.
+__device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 template <int P>
 __device__ __forceinline__ void gather_row(const double *__restrict__ T, int32_t c, double (&x)[P]) {
   const double *t = T + (size_t)c * P;
-  if constexpr (P % 2 == 0) {
+  if constexpr (P % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < P; k += 4) ldg256(t + k, x[k], x[k + 1], x[k + 2], x[k + 3]);
+  } else if constexpr (P % 2 == 0) {
 #pragma unroll
     for (int k = 0; k < P; k += 2) {
       double2 v = __ldg(reinterpret_cast<const double2 *>(t + k));
@@ -91,60 +100,84 @@ __device__ __forceinline__ void gather_row(const double *__restrict__ T, int32_t
   }
 }
 
-// Rows [r0, r1) of one block; cs/vs are indexed by absolute CSR entry (already offset).
+__device__ __forceinline__ double ld_stream(const double *p) {  // read-once operand: do not keep in L1
+  double v;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(double *p, double v) {
+  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+constexpr int kUnroll = 4;  // gathers in flight per lane
+
+// Rows [r0, r1) of one block.  cs/vs are indexed by absolute CSR entry and rp by absolute
+// row (both already offset), whether they point into shared memory or global memory.
 template <int P, int G>
 __device__ __forceinline__ void process_rows(const StepArgs &a, int r0, int r1, const int32_t *cs, const double *vs,
-                                             int gid, int gl, int ngroups) {
+                                             const int32_t *rp, int gid, int gl, int ngroups) {
   for (int rb = r0; rb < r1; rb += ngroups) {  // CTA-uniform trip count (full-mask shuffles below)
     const int r = rb + gid;
     const bool act = r < r1;
     int eb = 0, ee = 0;
     if (act) {
-      eb = __ldg(a.row_ptr + r);
-      ee = __ldg(a.row_ptr + r + 1);
+      eb = rp[r];
+      ee = rp[r + 1];
+    }
+    // Epilogue operands are requested first so their DRAM latency overlaps the gathers.
+    const bool epi = act && gl < P;
+    const size_t li = (size_t)r * P + gl;
+    double tc = 0.0, told = 0.0, rold = 0.0;
+    if (epi) {
+      tc = __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
+      if (a.gamma != 0.0) told = ld_stream(a.Told + li);
+      if (a.R != nullptr && a.r_acc) rold = ld_stream(a.R + li);
     }
     double acc[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) acc[k] = 0.0;
-    int e = eb + gl;
-    for (; e + G < ee; e += 2 * G) {  // two independent gathers in flight per lane
-      const int32_t c0 = cs[e], c1 = cs[e + G];
-      const double v0 = vs[e], v1 = vs[e + G];
-      double x0[P], x1[P];
-      gather_row<P>(a.Tcur, c0, x0);
-      gather_row<P>(a.Tcur, c1, x1);
+    for (int e = eb + gl; e < ee; e += kUnroll * G) {
+      int32_t c[kUnroll];
+      double v[kUnroll];
+      double x[kUnroll][P];
 #pragma unroll
-      for (int k = 0; k < P; ++k) acc[k] = fma(v0, x0[k], acc[k]);
+      for (int u = 0; u < kUnroll; ++u) {
+        const bool in = e + u * G < ee;
+        c[u] = in ? cs[e + u * G] : 0;
+        v[u] = in ? vs[e + u * G] : 0.0;
+      }
 #pragma unroll
-      for (int k = 0; k < P; ++k) acc[k] = fma(v1, x1[k], acc[k]);
-    }
-    if (e < ee) {
-      const int32_t c0 = cs[e];
-      const double v0 = vs[e];
-      double x0[P];
-      gather_row<P>(a.Tcur, c0, x0);
+      for (int u = 0; u < kUnroll; ++u) {
+        if (e + u * G < ee) {
+          gather_row<P>(a.Tcur, c[u], x[u]);
+        } else {
 #pragma unroll
-      for (int k = 0; k < P; ++k) acc[k] = fma(v0, x0[k], acc[k]);
+          for (int k = 0; k < P; ++k) x[u][k] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc[k] = fma(v[u], x[u][k], acc[k]);
+      }
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) {
 #pragma unroll
       for (int k = 0; k < P; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     }
-    if (act && gl < P) {
+    if (epi) {
       double y = acc[0];
 #pragma unroll
       for (int k = 1; k < P; ++k)
         if (gl == k) y = acc[k];
-      const size_t li = (size_t)r * P + gl;
-      const double tc = __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
       double tn = a.alpha * (y - a.shift * tc);
-      if (a.gamma != 0.0) tn -= a.gamma * a.Told[li];
-      if (a.Tnew) a.Tnew[li] = tn;
+      if (a.gamma != 0.0) tn -= a.gamma * told;
+      if (a.Tnew) a.Tnew[li] = tn;  // re-read by the next step's gathers: keep cacheable
       if (a.R) {
         double rv = a.c * tn + a.c_cur * tc;
-        if (a.r_acc) rv += a.R[li];
-        a.R[li] = rv;
+        if (a.r_acc) rv += rold;
+        st_stream(a.R + li, rv);
       }
     }
   }
@@ -153,10 +186,11 @@ __device__ __forceinline__ void process_rows(const StepArgs &a, int r0, int r1, 
 template <int P, int G>
 __global__ void cheby_step_kernel(const StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int cap = a.cap, ns = a.n_stage;
+  const int cap = a.cap, rcap = a.rcap, ns = a.n_stage;
   double *sval = reinterpret_cast<double *>(smem_raw);
-  int32_t *scol = reinterpret_cast<int32_t *>(smem_raw + (size_t)ns * cap * sizeof(double));
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ns * cap * (sizeof(double) + sizeof(int32_t)));
+  int32_t *scol = reinterpret_cast<int32_t *>(smem_raw + (size_t)ns * cap * 8);
+  int32_t *srp = reinterpret_cast<int32_t *>(smem_raw + (size_t)ns * cap * 12);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ns * cap * 12 + (size_t)ns * rcap * 4);
 
   const int tid = threadIdx.x;
   const int ngroups = blockDim.x / G;
@@ -169,16 +203,20 @@ __global__ void cheby_step_kernel(const StepArgs a) {
   }
   __syncthreads();
 
-  // Thread 0 is the TMA producer: arm the stage barrier, then two bulk copies.
+  // Thread 0 is the TMA producer: arm the stage barrier, then three bulk copies
+  // (values, columns, row pointers), each 16-byte aligned at both ends.
   auto issue = [&](int b, int s) {
     const int r0 = __ldg(a.blk + b), r1 = __ldg(a.blk + b + 1);
     const int e0 = __ldg(a.row_ptr + r0), e1 = __ldg(a.row_ptr + r1);
-    const int a0 = e0 & ~3;                  // 16-byte aligned start for the int32 columns
+    const int a0 = e0 & ~3;                  // aligned start for the int32 columns
     const int n = ((e1 - a0) + 3) & ~3;      // multiple of 4 entries (tail lands in kCsrPad)
-    if (n > 0 && n <= cap) {
-      mbar_arrive_expect_tx(&bars[s], (uint32_t)n * 12u);
+    const int ra = r0 & ~3;
+    const int nr = ((r1 + 1 - ra) + 3) & ~3;
+    if (n > 0 && n <= cap && nr <= rcap) {
+      mbar_arrive_expect_tx(&bars[s], (uint32_t)n * 12u + (uint32_t)nr * 4u);
       bulk_g2s(sval + (size_t)s * cap, a.val + a0, (uint32_t)n * 8u, &bars[s]);
       bulk_g2s(scol + (size_t)s * cap, a.col + a0, (uint32_t)n * 4u, &bars[s]);
+      bulk_g2s(srp + (size_t)s * rcap, a.row_ptr + ra, (uint32_t)nr * 4u, &bars[s]);
     } else {
       mbar_arrive(&bars[s]);  // oversize / empty block: nothing staged, phase still advances
     }
@@ -199,11 +237,14 @@ __global__ void cheby_step_kernel(const StepArgs a) {
     const int e0 = __ldg(a.row_ptr + r0), e1 = __ldg(a.row_ptr + r1);
     const int a0 = e0 & ~3;
     const int n = ((e1 - a0) + 3) & ~3;
+    const int ra = r0 & ~3;
+    const int nr = ((r1 + 1 - ra) + 3) & ~3;
     mbar_wait(&bars[s], parity);
-    if (n <= cap) {
-      process_rows<P, G>(a, r0, r1, scol + (size_t)s * cap - a0, sval + (size_t)s * cap - a0, gid, gl, ngroups);
+    if (n <= cap && nr <= rcap) {
+      process_rows<P, G>(a, r0, r1, scol + (size_t)s * cap - a0, sval + (size_t)s * cap - a0,
+                         srp + (size_t)s * rcap - ra, gid, gl, ngroups);
     } else {
-      process_rows<P, G>(a, r0, r1, a.col, a.val, gid, gl, ngroups);  // row block too long for a stage
+      process_rows<P, G>(a, r0, r1, a.col, a.val, a.row_ptr, gid, gl, ngroups);  // block too long for a stage
     }
     __syncthreads();  // every lane is done reading stage s before it is refilled
     if (tid == 0) {
@@ -264,10 +305,11 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, cudaStream_t
   a.n_blk = g->n_blk;
   a.row0 = g->row0;
   a.cap = t.stage_cap;
+  a.rcap = t.row_cap;
   a.n_stage = t.n_stage;
-  const size_t smem = (size_t)t.n_stage * t.stage_cap * 12 + (size_t)t.n_stage * 8;
+  const size_t smem = (size_t)t.n_stage * ((size_t)t.stage_cap * 12 + (size_t)t.row_cap * 4 + 8);
   MELD_REQUIRE(smem <= 227 * 1024, "cheby_step: %zu bytes of shared memory requested", smem);
-  MELD_REQUIRE(t.threads % 32 == 0 && t.threads >= 32 && t.threads <= 1024 && t.stage_cap % 16 == 0,
+  MELD_REQUIRE(t.threads % 32 == 0 && t.threads >= 32 && t.threads <= 1024 && t.stage_cap % 16 == 0 && t.row_cap % 16 == 0,
                "cheby_step: bad tuning");
   MELD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count() * t.ctas_per_sm;

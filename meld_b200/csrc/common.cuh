@@ -37,7 +37,14 @@ void set_error(const char *fmt, ...);
     }                                  \
   } while (0)
 
-#define MELD_LAUNCH_CHECK() MELD_CUDA(cudaGetLastError())
+// Every kernel launch of this library goes through MELD_LAUNCH_CHECK, which also counts it
+// (meld_b200_launch_count; bench.py reports the count as "gpu_launches").
+extern long long g_launches;
+#define MELD_LAUNCH_CHECK()          \
+  do {                               \
+    ++meld::g_launches;              \
+    MELD_CUDA(cudaGetLastError());   \
+  } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
@@ -49,9 +56,10 @@ int sm_count();
 struct Tuning {
   int blk_chunk = 1536;   // target CSR entries per row block (C)
   int stage_cap = 2048;   // entries of shared memory per pipeline stage
+  int row_cap = 512;      // row pointers of shared memory per pipeline stage
   int n_stage = 3;        // TMA pipeline depth per CTA
-  int threads = 128;      // threads per CTA
-  int ctas_per_sm = 3;    // persistent CTAs per SM
+  int threads = 256;      // threads per CTA
+  int ctas_per_sm = 2;    // persistent CTAs per SM
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)
   int use_graph = 1;      // capture the m-step recurrence in a CUDA graph
 };
@@ -106,11 +114,11 @@ struct meld_b200_graph {
   int32_t max_row_nnz = 0;
   // Chebyshev / Lanczos workspace, grown on demand.
   meld::DevBuf<double> work;
-  // Un-symmetrised kNN kernel kept for export (padded rows), optional.
-  meld::DevBuf<int32_t> knn_cnt;   // n
-  meld::DevBuf<int32_t> knn_col;   // n * knn_cap
-  meld::DevBuf<double> knn_val;    // n * knn_cap
-  int32_t knn_cap = 0;
+  // Un-symmetrised kNN kernel kept for export (compact CSR, slot order), optional.
+  meld::DevBuf<int64_t> knn_ptr;   // n + 1
+  meld::DevBuf<int32_t> knn_cnt;   // n + 1
+  meld::DevBuf<int32_t> knn_col;   // knn_nnz
+  meld::DevBuf<double> knn_val;    // knn_nnz
   int64_t knn_nnz = -1;
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };

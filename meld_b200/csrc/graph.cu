@@ -7,6 +7,7 @@
 namespace meld {
 
 static thread_local char g_err[1024] = "";
+long long g_launches = 0;
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -97,6 +98,8 @@ extern "C" {
 
 int meld_b200_version(void) { return 100; /* 0.1.0 */ }
 
+int64_t meld_b200_launch_count(void) { return (int64_t)g_launches; }
+
 const char *meld_b200_last_error(void) { return g_err; }
 
 int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host) {
@@ -117,6 +120,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   Tuning &t = tuning();
   if (!strcmp(key, "blk_chunk")) t.blk_chunk = value;
   else if (!strcmp(key, "stage_cap")) t.stage_cap = value;
+  else if (!strcmp(key, "row_cap")) t.row_cap = value;
   else if (!strcmp(key, "n_stage")) t.n_stage = value;
   else if (!strcmp(key, "threads")) t.threads = value;
   else if (!strcmp(key, "ctas_per_sm")) t.ctas_per_sm = value;
@@ -155,11 +159,12 @@ int meld_b200_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t row0, int64
     delete g;
     return code;
   };
-  if ((rc = g->row_ptr.alloc((size_t)n_rows + 1))) return fail(rc);
+  if ((rc = g->row_ptr.alloc((size_t)n_rows + 1 + kCsrPad))) return fail(rc);
   if ((rc = g->col.alloc((size_t)nnz + kCsrPad))) return fail(rc);
   if ((rc = g->val.alloc((size_t)nnz + kCsrPad))) return fail(rc);
   indptr64_to_32_kernel<<<(unsigned)ceil_div(n_rows + 1, 256), 256, 0, stream>>>(indptr, n_rows + 1, g->row_ptr.p);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->row_ptr.p + n_rows + 1, 0, kCsrPad * sizeof(int32_t), stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(g->col.p + nnz, 0, kCsrPad * sizeof(int32_t), stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(g->val.p + nnz, 0, kCsrPad * sizeof(double), stream);
   if (e == cudaSuccess && nnz > 0)

@@ -1,14 +1,640 @@
-// placeholder
+// kNN alpha-decay graph build on the device (SURVEY 8a rows C..F).
+//
+// What the reference computes (graphtools 1.5.x kNNGraph.build_kernel_to_data +
+// BaseGraph.symmetrize_kernel / apply_anisotropy + PyGSPGraph + pygsp compute_laplacian,
+// reached from MELD.fit, reference meld/meld.py:117-118,273):
+//   eps_i = distance to the knn-th non-self neighbour (x bandwidth_scale, floored at eps)
+//   K_ij  = exp(-(d_ij/eps_i)^decay) for every j with K_ij >= thresh   (K_ii = 1)
+//   K     = (K + K^T)/2 ;  q = K 1 ;  K_ij /= (q_i q_j)^anisotropy
+//   W     = K - diag(K) ;  L = diag(W 1) - W
+//
+// How it is computed here:
+//   1. candidate search in reduced precision (tcgen05 bf16-split GEMM, or the SIMT fp32
+//      cross-check): pass 1 finds an upper bound of eps_i^2, pass 2 emits every j whose
+//      approximate distance is inside the kernel radius plus a rigorous error margin, so
+//      the candidate set is a superset of the exact neighbourhood;
+//   2. exact float64 distances for the candidates only, summed in the same order as
+//      scikit-learn's ball tree (sequential over features, no FMA) -> exact eps_i;
+//   3. K_ij and K_ji both follow from d_ij (= d_ji bit for bit), eps_i and eps_j, so the
+//      symmetrised value needs no transpose lookup; entries whose reverse edge is missing
+//      are appended to the other row;
+//   4. rows sorted by column (CUB segmented sort), then anisotropy + Laplacian in place.
 #include "common.cuh"
+#include "knn_search.cuh"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
+#include <float.h>
+#include <math.h>
+
+namespace meld {
+
+// ---- 0. preparation: column means, centred norms -------------------------------------------
+constexpr int kMeanBlocks = 128;
+
+__global__ void col_partial_sums_kernel(const double *__restrict__ X, int64_t n, int64_t d, double *partial) {
+  // block b sums rows b, b + gridDim.x, ... ; thread t handles columns t, t + blockDim.x, ...
+  for (int64_t k = threadIdx.x; k < d; k += blockDim.x) {
+    double s = 0.0;
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) s += X[i * d + k];
+    partial[(int64_t)blockIdx.x * d + k] = s;
+  }
+}
+
+__global__ void col_mean_kernel(const double *__restrict__ partial, int64_t n, int64_t d, int nblocks, double *mu) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * d + k];
+  mu[k] = s / (double)n;
+}
+
+// one warp per row: n_i = |x_i - mu|^2 (float64) and the running maximum over rows
+__global__ void row_norms_kernel(const double *__restrict__ X, const double *__restrict__ mu, int64_t n, int64_t d,
+                                 double *__restrict__ norm, unsigned long long *ymax2_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    double s = 0.0;
+    for (int64_t k = lane; k < d; k += 32) {
+      const double v = X[i * d + k] - mu[k];
+      s = fma(v, v, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      norm[i] = s;
+      atomicMax(ymax2_bits, (unsigned long long)__double_as_longlong(s));  // s >= 0: bit order = value order
+    }
+  }
+}
+
+// ---- 1b. merge the per-(row, list) top-k1 lists of pass 1 into the emit threshold of pass 2 ----
+// lists: [n][nlists][k1] floats sorted descending in s-space (s = x.y - n_j/2, larger = closer).
+__global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t n, int nlists, int k1,
+                                   const double *__restrict__ norm, const unsigned long long *ymax2_bits,
+                                   double margin_c, double radius_factor, float *__restrict__ key2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *base = lists + (size_t)i * nlists * k1;
+  int idx[kMaxLists];
+  for (int l = 0; l < nlists; ++l) idx[l] = 0;
+  float sk = -INFINITY;
+  for (int t = 0; t < k1; ++t) {  // t-th largest of the union
+    float best = -INFINITY;
+    int bl = 0;
+    for (int l = 0; l < nlists; ++l) {
+      const float v = idx[l] < k1 ? base[l * k1 + idx[l]] : -INFINITY;
+      if (v > best) {
+        best = v;
+        bl = l;
+      }
+    }
+    idx[bl]++;
+    sk = best;
+  }
+  const double ni = norm[i];
+  const double ymax2 = __longlong_as_double((long long)*ymax2_bits);
+  const double m = margin_c * (ni + ymax2);
+  double tau = ni - 2.0 * (double)sk;  // approximate k1-th smallest squared distance
+  if (!(tau > 0.0)) tau = 0.0;
+  if (!isfinite((double)sk)) tau = INFINITY;  // fewer than k1 columns seen: keep everything
+  const double t2 = radius_factor * (tau + m) + m;  // emit radius^2, error margins on both sides
+  // emit iff s >= (n_i - t2)/2 ; round the key down so float rounding cannot drop a candidate
+  double key = 0.5 * (ni - t2);
+  float kf = (float)key;
+  if ((double)kf > key) kf = nextafterf(kf, -INFINITY);
+  key2[i] = isfinite(tau) ? kf : -INFINITY;
+}
+
+// ---- 2. exact float64 distances of the candidates, eps_i ----------------------------------------
+// One warp per row.  d2buf[i*cap + t] receives the exact squared distance of candidate t.
+__global__ void refine_dist_kernel(const double *__restrict__ X, int64_t n, int64_t d, const int32_t *__restrict__ cand,
+                                   const int32_t *__restrict__ cnt, int cap, int k1, double bandwidth_scale,
+                                   double *__restrict__ d2buf, double *__restrict__ eps, int *__restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int c = min(cnt[i], cap);
+    const int32_t *ci = cand + (size_t)i * cap;
+    double *di = d2buf + (size_t)i * cap;
+    const double *xi = X + i * d;
+    for (int t = lane; t < c; t += 32) {
+      const double *xj = X + (int64_t)ci[t] * d;
+      double acc = 0.0;
+      for (int64_t k = 0; k < d; ++k) {  // sequential, unfused: the ball tree's rdist order
+        const double diff = __dsub_rn(xi[k], xj[k]);
+        acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      }
+      di[t] = acc;
+    }
+    __syncwarp();
+    if (c < k1) {
+      if (lane == 0) atomicExch(err_flag, 1);
+      continue;
+    }
+    // k1-th smallest (value, slot) by repeated extraction of the next minimum
+    double last_v = -1.0;
+    int last_t = -1;
+    for (int s = 0; s < k1; ++s) {
+      double best_v = INFINITY;
+      int best_t = 0x7fffffff;
+      for (int t = lane; t < c; t += 32) {
+        const double v = di[t];
+        const bool after = (v > last_v) || (v == last_v && t > last_t);
+        if (after && (v < best_v || (v == best_v && t < best_t))) {
+          best_v = v;
+          best_t = t;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+        if (ov < best_v || (ov == best_v && ot < best_t)) {
+          best_v = ov;
+          best_t = ot;
+        }
+      }
+      last_v = best_v;
+      last_t = best_t;
+    }
+    if (lane == 0) {
+      double e = sqrt(last_v) * bandwidth_scale;
+      eps[i] = e > DBL_EPSILON ? e : DBL_EPSILON;
+    }
+  }
+}
+
+__device__ __forceinline__ double alpha_decay(double dist, double eps, double decay) {
+  double v = exp(-pow(dist / eps, decay));
+  if (isnan(v)) v = 1.0;
+  return v;
+}
+
+// ---- 3. kernel values, symmetrisation bookkeeping --------------------------------------------------
+// Per candidate slot: if K_ij >= thresh the slot is kept with value (K_ij + K_ji)/2 (K_ji zeroed
+// below thresh).  When K_ji is zero the mirrored entry (j, i) does not exist in row j's own list and
+// must be appended there: the slot is flagged (column stored as ~j) and extra[j] is bumped.
+// kraw (optional) keeps the un-symmetrised K_ij for export.
+__global__ void kernel_values_kernel(int64_t n, int32_t *__restrict__ cand, const int32_t *__restrict__ cnt, int cap,
+                                     double *__restrict__ d2buf, const double *__restrict__ eps, double decay,
+                                     double thresh, int32_t *__restrict__ kept, int32_t *__restrict__ extra,
+                                     double *__restrict__ kraw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int c = min(cnt[i], cap);
+    int32_t *ci = cand + (size_t)i * cap;
+    double *di = d2buf + (size_t)i * cap;
+    const double ei = eps[i];
+    int nk = 0;
+    for (int t = lane; t < c; t += 32) {
+      const int32_t j = ci[t];
+      const double dist = sqrt(di[t]);
+      const double kij = alpha_decay(dist, ei, decay);
+      if (kij >= thresh) {
+        double kji = (j == (int32_t)i) ? kij : alpha_decay(dist, eps[j], decay);
+        if (kji < thresh) kji = 0.0;
+        di[t] = (kij + kji) / 2;
+        if (kraw) kraw[(size_t)i * cap + t] = kij;
+        if (kji == 0.0) {
+          ci[t] = ~j;
+          atomicAdd(extra + j, 1);
+        }
+        ++nk;
+      } else {
+        ci[t] = INT32_MIN;  // dead slot
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) nk += __shfl_xor_sync(0xffffffffu, nk, o);
+    if (lane == 0) kept[i] = nk;
+  }
+}
+
+__global__ void add_counts_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t n,
+                                  int32_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + (b ? b[i] : 0);
+  if (i == n) out[i] = 0;
+}
+
+// Scatter the kept slots into the CSR rows: own entries first (compacted in slot order), mirrored
+// entries of flagged slots appended behind row j's own entries through an atomic cursor.
+__global__ void fill_sym_kernel(int64_t n, const int32_t *__restrict__ cand, const int32_t *__restrict__ cnt, int cap,
+                                const double *__restrict__ vbuf, const int32_t *__restrict__ row_ptr,
+                                const int32_t *__restrict__ kept, int32_t *__restrict__ cursor,
+                                int32_t *__restrict__ col, double *__restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int c = min(cnt[i], cap);
+    const int32_t *ci = cand + (size_t)i * cap;
+    const double *vi = vbuf + (size_t)i * cap;
+    int base = row_ptr[i];
+    for (int t0 = 0; t0 < c; t0 += 32) {
+      const int t = t0 + lane;
+      int32_t j = INT32_MIN;
+      double v = 0.0;
+      if (t < c) {
+        j = ci[t];
+        v = vi[t];
+      }
+      const bool live = j != INT32_MIN;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        const bool flagged = j < 0;
+        const int32_t jj = flagged ? ~j : j;
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        col[pos] = jj;
+        val[pos] = v;
+        if (flagged) {
+          const int p2 = row_ptr[jj] + kept[jj] + atomicAdd(cursor + jj, 1);
+          col[p2] = (int32_t)i;
+          val[p2] = v;
+        }
+      }
+      base += __popc(m);
+    }
+  }
+}
+
+// Compact the un-symmetrised kernel (slot order -> sorted later on the host side of the test).
+__global__ void fill_raw_kernel(int64_t n, const int32_t *__restrict__ cand, const int32_t *__restrict__ cnt, int cap,
+                                const double *__restrict__ kraw, const int64_t *__restrict__ out_ptr,
+                                int32_t *__restrict__ col, double *__restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int c = min(cnt[i], cap);
+    int64_t base = out_ptr[i];
+    for (int t0 = 0; t0 < c; t0 += 32) {
+      const int t = t0 + lane;
+      int32_t j = INT32_MIN;
+      if (t < c) j = cand[(size_t)i * cap + t];
+      const bool live = j != INT32_MIN;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        const int64_t pos = base + __popc(m & ((1u << lane) - 1u));
+        col[pos] = j < 0 ? ~j : j;
+        val[pos] = kraw[(size_t)i * cap + t];
+      }
+      base += __popc(m);
+    }
+  }
+}
+
+// ---- 4. anisotropy and Laplacian (rows sorted by column) ------------------------------------------
+__global__ void row_sum_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const double *__restrict__ val,
+                               double *__restrict__ q) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    double s = 0.0;
+    for (int e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) s += val[e];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) q[i] = s;
+  }
+}
+
+// K_ij <- K_ij (q_i q_j)^-a off the diagonal; L_ij = -K_ij; L_ii = sum_j K_ij (j != i)
+__global__ void laplacian_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                 double *__restrict__ val, const double *__restrict__ q, double anisotropy) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const double qi = q[i];
+    double dw = 0.0;
+    int diag = -1;
+    for (int e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
+      const int32_t j = col[e];
+      if (j == (int32_t)i) {
+        diag = e;
+        continue;
+      }
+      double w = val[e];
+      if (anisotropy != 0.0) {
+        const double qq = qi * q[j];
+        w = (anisotropy == 1.0 ? 1.0 / qq : pow(qq, -anisotropy)) * w;
+      }
+      val[e] = -w;
+      dw += w;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      dw += __shfl_xor_sync(0xffffffffu, dw, o);
+      diag = max(diag, __shfl_xor_sync(0xffffffffu, diag, o));
+    }
+    if (lane == 0 && diag >= 0) val[diag] = dw;
+  }
+}
+
+__global__ void max_count_kernel(const int32_t *__restrict__ cnt, int64_t n, int cap, int32_t *out2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t m = 0, over = 0;
+  for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    m = max(m, cnt[i]);
+    over += cnt[i] > cap ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    over += __shfl_xor_sync(0xffffffffu, over, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out2, m);
+    if (over) atomicAdd(out2 + 1, over);
+  }
+}
+
+static int warp_grid(int64_t n_rows, int threads) {
+  const int64_t warps_per_block = threads / 32;
+  int64_t b = ceil_div(n_rows, warps_per_block);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace meld
+
 using namespace meld;
+
+// Steps 0 and 1: centred norms, pass 1 (eps upper bounds), pass 2 (candidate lists).
+static int candidate_search(const double *X, int64_t n, int64_t d, int k1, double radius_factor, bool simt,
+                            cudaStream_t stream, DevBuf<float> &key2, DevBuf<int32_t> &cand, DevBuf<int32_t> &cnt,
+                            int64_t &cap, int &passes, int64_t &overflow_rows, int32_t (&h_max)[2]) {
+  // -- 0. means / norms
+  DevBuf<double> partial, mu, norm;
+  DevBuf<unsigned long long> ymax2;
+  MELD_CHECK(partial.alloc((size_t)kMeanBlocks * d));
+  MELD_CHECK(mu.alloc((size_t)d));
+  MELD_CHECK(norm.alloc((size_t)n));
+  MELD_CHECK(ymax2.alloc(1));
+  MELD_CUDA(cudaMemsetAsync(ymax2.p, 0, sizeof(unsigned long long), stream));
+  col_partial_sums_kernel<<<kMeanBlocks, 256, 0, stream>>>(X, n, d, partial.p);
+  MELD_LAUNCH_CHECK();
+  col_mean_kernel<<<(unsigned)ceil_div(d, 256), 256, 0, stream>>>(partial.p, n, d, kMeanBlocks, mu.p);
+  MELD_LAUNCH_CHECK();
+  row_norms_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(X, mu.p, n, d, norm.p, ymax2.p);
+  MELD_LAUNCH_CHECK();
+
+  // -- 1. candidate search
+  SearchPlan plan;
+  MELD_CHECK(search_plan(simt, n, d, k1, &plan));
+  SearchState st;
+  MELD_CHECK(search_prepare(plan, X, mu.p, norm.p, stream, &st));
+  DevBuf<float> lists;
+  MELD_CHECK(lists.alloc((size_t)n * plan.nlists * k1));
+  MELD_CHECK(key2.alloc((size_t)n));
+  MELD_CHECK(search_pass1(plan, st, lists.p, stream));
+  merge_lists_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(lists.p, n, plan.nlists, k1, norm.p, ymax2.p,
+                                                                      plan.margin_c, radius_factor, key2.p);
+  MELD_LAUNCH_CHECK();
+  lists.release();
+
+  // candidate capacity per row: generous (memory is cheap), retried with the exact maximum on overflow
+  cap = k1 <= 8 ? 256 : 512;
+  while (cap * 12 * n > (int64_t)24e9 && cap > 64) cap /= 2;
+  if (cap > round_up(n, 32)) cap = round_up(n, 32);
+  DevBuf<int32_t> maxcnt;
+  MELD_CHECK(cnt.alloc((size_t)n));
+  MELD_CHECK(maxcnt.alloc(2));
+  passes = 1;
+  overflow_rows = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    MELD_CHECK(cand.alloc((size_t)n * cap));
+    MELD_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)n * sizeof(int32_t), stream));
+    MELD_CUDA(cudaMemsetAsync(maxcnt.p, 0, 2 * sizeof(int32_t), stream));
+    MELD_CHECK(search_pass2(plan, st, key2.p, cand.p, cnt.p, (int)cap, stream));
+    ++passes;
+    max_count_kernel<<<296, 256, 0, stream>>>(cnt.p, n, (int)cap, maxcnt.p);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaMemcpyAsync(h_max, maxcnt.p, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));
+    if (h_max[0] <= cap) break;
+    if (attempt == 1) {
+      set_error("knn_graph_build: candidate overflow persisted (max %d > cap %lld)", h_max[0], (long long)cap);
+      return MELD_B200_ERR_INTERNAL;
+    }
+    overflow_rows = h_max[1];
+    cap = round_up(h_max[0], 32);
+  }
+  search_release(&st);
+  return 0;
+}
+
+
 extern "C" {
+
 int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay, double thresh,
-                              double anisotropy, double bandwidth_scale, int flags, void *stream,
+                              double anisotropy, double bandwidth_scale, int flags, void *stream_,
                               meld_b200_graph_t **graph_out) {
-  set_error("knn_graph_build: not built yet");
-  return MELD_B200_ERR_UNSUPPORTED;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(graph_out != nullptr, "knn_graph_build: graph_out is NULL");
+  *graph_out = nullptr;
+  MELD_REQUIRE(X != nullptr && n >= 2 && d >= 1, "knn_graph_build: bad data shape (%lld, %lld)", (long long)n,
+               (long long)d);
+  MELD_REQUIRE(n < (int64_t)2000000000, "knn_graph_build: n too large for int32 columns");
+  MELD_REQUIRE(knn >= 1 && (int64_t)knn + 1 <= n, "knn_graph_build: knn=%d with n=%lld", knn, (long long)n);
+  MELD_REQUIRE(knn + 1 <= kMaxK1, "knn_graph_build: knn + 1 = %d exceeds the engine limit %d", knn + 1, kMaxK1);
+  MELD_REQUIRE(decay > 0 && isfinite(decay), "knn_graph_build: decay=%g (decay=None is not supported)", decay);
+  MELD_REQUIRE(thresh > 0 && thresh < 1, "knn_graph_build: thresh=%g outside (0, 1)", thresh);
+  MELD_REQUIRE(anisotropy >= 0 && anisotropy <= 1, "knn_graph_build: anisotropy=%g outside [0, 1]", anisotropy);
+  MELD_REQUIRE(bandwidth_scale > 0, "knn_graph_build: bandwidth_scale=%g", bandwidth_scale);
+  const int k1 = knn + 1;
+  const double thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
+  const double rho = pow(-log(thresh_eff), 1.0 / decay);  // kernel radius in units of eps_i
+  double radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
+  if (radius_factor < 1.0) radius_factor = 1.0;  // the k1 nearest must be candidates to get eps_i
+  const bool simt = (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0;
+  const bool keep_raw = (flags & MELD_B200_FLAG_KEEP_KNN_KERNEL) != 0;
+
+  // -- 0./1. means, norms, candidate search
+  DevBuf<float> key2;
+  DevBuf<int32_t> cand, cnt;
+  int64_t cap = 0, overflow_rows = 0;
+  int passes = 0;
+  int32_t h_max[2] = {0, 0};
+  MELD_CHECK(candidate_search(X, n, d, k1, radius_factor, simt, stream, key2, cand, cnt, cap, passes, overflow_rows,
+                              h_max));
+  key2.release();
+
+  // -- 2. exact distances, eps
+  DevBuf<double> vbuf, eps, kraw;
+  DevBuf<int> err;
+  MELD_CHECK(vbuf.alloc((size_t)n * cap));
+  MELD_CHECK(eps.alloc((size_t)n));
+  MELD_CHECK(err.alloc(1));
+  MELD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
+  refine_dist_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(X, n, d, cand.p, cnt.p, (int)cap, k1, bandwidth_scale,
+                                                            vbuf.p, eps.p, err.p);
+  MELD_LAUNCH_CHECK();
+
+  // -- 3. kernel values + symmetrisation
+  DevBuf<int32_t> kept, extra, total;
+  MELD_CHECK(kept.alloc((size_t)n));
+  MELD_CHECK(extra.alloc((size_t)n));
+  MELD_CHECK(total.alloc((size_t)n + 1));
+  MELD_CUDA(cudaMemsetAsync(extra.p, 0, (size_t)n * sizeof(int32_t), stream));
+  if (keep_raw) MELD_CHECK(kraw.alloc((size_t)n * cap));
+  kernel_values_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cnt.p, (int)cap, vbuf.p, eps.p, decay,
+                                                              thresh_eff, kept.p, extra.p, keep_raw ? kraw.p : nullptr);
+  MELD_LAUNCH_CHECK();
+  add_counts_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(kept.p, extra.p, n, total.p);
+  MELD_LAUNCH_CHECK();
+
+  meld_b200_graph *g = new (std::nothrow) meld_b200_graph();
+  if (!g) {
+    set_error("knn_graph_build: host allocation failed");
+    return MELD_B200_ERR_NOMEM;
+  }
+  struct Guard {
+    meld_b200_graph *g;
+    ~Guard() { delete g; }
+  } guard{g};
+  g->n_rows = g->n_cols = n;
+  g->row0 = 0;
+  MELD_CHECK(g->row_ptr.alloc((size_t)n + 1 + kCsrPad));
+  MELD_CUDA(cudaMemsetAsync(g->row_ptr.p + n + 1, 0, kCsrPad * sizeof(int32_t), stream));
+  {
+    size_t tmp_bytes = 0;
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, total.p, g->row_ptr.p, (int)(n + 1), stream));
+    DevBuf<unsigned char> tmp;
+    MELD_CHECK(tmp.alloc(tmp_bytes));
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, total.p, g->row_ptr.p, (int)(n + 1), stream));
+    int32_t h_nnz = 0;
+    int h_err = 0;
+    MELD_CUDA(cudaMemcpyAsync(&h_nnz, g->row_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));
+    if (h_err) {
+      set_error("knn_graph_build: a row has fewer than knn+1 candidates (candidate search failed)");
+      return MELD_B200_ERR_INTERNAL;
+    }
+    if (h_nnz < 0) {
+      set_error("knn_graph_build: nnz overflows int32");
+      return MELD_B200_ERR_UNSUPPORTED;
+    }
+    g->nnz = h_nnz;
+  }
+  {
+    DevBuf<int32_t> ucol, cursor;
+    DevBuf<double> uval;
+    MELD_CHECK(ucol.alloc((size_t)g->nnz));
+    MELD_CHECK(uval.alloc((size_t)g->nnz));
+    MELD_CHECK(cursor.alloc((size_t)n));
+    MELD_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)n * sizeof(int32_t), stream));
+    fill_sym_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cnt.p, (int)cap, vbuf.p, g->row_ptr.p, kept.p,
+                                                           cursor.p, ucol.p, uval.p);
+    MELD_LAUNCH_CHECK();
+    MELD_CHECK(g->col.alloc((size_t)g->nnz + kCsrPad));
+    MELD_CHECK(g->val.alloc((size_t)g->nnz + kCsrPad));
+    MELD_CUDA(cudaMemsetAsync(g->col.p + g->nnz, 0, kCsrPad * sizeof(int32_t), stream));
+    MELD_CUDA(cudaMemsetAsync(g->val.p + g->nnz, 0, kCsrPad * sizeof(double), stream));
+    size_t tmp_bytes = 0;
+    MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p, (int)g->nnz,
+                                                  (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
+    DevBuf<unsigned char> tmp;
+    MELD_CHECK(tmp.alloc(tmp_bytes));
+    MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp.p, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p, (int)g->nnz,
+                                                  (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
+  }
+
+  // optional export copy of the un-symmetrised kernel
+  if (keep_raw) {
+    DevBuf<int64_t> rp64;
+    MELD_CHECK(rp64.alloc((size_t)n + 1));
+    MELD_CHECK(g->knn_cnt.alloc((size_t)n + 1));
+    add_counts_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(kept.p, nullptr, n, g->knn_cnt.p);
+    MELD_LAUNCH_CHECK();
+    size_t tmp_bytes = 0;
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, g->knn_cnt.p, rp64.p, (int)(n + 1), stream));
+    DevBuf<unsigned char> tmp;
+    MELD_CHECK(tmp.alloc(tmp_bytes));
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, g->knn_cnt.p, rp64.p, (int)(n + 1), stream));
+    int64_t h_raw = 0;
+    MELD_CUDA(cudaMemcpyAsync(&h_raw, rp64.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));
+    g->knn_nnz = h_raw;
+    MELD_CHECK(g->knn_col.alloc((size_t)h_raw));
+    MELD_CHECK(g->knn_val.alloc((size_t)h_raw));
+    MELD_CHECK(g->knn_ptr.alloc((size_t)n + 1));
+    MELD_CUDA(cudaMemcpyAsync(g->knn_ptr.p, rp64.p, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+    fill_raw_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cnt.p, (int)cap, kraw.p, g->knn_ptr.p,
+                                                           g->knn_col.p, g->knn_val.p);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // -- 4. anisotropy + Laplacian
+  {
+    DevBuf<double> q;
+    MELD_CHECK(q.alloc((size_t)n));
+    row_sum_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(n, g->row_ptr.p, g->val.p, q.p);
+    MELD_LAUNCH_CHECK();
+    laplacian_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(n, g->row_ptr.p, g->col.p, g->val.p, q.p, anisotropy);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaStreamSynchronize(stream));
+  }
+  MELD_CHECK(graph_finalize(g, stream));
+  g->stats[0] = passes;
+  g->stats[1] = h_max[0];
+  g->stats[2] = cap;
+  g->stats[3] = overflow_rows;
+  g->stats[4] = simt ? 1 : 0;
+  guard.g = nullptr;
+  *graph_out = g;
+  return 0;
 }
-int meld_b200_graph_knn_kernel_nnz(const meld_b200_graph_t *g, int64_t *nnz_host) { return MELD_B200_ERR_UNSUPPORTED; }
+
+int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int knn, double decay, double thresh,
+                                     double bandwidth_scale, int flags, void *stream_, float *key2_out,
+                                     int32_t *cnt_out, int64_t *cap_host) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(X && key2_out && cnt_out && n >= 2 && d >= 1 && knn >= 1 && knn + 1 <= n && knn + 1 <= kMaxK1,
+               "debug_candidate_search: bad argument");
+  const double thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
+  const double rho = pow(-log(thresh_eff), 1.0 / decay);
+  double radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
+  if (radius_factor < 1.0) radius_factor = 1.0;
+  DevBuf<float> key2;
+  DevBuf<int32_t> cand, cnt;
+  int64_t cap = 0, overflow_rows = 0;
+  int passes = 0;
+  int32_t h_max[2] = {0, 0};
+  MELD_CHECK(candidate_search(X, n, d, knn + 1, radius_factor, (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0, stream, key2,
+                              cand, cnt, cap, passes, overflow_rows, h_max));
+  MELD_CUDA(cudaMemcpyAsync(key2_out, key2.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  MELD_CUDA(cudaMemcpyAsync(cnt_out, cnt.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  MELD_CUDA(cudaStreamSynchronize(stream));
+  if (cap_host) *cap_host = cap;
+  return 0;
+}
+
+int meld_b200_graph_knn_kernel_nnz(const meld_b200_graph_t *g, int64_t *nnz_host) {
+  MELD_REQUIRE(g && nnz_host, "graph_knn_kernel_nnz: NULL argument");
+  MELD_REQUIRE(g->knn_nnz >= 0, "graph_knn_kernel_nnz: graph was built without MELD_B200_FLAG_KEEP_KNN_KERNEL");
+  *nnz_host = g->knn_nnz;
+  return 0;
+}
+
 int meld_b200_graph_export_knn_kernel(const meld_b200_graph_t *g, int64_t *indptr, int32_t *indices, double *data,
-                                      void *stream) { return MELD_B200_ERR_UNSUPPORTED; }
+                                      void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(g && indptr && indices && data, "graph_export_knn_kernel: NULL argument");
+  MELD_REQUIRE(g->knn_nnz >= 0, "graph_export_knn_kernel: graph was built without MELD_B200_FLAG_KEEP_KNN_KERNEL");
+  MELD_CUDA(cudaMemcpyAsync(indptr, g->knn_ptr.p, ((size_t)g->n_rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice,
+                            stream));
+  if (g->knn_nnz > 0) {
+    MELD_CUDA(cudaMemcpyAsync(indices, g->knn_col.p, (size_t)g->knn_nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                              stream));
+    MELD_CUDA(cudaMemcpyAsync(data, g->knn_val.p, (size_t)g->knn_nnz * sizeof(double), cudaMemcpyDeviceToDevice,
+                              stream));
+  }
+  return 0;
 }
+
+}  // extern "C"

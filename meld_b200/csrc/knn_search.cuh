@@ -1,0 +1,56 @@
+// Candidate search interface shared by the tcgen05 and the SIMT implementations (knn.cu drives it).
+//
+// Both work in "s-space": s_ij = x_i . x_j - n_j / 2 on centred data (n_j = |x_j|^2), so that
+// d_ij^2 = n_i - 2 s_ij and a larger s means a closer neighbour.
+//   pass 1: for every row, nlists sorted (descending) lists of the k1 largest s seen by each
+//           (column segment x epilogue half) -> merged by merge_lists_kernel into key2_i;
+//   pass 2: append every column j with s_ij >= key2_i to the row's candidate buffer.
+// margin_c bounds the implementation's error: |d2_approx - d2_exact| <= margin_c (n_i + max_j n_j).
+#pragma once
+#include "common.cuh"
+
+namespace meld {
+
+constexpr int kMaxK1 = 64;     // knn + 1 limit (shared-memory top-k lists)
+constexpr int kMaxLists = 64;  // lists per row merged after pass 1
+
+struct SearchPlan {
+  bool simt = false;
+  int64_t n = 0, d = 0;
+  int k1 = 0;
+  int nseg = 1;    // column segments (independent work units per row tile)
+  int nlists = 1;  // lists per row written by pass 1
+  double margin_c = 0.0;
+  // tcgen05 path
+  int64_t n_pad = 0;  // rows padded to the tile size
+  int kp = 0;         // padded K of the bf16 operand (3 d + 3 rounded up to 64)
+  int terms = 3;      // bf16 split terms (3: hi*hi + hi*lo + lo*hi)
+};
+
+struct SearchState {
+  // SIMT
+  DevBuf<float> xc32;  // n x d centred float32
+  DevBuf<float> hn32;  // -n_j / 2
+  // tcgen05
+  DevBuf<uint16_t> a_op;  // n_pad x kp bf16, row operand
+  DevBuf<uint16_t> b_op;  // n_pad x kp bf16, column operand (carries -n_j/2 in its tail columns)
+  alignas(64) unsigned char tmap_a[128];
+  alignas(64) unsigned char tmap_b[128];
+};
+
+int search_plan(bool simt, int64_t n, int64_t d, int k1, SearchPlan *plan);
+int search_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
+                   SearchState *st);
+int search_pass1(const SearchPlan &plan, SearchState &st, float *lists, cudaStream_t stream);
+int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, int32_t *cand, int32_t *cnt, int cap,
+                 cudaStream_t stream);
+void search_release(SearchState *st);
+
+// tcgen05 implementation (knn_tc.cu)
+int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan);
+int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
+               SearchState *st);
+int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2, int32_t *cand,
+            int32_t *cnt, int cap, cudaStream_t stream);
+
+}  // namespace meld

@@ -1,0 +1,456 @@
+// tcgen05 candidate search: the pairwise-distance contraction on 5th-gen tensor cores.
+//
+// s_ij = x_i . x_j - n_j/2 for all pairs is one bf16 GEMM  S = A' B'^T  with fp32 accumulation:
+//   A'_i = [ hi(x_i) | hi(x_i) | lo(x_i) | 1 1 1 | 0.. ]      (x = hi + lo, both bf16)
+//   B'_j = [ hi(x_j) | lo(x_j) | hi(x_j) | h0 h1 h2 | 0.. ]   (h0+h1+h2 = -n_j/2 in bf16 pieces)
+// so the epilogue needs ONE compare per element: pass 1 keeps the k1 largest s per row, pass 2
+// appends every column with s >= key2_i.  K' = 3d+3 is padded to a multiple of 64.
+//
+// Kernel: persistent, warp-specialised, one CTA per SM (192 threads):
+//   warp 0     TMA producer  (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier complete_tx)
+//   warp 1     MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16; TMEM alloc)
+//   warps 2-5  epilogue      (tcgen05.ld 32x32b: thread = row, 32 columns per load)
+// A work unit is (128-row tile, column segment).  When K' <= 384 the row tile's A operand stays
+// resident in shared memory for the whole unit and only B tiles stream through a 3-stage ring;
+// otherwise A and B stream together.  The 512 TMEM columns hold two 128x256 fp32 accumulators so
+// the epilogue of tile t overlaps the MMAs of tile t+1.
+#include "knn_search.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace meld {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kStages = 3;
+constexpr int kTcThreads = 192;
+constexpr int kABytes = BM * BK * 2;   // 16 KB
+constexpr int kBBytes = BN * BK * 2;   // 32 KB
+constexpr int kMaxResidentKb = 6;      // A resident up to K' = 384
+constexpr int kARegion = kMaxResidentKb * kABytes;  // 96 KB
+constexpr int kBRegion = kStages * kBBytes;         // 96 KB
+constexpr float kPadSentinel = -1e30f;
+
+// ---- operand preparation ------------------------------------------------------------------------
+__global__ void tc_prep_kernel(const double *__restrict__ X, const double *__restrict__ mu,
+                               const double *__restrict__ norm, int64_t n, int64_t n_pad, int64_t d, int kp,
+                               __nv_bfloat16 *__restrict__ A, __nv_bfloat16 *__restrict__ B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f), one = __float2bfloat16(1.f);
+  for (int64_t i = warp; i < n_pad; i += nwarps) {
+    __nv_bfloat16 *a = A + i * kp, *b = B + i * kp;
+    if (i >= n) {
+      for (int k = lane; k < kp; k += 32) {
+        a[k] = zero;
+        b[k] = (k == 3 * d) ? __float2bfloat16(kPadSentinel) : zero;
+      }
+      continue;
+    }
+    for (int64_t k = lane; k < d; k += 32) {
+      const float xf = (float)(X[i * d + k] - mu[k]);
+      const __nv_bfloat16 hi = __float2bfloat16(xf);
+      const __nv_bfloat16 lo = __float2bfloat16(xf - __bfloat162float(hi));
+      a[k] = hi;
+      a[d + k] = hi;
+      a[2 * d + k] = lo;
+      b[k] = hi;
+      b[d + k] = lo;
+      b[2 * d + k] = hi;
+    }
+    const float h = (float)(-0.5 * norm[i]);
+    const __nv_bfloat16 h0 = __float2bfloat16(h);
+    const float r1 = h - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16(r1);
+    const __nv_bfloat16 h2 = __float2bfloat16(r1 - __bfloat162float(h1));
+    for (int k = 3 * (int)d + lane; k < kp; k += 32) {
+      const int t = k - 3 * (int)d;
+      a[k] = t < 3 ? one : zero;
+      b[k] = t == 0 ? h0 : (t == 1 ? h1 : (t == 2 ? h2 : zero));
+    }
+  }
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = s32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(const void *tmap, uint64_t *bar, void *dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          s32(dst)),
+      "l"(tmap), "r"(s32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct TcArgs {
+  int mode;  // 1: top-k1 lists, 2: emit candidates
+  int64_t n;
+  int n_row_tiles, n_col_tiles, nseg, nkb, a_resident, k1;
+  float *lists;
+  const float *key2;
+  int32_t *cand;
+  int32_t *cnt;
+  int cap;
+};
+
+struct Bars {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t a_full, a_empty;
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+    tc_search_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const TcArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char *smA = smem;                   // resident A (nkb x 16 KB) or A stages
+  unsigned char *smB = smem + kARegion;        // B stages
+  float *lst = reinterpret_cast<float *>(smem + kARegion + kBRegion);  // [k1][128] (pass 1)
+  Bars *bars = reinterpret_cast<Bars *>(smem + kARegion + kBRegion + (size_t)(a.mode == 1 ? a.k1 : 0) * BM * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = a.n_row_tiles * a.nseg;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        bar_init(&bars->full[s], 1);
+        bar_init(&bars->empty[s], 1);
+      }
+      bar_init(&bars->a_full, 1);
+      bar_init(&bars->a_empty, 1);
+      for (int b = 0; b < 2; ++b) {
+        bar_init(&bars->tmem_full[b], 1);
+        bar_init(&bars->tmem_empty[b], 4);  // one arrival per epilogue warp
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, uphase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int rt = u / a.nseg, seg = u % a.nseg;
+        const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
+        const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
+        if (a.a_resident) {
+          bar_wait(&bars->a_empty, uphase ^ 1u);
+          bar_expect_tx(&bars->a_full, (uint32_t)a.nkb * kABytes);
+          for (int kb = 0; kb < a.nkb; ++kb) tma_load_2d(&tmap_a, &bars->a_full, smA + kb * kABytes, kb * BK, rt * BM);
+        }
+        for (int ct = ct0; ct < ct1; ++ct) {
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            bar_wait(&bars->empty[stage], phase ^ 1u);
+            bar_expect_tx(&bars->full[stage], a.a_resident ? kBBytes : kBBytes + kABytes);
+            tma_load_2d(&tmap_b, &bars->full[stage], smB + stage * kBBytes, kb * BK, ct * BN);
+            if (!a.a_resident) tma_load_2d(&tmap_a, &bars->full[stage], smA + stage * kABytes, kb * BK, rt * BM);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        uphase ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, bphase = 0, uphase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int seg = u % a.nseg;
+        const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
+        const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
+        if (a.a_resident) {
+          bar_wait(&bars->a_full, uphase);
+          tc_fence_after();
+        }
+        for (int ct = ct0; ct < ct1; ++ct) {
+          bar_wait(&bars->tmem_empty[buf], bphase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)buf * BN;
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            bar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_base = s32(a.a_resident ? smA + kb * kABytes : smA + stage * kABytes);
+            const uint32_t b_base = s32(smB + stage * kBBytes);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              tc_mma_bf16(tmem_d, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
+                          (uint32_t)((kb | k) != 0));
+            }
+            tc_commit(&bars->empty[stage]);  // stage reusable once these MMAs retire
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tc_commit(&bars->tmem_full[buf]);
+          buf ^= 1;
+          if (buf == 0) bphase ^= 1u;
+        }
+        if (a.a_resident) tc_commit(&bars->a_empty);
+        uphase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue: thread = row of the tile =====
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int rin = q * 32 + lane;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int rt = u / a.nseg, seg = u % a.nseg;
+      const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
+      const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
+      const int64_t row = (int64_t)rt * BM + rin;
+      float thr;
+      if (a.mode == 1) {
+        for (int s = 0; s < a.k1; ++s) lst[s * BM + rin] = -INFINITY;
+        thr = -INFINITY;
+      } else {
+        thr = row < a.n ? a.key2[row] : INFINITY;
+      }
+      for (int ct = ct0; ct < ct1; ++ct) {
+        bar_wait(&bars->tmem_full[buf], bphase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
+          tmem_ld32(tbase + chunk * 32, v);
+          tmem_ld_wait();
+          const int col0 = ct * BN + chunk * 32;
+          if (a.mode == 1) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float s = __uint_as_float(v[c]);
+              if (s > thr) {
+                int pos = a.k1 - 1;
+                while (pos > 0 && lst[(pos - 1) * BM + rin] < s) {
+                  lst[pos * BM + rin] = lst[(pos - 1) * BM + rin];
+                  --pos;
+                }
+                lst[pos * BM + rin] = s;
+                thr = lst[(a.k1 - 1) * BM + rin];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float s = __uint_as_float(v[c]);
+              if (s >= thr) {
+                const int pos = atomicAdd(a.cnt + row, 1);
+                if (pos < a.cap) a.cand[(size_t)row * a.cap + pos] = col0 + c;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(&bars->tmem_empty[buf]);
+        buf ^= 1;
+        if (buf == 0) bphase ^= 1u;
+      }
+      if (a.mode == 1 && row < a.n) {
+        float *out = a.lists + ((size_t)row * a.nseg + seg) * a.k1;
+        for (int s = 0; s < a.k1; ++s) out[s] = lst[s * BM + rin];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_operand_map(void *base, int64_t rows, int kp, int box_rows, unsigned char *out) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MELD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return MELD_B200_ERR_CUDA;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)kp * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return MELD_B200_ERR_CUDA;
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  memcpy(out, &m, sizeof(m));
+  return 0;
+}
+
+int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan) {
+  plan->simt = false;
+  plan->n = n;
+  plan->d = d;
+  plan->k1 = k1;
+  plan->terms = 3;
+  const int64_t kp = round_up(3 * d + 3, BK);
+  MELD_REQUIRE(kp <= (1 << 20), "knn_graph_build: d=%lld too large for the tensor-core search", (long long)d);
+  plan->kp = (int)kp;
+  plan->n_pad = round_up(n, BN);
+  const int64_t row_tiles = plan->n_pad / BM, col_tiles = plan->n_pad / BN;
+  // enough (row tile, segment) units for ~4 waves of the SMs, never more segments than column tiles
+  int64_t nseg = ceil_div(4 * (int64_t)sm_count(), row_tiles);
+  if (nseg > kMaxLists) nseg = kMaxLists;
+  if (nseg > col_tiles) nseg = col_tiles;
+  if (nseg < 1) nseg = 1;
+  plan->nseg = (int)nseg;
+  plan->nlists = (int)nseg;
+  // bf16 split error of x.y (~2^-15.8 |x||y|) plus fp32 accumulation, x2 for d^2, 4x safety
+  plan->margin_c = ldexp(1.0, -11);
+  return 0;
+}
+
+int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
+               SearchState *st) {
+  MELD_CHECK(st->a_op.alloc((size_t)plan.n_pad * plan.kp));
+  MELD_CHECK(st->b_op.alloc((size_t)plan.n_pad * plan.kp));
+  tc_prep_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, mu, norm, plan.n, plan.n_pad, plan.d, plan.kp,
+                                                     reinterpret_cast<__nv_bfloat16 *>(st->a_op.p),
+                                                     reinterpret_cast<__nv_bfloat16 *>(st->b_op.p));
+  MELD_LAUNCH_CHECK();
+  MELD_CHECK(encode_operand_map(st->a_op.p, plan.n_pad, plan.kp, BM, st->tmap_a));
+  MELD_CHECK(encode_operand_map(st->b_op.p, plan.n_pad, plan.kp, BN, st->tmap_b));
+  return 0;
+}
+
+int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2, int32_t *cand,
+            int32_t *cnt, int cap, cudaStream_t stream) {
+  TcArgs a{};
+  a.mode = mode;
+  a.n = plan.n;
+  a.n_row_tiles = (int)(plan.n_pad / BM);
+  a.n_col_tiles = (int)(plan.n_pad / BN);
+  a.nseg = plan.nseg;
+  a.nkb = plan.kp / BK;
+  a.a_resident = a.nkb <= kMaxResidentKb ? 1 : 0;
+  a.k1 = plan.k1;
+  a.lists = lists;
+  a.key2 = key2;
+  a.cand = cand;
+  a.cnt = cnt;
+  a.cap = cap;
+  const size_t smem = 1024 + (size_t)kARegion + kBRegion + (mode == 1 ? (size_t)plan.k1 * BM * 4 : 0) + sizeof(Bars);
+  MELD_REQUIRE(smem <= 227 * 1024, "tc_search: %zu bytes of shared memory (knn too large)", smem);
+  MELD_CUDA(cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap ma, mb;
+  memcpy(&ma, st.tmap_a, sizeof(ma));
+  memcpy(&mb, st.tmap_b, sizeof(mb));
+  int grid = sm_count();
+  const int units = a.n_row_tiles * a.nseg;
+  if (grid > units) grid = units;
+  tc_search_kernel<<<grid, kTcThreads, smem, stream>>>(ma, mb, a);
+  MELD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace meld

