@@ -274,6 +274,8 @@ def run_b200(args):
                 "workload": workload_name(args, cfg, n), "parallelism": "replicas x{}".format(world),
                 "nnz_L": int(nnz), "nnz_per_row": nnz / n, "lmax": lmax, "candidate_cap": stats["candidate_cap"],
                 "max_candidates": stats["max_candidates"], "search_passes": stats["search_passes"],
+                "row_blocks": stats["row_blocks"], "direct_blocks": stats["direct_blocks"],
+                "dict_entries_per_nnz": stats["dict_total"] / max(nnz, 1),
                 "l2_note": "inputs (X {} MB, L {} MB) exceed the 126 MB L2; no explicit flush".format(
                     Xh.nbytes // 2**20, nnz * 12 // 2**20),
             },

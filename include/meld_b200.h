@@ -52,8 +52,8 @@ int64_t meld_b200_launch_count(void);
 int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
 
 /* Launch-configuration knobs of the Chebyshev kernel, for bench sweeps and tests
- * only (keys: blk_chunk, stage_cap, row_cap, n_stage, threads, ctas_per_sm, group,
- * use_graph).  Takes effect for graphs created afterwards.                       */
+ * only (keys: blk_chunk, stage_cap, dict_cap, row_cap, n_stage, threads, gather_warps,
+ * ctas_per_sm, group, use_dict, reorder, tc_multicast).  Takes effect for graphs created afterwards.                       */
 int meld_b200_set_tuning(const char *key, int value);
 
 /* ---- graph construction ------------------------------------------------------ */
@@ -93,6 +93,12 @@ int meld_b200_graph_info(const meld_b200_graph_t *g, int64_t *n_rows_host, int64
 /* Copies L out (caller-allocated: indptr n_rows+1 int64, indices nnz int32, data nnz f64). */
 int meld_b200_graph_export_csr(const meld_b200_graph_t *g, int64_t *indptr, int32_t *indices,
                                double *data, void *stream);
+/* Graphs built by meld_b200_knn_graph_build keep their rows in an internal cell order (Morton curve
+ * of the leading features; row a of the exported CSR = caller's cell perm[a], columns likewise).
+ * cheby_filter takes and returns signals in the CALLER's order.  perm_out: n_rows int32 (device),
+ * may be NULL; *is_identity_host = 1 when no reordering was applied.                       */
+int meld_b200_graph_permutation(const meld_b200_graph_t *g, int32_t *perm_out, int *is_identity_host,
+                                void *stream);
 /* Un-symmetrised alpha-decay kernel (graphtools kNNGraph.build_kernel_to_data);
  * only when built with MELD_B200_FLAG_KEEP_KNN_KERNEL.                           */
 int meld_b200_graph_knn_kernel_nnz(const meld_b200_graph_t *g, int64_t *nnz_host);
@@ -100,7 +106,8 @@ int meld_b200_graph_export_knn_kernel(const meld_b200_graph_t *g, int64_t *indpt
                                       double *data, void *stream);
 /* Build statistics (host): [0] candidate-search passes run, [1] max candidates/row,
  * [2] candidate capacity used, [3] rows that overflowed on the first emit pass,
- * [4] search implementation (0 tcgen05, 1 SIMT), [5..7] reserved.                */
+ * [4] search implementation (0 tcgen05, 1 SIMT), [5] sum of block dictionary sizes,
+ * [6] row blocks on the direct path, [7] row blocks.                */
 int meld_b200_graph_build_stats(const meld_b200_graph_t *g, int64_t *stats8_host);
 int meld_b200_graph_destroy(meld_b200_graph_t *g);
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "meld_b200_graph_from_csr": (C.c_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "meld_b200_graph_info": (C.c_int, [_vp, _pi64, _pi64, _pi64, _pi64]),
     "meld_b200_graph_export_csr": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "meld_b200_graph_permutation": (C.c_int, [_vp, _vp, _pint, _vp]),
     "meld_b200_graph_knn_kernel_nnz": (C.c_int, [_vp, _pi64]),
     "meld_b200_graph_export_knn_kernel": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "meld_b200_graph_build_stats": (C.c_int, [_vp, _pi64]),

@@ -6,16 +6,22 @@
 //             T_k = (2/a1)(L - a2 I) T_{k-1} - T_{k-2}; R += c_k T_k      (a1 = a2 = lmax/2)
 //   estimate_lmax: 1.01 * largest eigenvalue of L.
 //
-// Kernel design (one launch per recurrence term):
-//   * persistent CTAs; each walks row blocks b = blockIdx.x, += gridDim.x;
-//   * a row block is a contiguous run of ~blk_chunk CSR entries; its columns and values
-//     are staged into shared memory with two 1-D TMA bulk copies (cp.async.bulk +
-//     mbarrier complete_tx), n_stage blocks deep, so HBM streaming of the matrix is
-//     decoupled from the L2 gathers of T_{k-1};
-//   * G lanes cooperate on a row: coalesced shared-memory reads of (col, val),
-//     128-bit gathers of the P-wide signal row, warp-shuffle reduction over the G lanes;
-//   * the three-term update and the R accumulation are fused into the epilogue, T_k is
-//     written over T_{k-2} (row i of T_{k-2} is only ever read by row i).
+// Kernel design (one launch per recurrence term, one persistent 512-thread CTA per SM):
+//   * the matrix is cut into row blocks of ~blk_chunk CSR entries.  graph_finalize gives every
+//     block a dictionary of its distinct columns and rewrites its column indices as 16-bit
+//     positions in that dictionary (neighbouring rows of a kNN graph share most of their
+//     columns once cells are ordered along a space-filling curve);
+//   * warp 0 (one lane) is the TMA producer: per block it bulk-copies values, local indices,
+//     row pointers, the dictionary and the rows' own T_{k-1} / T_{k-2} / R slices into one of
+//     n_stage shared-memory stages (cp.async.bulk + mbarrier complete_tx);
+//   * gather warps wait for a stage's dictionary and pull the P-wide rows of T_{k-1} for the
+//     distinct columns into the stage with cp.async (LDGSTS): no registers are held while the
+//     L2 gathers are in flight and each distinct row is fetched once per block;
+//   * compute warps multiply out of shared memory only (G lanes per row, warp-shuffle
+//     reduction), apply the fused three-term update and R accumulation, and release the stage;
+//   * T_k is written over T_{k-2} (row i of T_{k-2} is only ever read by row i).
+// Blocks that do not fit a stage (a row longer than the stage, too many distinct columns) take
+// the direct path: same arithmetic, operands read straight from global memory.
 #include "common.cuh"
 
 #include <math.h>
@@ -23,7 +29,7 @@
 
 namespace meld {
 
-// ---- PTX helpers: mbarrier + 1-D TMA bulk copy ---------------------------------------
+// ---- PTX helpers: mbarrier, 1-D TMA bulk copy, cp.async ---------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -56,11 +62,24 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// this thread's earlier cp.async copies count as one (pre-counted) arrival once they have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 struct StepArgs {
   const int32_t *row_ptr;
   const int32_t *col;
   const double *val;
+  const uint16_t *lidx;
+  const int32_t *dict;
+  const int32_t *dcnt;
   const int32_t *blk;
   int32_t n_blk;
   int64_t row0;
@@ -70,14 +89,18 @@ struct StepArgs {
   double *R;
   double alpha, shift, gamma, c, c_cur;
   int r_acc;
-  int cap;      // CSR entries per stage
-  int rcap;     // row pointers per stage
-  int n_stage;  // pipeline depth
+  int cap;         // CSR entries per stage
+  int ucap;        // dictionary entries (distinct columns) per stage
+  int rcap;        // row pointers per stage
+  int rows_cap;    // rows whose T/R slices are staged
+  int n_stage;     // pipeline depth
+  int gather_warps;
+  int stage_epi;   // 1: the T/R arrays are library workspace (padded), slices may be bulk-copied
+  int stage_bytes;
 };
 
-// Gather one P-wide signal row with the widest aligned loads available: every distinct
-// 128-byte line touched by a warp-level load costs ~2 L1 wavefront cycles, so a 32-byte row
-// must be one 256-bit request, not two 128-bit ones.
+// Gather one P-wide signal row straight from global memory (direct path): one 256-bit request per
+// 32-byte row -- every distinct 128-byte line touched by a warp-level load costs L1 wavefronts.
 __device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c, double &d) {
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
@@ -99,6 +122,22 @@ __device__ __forceinline__ void gather_row(const double *__restrict__ T, int32_t
     for (int k = 0; k < P; ++k) x[k] = __ldg(t + k);
   }
 }
+// Same row out of the stage's shared-memory copy.
+template <int P>
+__device__ __forceinline__ void smem_row(const double *xs, int li, double (&x)[P]) {
+  const double *t = xs + (size_t)li * P;
+  if constexpr (P % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < P; k += 2) {
+      const double2 v = *reinterpret_cast<const double2 *>(t + k);
+      x[k] = v.x;
+      x[k + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < P; ++k) x[k] = t[k];
+  }
+}
 
 __device__ __forceinline__ double ld_stream(const double *p) {  // read-once operand: do not keep in L1
   double v;
@@ -109,48 +148,55 @@ __device__ __forceinline__ void st_stream(double *p, double v) {
   asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-constexpr int kUnroll = 4;  // gathers in flight per lane
+constexpr int kUnroll = 4;  // independent entries in flight per lane
 
-// Rows [r0, r1) of one block.  cs/vs are indexed by absolute CSR entry and rp by absolute
-// row (both already offset), whether they point into shared memory or global memory.
-template <int P, int G>
-__device__ __forceinline__ void process_rows(const StepArgs &a, int r0, int r1, const int32_t *cs, const double *vs,
-                                             const int32_t *rp, int gid, int gl, int ngroups) {
-  for (int rb = r0; rb < r1; rb += ngroups) {  // CTA-uniform trip count (full-mask shuffles below)
+// Where a block's operands live (shared-memory stage or global memory), already offset so that
+// CSR-entry / row indices are absolute.
+struct BlockView {
+  const double *vs;       // values, indexed by entry
+  const uint16_t *ls;     // dictionary positions, indexed by entry (staged blocks)
+  const int32_t *cs;      // columns, indexed by entry (direct blocks)
+  const int32_t *rp;      // row pointers, indexed by row
+  const double *xs;       // gathered T_cur rows of the dictionary (staged blocks)
+  const double *tc, *told, *rold;  // per-row slices indexed by (row * P + k), or nullptr -> global
+};
+
+template <int P, int G, bool STAGED>
+__device__ __forceinline__ void process_rows(const StepArgs &a, const BlockView &bv, int r0, int r1, int gid, int gl,
+                                             int ngroups) {
+  for (int rb = r0; rb < r1; rb += ngroups) {  // uniform trip count for all compute warps (full-mask shuffles)
     const int r = rb + gid;
     const bool act = r < r1;
     int eb = 0, ee = 0;
     if (act) {
-      eb = rp[r];
-      ee = rp[r + 1];
+      eb = bv.rp[r];
+      ee = bv.rp[r + 1];
     }
-    // Epilogue operands are requested first so their DRAM latency overlaps the gathers.
     const bool epi = act && gl < P;
     const size_t li = (size_t)r * P + gl;
     double tc = 0.0, told = 0.0, rold = 0.0;
-    if (epi) {
-      tc = __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
-      if (a.gamma != 0.0) told = ld_stream(a.Told + li);
-      if (a.R != nullptr && a.r_acc) rold = ld_stream(a.R + li);
+    if (epi) {  // requested first so their latency overlaps the row product
+      tc = bv.tc ? bv.tc[li] : __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
+      if (a.gamma != 0.0) told = bv.told ? bv.told[li] : ld_stream(a.Told + li);
+      if (a.R != nullptr && a.r_acc) rold = bv.rold ? bv.rold[li] : ld_stream(a.R + li);
     }
     double acc[P];
 #pragma unroll
     for (int k = 0; k < P; ++k) acc[k] = 0.0;
     for (int e = eb + gl; e < ee; e += kUnroll * G) {
-      int32_t c[kUnroll];
       double v[kUnroll];
       double x[kUnroll][P];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const bool in = e + u * G < ee;
-        c[u] = in ? cs[e + u * G] : 0;
-        v[u] = in ? vs[e + u * G] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        if (e + u * G < ee) {
-          gather_row<P>(a.Tcur, c[u], x[u]);
+        const int eu = e + u * G;
+        if (eu < ee) {
+          v[u] = bv.vs[eu];
+          if constexpr (STAGED)
+            smem_row<P>(bv.xs, (int)bv.ls[eu], x[u]);
+          else
+            gather_row<P>(a.Tcur, bv.cs[eu], x[u]);
         } else {
+          v[u] = 0.0;
 #pragma unroll
           for (int k = 0; k < P; ++k) x[u][k] = 0.0;
         }
@@ -173,7 +219,7 @@ __device__ __forceinline__ void process_rows(const StepArgs &a, int r0, int r1, 
         if (gl == k) y = acc[k];
       double tn = a.alpha * (y - a.shift * tc);
       if (a.gamma != 0.0) tn -= a.gamma * told;
-      if (a.Tnew) a.Tnew[li] = tn;  // re-read by the next step's gathers: keep cacheable
+      if (a.Tnew) a.Tnew[li] = tn;  // gathered by the next step: keep cacheable
       if (a.R) {
         double rv = a.c * tn + a.c_cur * tc;
         if (a.r_acc) rv += rold;
@@ -183,73 +229,170 @@ __device__ __forceinline__ void process_rows(const StepArgs &a, int r0, int r1, 
   }
 }
 
-template <int P, int G>
-__global__ void cheby_step_kernel(const StepArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int cap = a.cap, rcap = a.rcap, ns = a.n_stage;
-  double *sval = reinterpret_cast<double *>(smem_raw);
-  int32_t *scol = reinterpret_cast<int32_t *>(smem_raw + (size_t)ns * cap * 8);
-  int32_t *srp = reinterpret_cast<int32_t *>(smem_raw + (size_t)ns * cap * 12);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ns * cap * 12 + (size_t)ns * rcap * 4);
+// Geometry of one block; every role recomputes it from the same two small arrays.
+struct BlockGeom {
+  int r0, r1, e0, e1;
+  int a0, nal;   // entry range aligned to 8 entries (16 B of uint16 indices)
+  int ra, nr;    // row-pointer range aligned to 4
+  int u;         // dictionary size, < 0: direct block
+  bool staged, epi_staged;
+  size_t sc0, sl0;  // aligned first element of the T_cur-own / local-row slices
+  int nc, nl;       // their lengths (even)
+};
 
-  const int tid = threadIdx.x;
-  const int ngroups = blockDim.x / G;
-  const int gid = tid / G, gl = tid % G;
+template <int P>
+__device__ __forceinline__ BlockGeom block_geom(const StepArgs &a, int b) {
+  BlockGeom g;
+  g.r0 = __ldg(a.blk + b);
+  g.r1 = __ldg(a.blk + b + 1);
+  g.e0 = __ldg(a.row_ptr + g.r0);
+  g.e1 = __ldg(a.row_ptr + g.r1);
+  g.a0 = g.e0 & ~7;
+  g.nal = ((g.e1 - g.a0) + 7) & ~7;
+  g.ra = g.r0 & ~3;
+  g.nr = ((g.r1 + 1 - g.ra) + 3) & ~3;
+  g.u = __ldg(a.dcnt + b);
+  g.staged = g.u >= 0 && g.nal <= a.cap && g.nr <= a.rcap && g.u <= a.ucap && g.e1 > g.e0;
+  g.epi_staged = g.staged && a.stage_epi && (g.r1 - g.r0) <= a.rows_cap;
+  const size_t c0 = (size_t)(a.row0 + g.r0) * P, c1 = (size_t)(a.row0 + g.r1) * P;
+  const size_t l0 = (size_t)g.r0 * P, l1 = (size_t)g.r1 * P;
+  g.sc0 = c0 & ~(size_t)1;
+  g.sl0 = l0 & ~(size_t)1;
+  g.nc = (int)(((c1 - g.sc0) + 1) & ~(size_t)1);
+  g.nl = (int)(((l1 - g.sl0) + 1) & ~(size_t)1);
+  return g;
+}
+
+template <int P, int G>
+__global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int ns = a.n_stage;
+  // stage layout (bytes): values | local indices | row pointers | dictionary | gathered rows | tc | told | rold
+  const int off_l = a.cap * 8;
+  const int off_r = off_l + a.cap * 2;
+  const int off_d = off_r + a.rcap * 4;
+  const int off_x = off_d + a.ucap * 4;
+  const int epi_len = a.rows_cap * P + 2;
+  const int off_tc = off_x + a.ucap * P * 8;
+  const int off_to = off_tc + epi_len * 8;
+  const int off_ro = off_to + epi_len * 8;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ns * a.stage_bytes);
+  uint64_t *full_mat = bars, *full_x = bars + ns, *empty = bars + 2 * ns;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_compute_warps = (blockDim.x >> 5) - 1 - a.gather_warps;
   const int stride = gridDim.x;
 
   if (tid == 0) {
-    for (int s = 0; s < ns; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(&full_mat[s], 1);
+      mbar_init(&full_x[s], (uint32_t)a.gather_warps * 32u);
+      mbar_init(&empty[s], (uint32_t)n_compute_warps);
+    }
     fence_barrier_init();
   }
   __syncthreads();
 
-  // Thread 0 is the TMA producer: arm the stage barrier, then three bulk copies
-  // (values, columns, row pointers), each 16-byte aligned at both ends.
-  auto issue = [&](int b, int s) {
-    const int r0 = __ldg(a.blk + b), r1 = __ldg(a.blk + b + 1);
-    const int e0 = __ldg(a.row_ptr + r0), e1 = __ldg(a.row_ptr + r1);
-    const int a0 = e0 & ~3;                  // aligned start for the int32 columns
-    const int n = ((e1 - a0) + 3) & ~3;      // multiple of 4 entries (tail lands in kCsrPad)
-    const int ra = r0 & ~3;
-    const int nr = ((r1 + 1 - ra) + 3) & ~3;
-    if (n > 0 && n <= cap && nr <= rcap) {
-      mbar_arrive_expect_tx(&bars[s], (uint32_t)n * 12u + (uint32_t)nr * 4u);
-      bulk_g2s(sval + (size_t)s * cap, a.val + a0, (uint32_t)n * 8u, &bars[s]);
-      bulk_g2s(scol + (size_t)s * cap, a.col + a0, (uint32_t)n * 4u, &bars[s]);
-      bulk_g2s(srp + (size_t)s * rcap, a.row_ptr + ra, (uint32_t)nr * 4u, &bars[s]);
-    } else {
-      mbar_arrive(&bars[s]);  // oversize / empty block: nothing staged, phase still advances
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
+        const int s = it % ns;
+        const uint32_t ph = (uint32_t)(it / ns) & 1u;
+        unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const BlockGeom g = block_geom<P>(a, b);
+        if (!g.staged) {
+          mbar_arrive(&full_mat[s]);  // direct block: nothing staged, the phase still advances
+          continue;
+        }
+        const uint32_t ub = (uint32_t)((g.u + 3) & ~3) * 4u;
+        uint32_t bytes = (uint32_t)g.nal * 10u + (uint32_t)g.nr * 4u + ub;
+        if (g.epi_staged) {
+          bytes += (uint32_t)g.nc * 8u;
+          if (a.gamma != 0.0) bytes += (uint32_t)g.nl * 8u;
+          if (a.R != nullptr && a.r_acc) bytes += (uint32_t)g.nl * 8u;
+        }
+        mbar_arrive_expect_tx(&full_mat[s], bytes);
+        bulk_g2s(st, a.val + g.a0, (uint32_t)g.nal * 8u, &full_mat[s]);
+        bulk_g2s(st + off_l, a.lidx + g.a0, (uint32_t)g.nal * 2u, &full_mat[s]);
+        bulk_g2s(st + off_r, a.row_ptr + g.ra, (uint32_t)g.nr * 4u, &full_mat[s]);
+        if (ub) bulk_g2s(st + off_d, a.dict + (size_t)b * a.ucap, ub, &full_mat[s]);
+        if (g.epi_staged) {
+          bulk_g2s(st + off_tc, a.Tcur + g.sc0, (uint32_t)g.nc * 8u, &full_mat[s]);
+          if (a.gamma != 0.0) bulk_g2s(st + off_to, a.Told + g.sl0, (uint32_t)g.nl * 8u, &full_mat[s]);
+          if (a.R != nullptr && a.r_acc) bulk_g2s(st + off_ro, a.R + g.sl0, (uint32_t)g.nl * 8u, &full_mat[s]);
+        }
+      }
     }
-  };
-
-  if (tid == 0) {
-    for (int s = 0; s < ns; ++s) {
-      const int b = blockIdx.x + s * stride;
-      if (b < a.n_blk) issue(b, s);
+  } else if (warp <= a.gather_warps) {
+    // ===== gather warps: dictionary -> cp.async of the T_cur rows into the stage =====
+    const int gt = (warp - 1) * 32 + lane, ngt = a.gather_warps * 32;
+    int it = 0;
+    for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
+      const int s = it % ns;
+      const uint32_t ph = (uint32_t)(it / ns) & 1u;
+      unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
+      mbar_wait(&full_mat[s], ph);
+      const BlockGeom g = block_geom<P>(a, b);
+      if (g.staged) {
+        const int32_t *sd = reinterpret_cast<const int32_t *>(st + off_d);
+        double *xs = reinterpret_cast<double *>(st + off_x);
+        for (int t = gt; t < g.u; t += ngt) {
+          const double *src = a.Tcur + (size_t)sd[t] * P;
+          double *dst = xs + (size_t)t * P;
+          if constexpr (P % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < P; k += 2) cp_async16(dst + k, src + k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < P; ++k) cp_async8(dst + k, src + k);
+          }
+        }
+      }
+      cp_async_arrive_noinc(&full_x[s]);
     }
-  }
-
-  int it = 0;
-  for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
-    const int s = it % ns;
-    const uint32_t parity = (uint32_t)(it / ns) & 1u;
-    const int r0 = __ldg(a.blk + b), r1 = __ldg(a.blk + b + 1);
-    const int e0 = __ldg(a.row_ptr + r0), e1 = __ldg(a.row_ptr + r1);
-    const int a0 = e0 & ~3;
-    const int n = ((e1 - a0) + 3) & ~3;
-    const int ra = r0 & ~3;
-    const int nr = ((r1 + 1 - ra) + 3) & ~3;
-    mbar_wait(&bars[s], parity);
-    if (n <= cap && nr <= rcap) {
-      process_rows<P, G>(a, r0, r1, scol + (size_t)s * cap - a0, sval + (size_t)s * cap - a0,
-                         srp + (size_t)s * rcap - ra, gid, gl, ngroups);
-    } else {
-      process_rows<P, G>(a, r0, r1, a.col, a.val, a.row_ptr, gid, gl, ngroups);  // block too long for a stage
-    }
-    __syncthreads();  // every lane is done reading stage s before it is refilled
-    if (tid == 0) {
-      const int nb = b + ns * stride;
-      if (nb < a.n_blk) issue(nb, s);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    // ===== compute warps =====
+    const int ct = (warp - 1 - a.gather_warps) * 32 + lane;
+    const int ngroups = n_compute_warps * 32 / G;
+    const int gid = ct / G, gl = ct % G;
+    int it = 0;
+    for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
+      const int s = it % ns;
+      const uint32_t ph = (uint32_t)(it / ns) & 1u;
+      unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
+      const BlockGeom g = block_geom<P>(a, b);
+      mbar_wait(&full_mat[s], ph);
+      mbar_wait(&full_x[s], ph);
+      BlockView bv;
+      if (g.staged) {
+        bv.vs = reinterpret_cast<const double *>(st) - g.a0;
+        bv.ls = reinterpret_cast<const uint16_t *>(st + off_l) - g.a0;
+        bv.cs = nullptr;
+        bv.rp = reinterpret_cast<const int32_t *>(st + off_r) - g.ra;
+        bv.xs = reinterpret_cast<const double *>(st + off_x);
+        if (g.epi_staged) {
+          bv.tc = reinterpret_cast<const double *>(st + off_tc) - g.sc0 + (size_t)a.row0 * P;  // indexed by local row
+          bv.told = (a.gamma != 0.0) ? reinterpret_cast<const double *>(st + off_to) - g.sl0 : nullptr;
+          bv.rold = (a.R != nullptr && a.r_acc) ? reinterpret_cast<const double *>(st + off_ro) - g.sl0 : nullptr;
+        } else {
+          bv.tc = bv.told = bv.rold = nullptr;
+        }
+        process_rows<P, G, true>(a, bv, g.r0, g.r1, gid, gl, ngroups);
+      } else {
+        bv.vs = a.val;
+        bv.ls = nullptr;
+        bv.cs = a.col;
+        bv.rp = a.row_ptr;
+        bv.xs = nullptr;
+        bv.tc = bv.told = bv.rold = nullptr;
+        process_rows<P, G, false>(a, bv, g.r0, g.r1, gid, gl, ngroups);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
     }
   }
 }
@@ -293,7 +436,9 @@ static int choose_group(const meld_b200_graph *g, int P) {
   return G;
 }
 
-static int launch_step(const meld_b200_graph *g, StepArgs a, int P, cudaStream_t stream) {
+// stage_epi: the T/R arrays come from library workspace (padded by two doubles), so the rows' own
+// slices may be bulk-copied with 16-byte aligned, even-length requests.
+static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_epi, cudaStream_t stream) {
   const Tuning &t = tuning();
   const int G = choose_group(g, P);
   StepKernel k = pick_kernel(P, G);
@@ -301,28 +446,63 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, cudaStream_t
   a.row_ptr = g->row_ptr.p;
   a.col = g->col.p;
   a.val = g->val.p;
+  a.lidx = g->lidx.p;
+  a.dict = g->dict.p;
+  a.dcnt = g->dcnt.p;
   a.blk = g->blk.p;
   a.n_blk = g->n_blk;
   a.row0 = g->row0;
-  a.cap = t.stage_cap;
-  a.rcap = t.row_cap;
-  a.n_stage = t.n_stage;
-  const size_t smem = (size_t)t.n_stage * ((size_t)t.stage_cap * 12 + (size_t)t.row_cap * 4 + 8);
-  MELD_REQUIRE(smem <= 227 * 1024, "cheby_step: %zu bytes of shared memory requested", smem);
-  MELD_REQUIRE(t.threads % 32 == 0 && t.threads >= 32 && t.threads <= 1024 && t.stage_cap % 16 == 0 && t.row_cap % 16 == 0,
-               "cheby_step: bad tuning");
+  a.cap = g->stage_cap;
+  a.ucap = g->dict_cap;
+  a.rcap = g->row_cap + 8;
+  a.rows_cap = g->row_cap;
+  a.gather_warps = t.gather_warps;
+  a.stage_epi = stage_epi;
+  const int threads = t.threads;
+  MELD_REQUIRE(threads % 32 == 0 && threads >= 96 && threads <= 512 && t.gather_warps >= 1 &&
+                   threads / 32 - 1 - t.gather_warps >= 1,
+               "cheby_step: bad tuning (threads=%d gather_warps=%d)", threads, t.gather_warps);
+  const size_t epi_len = (size_t)a.rows_cap * P + 2;
+  size_t stage = (size_t)a.cap * 10 + (size_t)a.rcap * 4 + (size_t)a.ucap * 4 + (size_t)a.ucap * P * 8 + 3 * epi_len * 8;
+  stage = (stage + 127) & ~(size_t)127;
+  const size_t budget = 227 * 1024 - 256;
+  int ns = t.n_stage > 0 ? t.n_stage : (int)(budget / stage);
+  if (ns > 8) ns = 8;
+  while (ns > 1 && (size_t)ns * stage + (size_t)ns * 24 > budget) --ns;
+  MELD_REQUIRE(ns >= 1 && (size_t)ns * stage + (size_t)ns * 24 <= budget, "cheby_step: a %zu-byte stage does not fit",
+               stage);
+  a.n_stage = ns;
+  a.stage_bytes = (int)stage;
+  const size_t smem = (size_t)ns * stage + (size_t)ns * 24;
   MELD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count() * t.ctas_per_sm;
   if (grid > g->n_blk) grid = g->n_blk;
   if (grid < 1) grid = 1;
-  k<<<grid, t.threads, smem, stream>>>(a);
+  k<<<grid, threads, smem, stream>>>(a);
   MELD_LAUNCH_CHECK();
   return 0;
 }
 
+static int grid_for(int64_t n, int threads);
+
 static int ensure_work(meld_b200_graph *g, size_t count) {
   if (g->work.n >= count) return 0;
   return g->work.alloc(count);
+}
+
+// rows of an (n, p) array through a permutation: out[a] = in[perm[a]] (gather) or out[perm[a]] = in[a]
+__global__ void permute_rows_kernel(const double *__restrict__ in, const int32_t *__restrict__ perm, int64_t n, int p,
+                                    int scatter, double *__restrict__ out) {
+  const int64_t total = n * p;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / p;
+    const int j = (int)(t - i * p);
+    const int64_t o = perm ? (int64_t)perm[i] : i;
+    if (scatter)
+      out[o * p + j] = in[t];
+    else
+      out[t] = in[o * p + j];
+  }
 }
 
 // ---- Lanczos helpers ----------------------------------------------------------------
@@ -501,6 +681,8 @@ int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double
   MELD_REQUIRE(p >= 1 && p <= 8, "cheby_step: p=%d outside 1..8", p);
   MELD_REQUIRE(gamma == 0.0 || T_old != nullptr, "cheby_step: gamma != 0 needs T_old");
   MELD_REQUIRE((const double *)T_new != T_cur, "cheby_step: T_new may not alias T_cur");
+  MELD_REQUIRE(g->perm.p == nullptr, "cheby_step: graph rows are internally reordered; use cheby_filter");
+  MELD_REQUIRE(((uintptr_t)T_cur & 31) == 0, "cheby_step: T_cur must be 32-byte aligned");
   StepArgs a{};
   a.Tcur = T_cur;
   a.Told = T_old;
@@ -512,7 +694,7 @@ int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double
   a.c = c;
   a.c_cur = c_cur;
   a.r_acc = r_accumulate;
-  return launch_step(g, a, p, (cudaStream_t)stream_);
+  return launch_step(g, a, p, /*stage_epi=*/0, (cudaStream_t)stream_);  // caller arrays: no padded bulk reads
 }
 
 int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coeffs_host, int n_coeffs, const double *S,
@@ -524,26 +706,31 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
   MELD_REQUIRE(lmax > 0.0 && isfinite(lmax), "cheby_filter: lmax=%g", lmax);
   MELD_REQUIRE(g->row0 == 0 && g->n_rows == g->n_cols, "cheby_filter: needs the full operator (use cheby_step)");
   MELD_REQUIRE(S != R, "cheby_filter: R may not alias S");
-  const size_t np = (size_t)g->n_rows * p;
-  MELD_CHECK(ensure_work(g, 2 * np));
-  double *Ta = g->work.p, *Tb = g->work.p + np;
+  const int64_t n = g->n_rows;
+  // four padded work arrays (S and R in graph order, two recurrence buffers): even length + 2 so
+  // the kernel's 16-byte aligned bulk copies of row slices stay inside the allocation
+  const size_t len = ((size_t)n * p + 2 + 3) & ~(size_t)3;  // multiple of 32 bytes: 256-bit gathers on the direct path
+  MELD_CHECK(ensure_work(g, 4 * len));
+  double *Sp = g->work.p, *Rp = Sp + len, *Ta = Rp + len, *Tb = Ta + len;
+  const int pgrid = grid_for(n * p, 256);
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, g->perm.p, n, p, /*scatter=*/0, Sp);  // S into graph order
+  MELD_LAUNCH_CHECK();
   const double a1 = lmax / 2.0, a2 = lmax / 2.0;
   // k = 1: T1 = (L S - a2 S)/a1 ; R = c0/2 S + c1 T1
   StepArgs a{};
-  a.Tcur = S;
+  a.Tcur = Sp;
   a.Told = nullptr;
   a.Tnew = (n_coeffs > 2) ? Ta : nullptr;
-  a.R = R;
+  a.R = Rp;
   a.alpha = 1.0 / a1;
   a.shift = a2;
   a.gamma = 0.0;
   a.c = coeffs_host[1];
   a.c_cur = 0.5 * coeffs_host[0];
   a.r_acc = 0;
-  MELD_CHECK(launch_step(g, a, p, stream));
-  // k = 2 reads T0 = S (caller-owned) so T2 goes to the second buffer; from k = 3 on
-  // T_k overwrites T_{k-2} and the two workspace buffers ping-pong.
-  const double *cur = Ta, *old = S;
+  MELD_CHECK(launch_step(g, a, p, 1, stream));
+  // k = 2 still reads T0 = S, so T2 goes to the second buffer; from k = 3 on T_k overwrites T_{k-2}.
+  const double *cur = Ta, *old = Sp;
   for (int k = 2; k < n_coeffs; ++k) {
     double *nxt = (k == 2) ? Tb : const_cast<double *>(old);
     a.Tcur = cur;
@@ -554,10 +741,12 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
     a.c = coeffs_host[k];
     a.c_cur = 0.0;
     a.r_acc = 1;
-    MELD_CHECK(launch_step(g, a, p, stream));
+    MELD_CHECK(launch_step(g, a, p, 1, stream));
     old = cur;
     cur = nxt;
   }
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(Rp, g->perm.p, n, p, /*scatter=*/1, R);  // back to caller order
+  MELD_LAUNCH_CHECK();
   return 0;
 }
 
@@ -571,10 +760,11 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
   if (max_iters > n) max_iters = (int)n;
   if (rel_tol <= 0) rel_tol = 1e-9;
   MELD_REQUIRE(n >= 1, "estimate_lmax: empty graph");
-  const size_t need = 3 * (size_t)n + 2 * kRedBlocks + 2 * ((size_t)max_iters + 2);
+  const size_t len = ((size_t)n + 2 + 3) & ~(size_t)3;  // padded like the filter's work arrays
+  const size_t need = 3 * len + 2 * kRedBlocks + 2 * ((size_t)max_iters + 2);
   MELD_CHECK(ensure_work(g, need));
-  double *v = g->work.p, *vprev = v + n, *w = vprev + n;
-  double *pa = w + n, *pb = pa + kRedBlocks;
+  double *v = g->work.p, *vprev = v + len, *w = vprev + len;
+  double *pa = w + len, *pb = pa + kRedBlocks;
   double *d_alpha = pb + kRedBlocks, *d_beta = d_alpha + max_iters + 2;
   MELD_CUDA(cudaMemsetAsync(vprev, 0, (size_t)n * sizeof(double), stream));
   MELD_CUDA(cudaMemsetAsync(pa, 0, (2 * kRedBlocks + 2 * ((size_t)max_iters + 2)) * sizeof(double), stream));
@@ -594,7 +784,7 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
       a.Tcur = v;
       a.Tnew = w;
       a.alpha = 1.0;
-      MELD_CHECK(launch_step(g, a, 1, stream));
+      MELD_CHECK(launch_step(g, a, 1, 1, stream));
       dot_partials_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(v, w, n, pa);
       MELD_LAUNCH_CHECK();
       lanczos_update_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(w, v, vprev, n, pa, d_beta, j, d_alpha, pb);

@@ -54,14 +54,19 @@ int sm_count();
 // Launch configuration of the Chebyshev SpMM kernel (see cheby.cu).  The defaults are
 // the shipped configuration; meld_b200_set_tuning changes them for bench sweeps.
 struct Tuning {
-  int blk_chunk = 1536;   // target CSR entries per row block (C)
-  int stage_cap = 2048;   // entries of shared memory per pipeline stage
-  int row_cap = 512;      // row pointers of shared memory per pipeline stage
-  int n_stage = 3;        // TMA pipeline depth per CTA
-  int threads = 256;      // threads per CTA
-  int ctas_per_sm = 2;    // persistent CTAs per SM
+  int blk_chunk = 1024;   // target CSR entries per row block (C)
+  int stage_cap = 1280;   // CSR entries of shared memory per pipeline stage (multiple of 8, <= 2048)
+  int dict_cap = 640;     // distinct columns (dictionary entries) per stage (multiple of 4)
+  int row_cap = 128;      // rows per stage whose own T / R slices are staged (multiple of 8)
+  int n_stage = 0;        // TMA pipeline depth per CTA (0 = as many as fit in shared memory)
+  int threads = 512;      // threads per CTA: 1 producer warp + gather warps + compute warps
+  int gather_warps = 3;
+  int ctas_per_sm = 1;    // persistent CTAs per SM
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)
-  int use_graph = 1;      // capture the m-step recurrence in a CUDA graph
+  int use_dict = 1;       // 0: every block takes the direct (global-memory) path
+  int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
+  int use_graph = 1;      // reserved
+  int tc_multicast = 1;   // candidate search: 2-CTA clusters sharing B tiles by TMA multicast
 };
 Tuning &tuning();
 
@@ -112,6 +117,15 @@ struct meld_b200_graph {
   int32_t n_blk = 0;
   int32_t blk_chunk = 0;  // target nnz per block (C)
   int32_t max_row_nnz = 0;
+  // Per-block column dictionaries: dict[b * dict_cap + t] = t-th distinct column of block b,
+  // dcnt[b] = their number (-1: block takes the direct path), lidx[e] = position of col[e].
+  meld::DevBuf<int32_t> dict;
+  meld::DevBuf<int32_t> dcnt;
+  meld::DevBuf<uint16_t> lidx;  // nnz + kCsrPad
+  int32_t stage_cap = 0, dict_cap = 0, row_cap = 0;
+  int64_t dict_total = 0, direct_blocks = 0;  // statistics
+  // Cell order used internally (graph row a = caller's cell perm[a]); null = identity.
+  meld::DevBuf<int32_t> perm;
   // Chebyshev / Lanczos workspace, grown on demand.
   meld::DevBuf<double> work;
   // Un-symmetrised kNN kernel kept for export (compact CSR, slot order), optional.

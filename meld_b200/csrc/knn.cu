@@ -23,7 +23,10 @@
 #include "knn_search.cuh"
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_sort.cuh>
+#include <algorithm>
+#include <vector>
 #include <float.h>
 #include <math.h>
 
@@ -66,6 +69,62 @@ __global__ void row_norms_kernel(const double *__restrict__ X, const double *__r
       norm[i] = s;
       atomicMax(ymax2_bits, (unsigned long long)__double_as_longlong(s));  // s >= 0: bit order = value order
     }
+  }
+}
+
+// ---- 0b. cell ordering along a Morton curve of the four highest-variance features ---------------
+// Neighbouring rows of the kNN graph then share most of their columns, which is what the Chebyshev
+// kernel's per-block column dictionaries (graph_finalize) and the L1/L2 caches feed on.
+__global__ void col_partial_sq_kernel(const double *__restrict__ X, const double *__restrict__ mu, int64_t n, int64_t d,
+                                      double *partial) {
+  for (int64_t k = threadIdx.x; k < d; k += blockDim.x) {
+    double s = 0.0;
+    const double m = mu[k];
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+      const double v = X[i * d + k] - m;
+      s = fma(v, v, s);
+    }
+    partial[(int64_t)blockIdx.x * d + k] = s;
+  }
+}
+
+struct MortonDims {
+  int dim[4];
+  double mu[4];
+  double inv_range[4];  // 1 / (12 sigma)
+  int ndim;
+};
+
+__device__ __forceinline__ unsigned long long spread16(unsigned int v, int ndim) {
+  unsigned long long r = 0;
+  for (int b = 0; b < 16; ++b) r |= (unsigned long long)((v >> b) & 1u) << (b * ndim);
+  return r;
+}
+
+__global__ void morton_keys_kernel(const double *__restrict__ X, int64_t n, int64_t d, MortonDims md,
+                                   unsigned long long *__restrict__ keys, int32_t *__restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long key = 0;
+  for (int k = 0; k < md.ndim; ++k) {
+    double q = (X[i * d + md.dim[k]] - md.mu[k]) * md.inv_range[k] + 0.5;
+    q = fmin(fmax(q, 0.0), 1.0);
+    const unsigned int v = (unsigned int)(q * 65535.0);
+    key |= spread16(v, md.ndim) << k;
+  }
+  keys[i] = key;
+  idx[i] = (int32_t)i;
+}
+
+__global__ void gather_rows_kernel(const double *__restrict__ X, const int32_t *__restrict__ perm, int64_t n, int64_t d,
+                                   double *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t a = warp; a < n; a += nwarps) {
+    const double *src = X + (int64_t)perm[a] * d;
+    double *dst = out + a * d;
+    for (int64_t k = lane; k < d; k += 32) dst[k] = src[k];
   }
 }
 
@@ -361,6 +420,61 @@ static int warp_grid(int64_t n_rows, int threads) {
 
 using namespace meld;
 
+// perm[a] = original index of the cell placed at position a; Xp = X rows in that order.
+static int morton_order(const double *X, int64_t n, int64_t d, cudaStream_t stream, DevBuf<int32_t> &perm,
+                        DevBuf<double> &Xp) {
+  DevBuf<double> partial, mu, var;
+  MELD_CHECK(partial.alloc((size_t)kMeanBlocks * d));
+  MELD_CHECK(mu.alloc((size_t)d));
+  MELD_CHECK(var.alloc((size_t)d));
+  col_partial_sums_kernel<<<kMeanBlocks, 256, 0, stream>>>(X, n, d, partial.p);
+  MELD_LAUNCH_CHECK();
+  col_mean_kernel<<<(unsigned)ceil_div(d, 256), 256, 0, stream>>>(partial.p, n, d, kMeanBlocks, mu.p);
+  MELD_LAUNCH_CHECK();
+  col_partial_sq_kernel<<<kMeanBlocks, 256, 0, stream>>>(X, mu.p, n, d, partial.p);
+  MELD_LAUNCH_CHECK();
+  col_mean_kernel<<<(unsigned)ceil_div(d, 256), 256, 0, stream>>>(partial.p, n, d, kMeanBlocks, var.p);
+  MELD_LAUNCH_CHECK();
+  std::vector<double> h_mu((size_t)d), h_var((size_t)d);
+  MELD_CUDA(cudaMemcpyAsync(h_mu.data(), mu.p, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  MELD_CUDA(cudaMemcpyAsync(h_var.data(), var.p, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  MELD_CUDA(cudaStreamSynchronize(stream));
+  std::vector<int> order((size_t)d);
+  for (int64_t k = 0; k < d; ++k) order[(size_t)k] = (int)k;
+  const int ndim = d < 4 ? (int)d : 4;
+  std::partial_sort(order.begin(), order.begin() + ndim, order.end(),
+                    [&](int a, int b) { return h_var[a] > h_var[b] || (h_var[a] == h_var[b] && a < b); });
+  MortonDims md;
+  md.ndim = ndim;
+  for (int k = 0; k < 4; ++k) {
+    const int dim = k < ndim ? order[(size_t)k] : 0;
+    md.dim[k] = dim;
+    md.mu[k] = h_mu[(size_t)dim];
+    const double sd = sqrt(h_var[(size_t)dim]);
+    md.inv_range[k] = sd > 0 ? 1.0 / (12.0 * sd) : 0.0;
+  }
+  DevBuf<unsigned long long> keys, keys_sorted;
+  DevBuf<int32_t> idx;
+  MELD_CHECK(keys.alloc((size_t)n));
+  MELD_CHECK(keys_sorted.alloc((size_t)n));
+  MELD_CHECK(idx.alloc((size_t)n));
+  MELD_CHECK(perm.alloc((size_t)n));
+  morton_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(X, n, d, md, keys.p, idx.p);
+  MELD_LAUNCH_CHECK();
+  size_t tmp_bytes = 0;
+  MELD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
+                                            stream));
+  DevBuf<unsigned char> tmp;
+  MELD_CHECK(tmp.alloc(tmp_bytes));
+  MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
+                                            stream));
+  MELD_CHECK(Xp.alloc((size_t)n * d));
+  gather_rows_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(X, perm.p, n, d, Xp.p);
+  MELD_LAUNCH_CHECK();
+  MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
+  return 0;
+}
+
 // Steps 0 and 1: centred norms, pass 1 (eps upper bounds), pass 2 (candidate lists).
 static int candidate_search(const double *X, int64_t n, int64_t d, int k1, double radius_factor, bool simt,
                             cudaStream_t stream, DevBuf<float> &key2, DevBuf<int32_t> &cand, DevBuf<int32_t> &cnt,
@@ -450,6 +564,14 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   if (radius_factor < 1.0) radius_factor = 1.0;  // the k1 nearest must be candidates to get eps_i
   const bool simt = (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0;
   const bool keep_raw = (flags & MELD_B200_FLAG_KEEP_KNN_KERNEL) != 0;
+
+  // -- 0a. internal cell order (Morton curve over the highest-variance features)
+  DevBuf<double> Xp;
+  DevBuf<int32_t> perm;
+  if (tuning().reorder && n >= 4096) {
+    MELD_CHECK(morton_order(X, n, d, stream, perm, Xp));
+    X = Xp.p;
+  }
 
   // -- 0./1. means, norms, candidate search
   DevBuf<float> key2;
@@ -580,6 +702,12 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     MELD_CUDA(cudaStreamSynchronize(stream));
   }
   MELD_CHECK(graph_finalize(g, stream));
+  if (perm.p) {
+    g->perm.p = perm.p;  // hand the buffer over to the graph
+    g->perm.n = perm.n;
+    perm.p = nullptr;
+    perm.n = 0;
+  }
   g->stats[0] = passes;
   g->stats[1] = h_max[0];
   g->stats[2] = cap;
@@ -611,6 +739,15 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   MELD_CUDA(cudaMemcpyAsync(cnt_out, cnt.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
   MELD_CUDA(cudaStreamSynchronize(stream));
   if (cap_host) *cap_host = cap;
+  return 0;
+}
+
+int meld_b200_graph_permutation(const meld_b200_graph_t *g, int32_t *perm_out, int *is_identity_host, void *stream_) {
+  MELD_REQUIRE(g && is_identity_host, "graph_permutation: NULL argument");
+  *is_identity_host = g->perm.p ? 0 : 1;
+  if (g->perm.p && perm_out)
+    MELD_CUDA(cudaMemcpyAsync(perm_out, g->perm.p, (size_t)g->n_rows * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream_));
   return 0;
 }
 

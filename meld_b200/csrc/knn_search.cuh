@@ -32,6 +32,7 @@ struct SearchState {
   DevBuf<float> xc32;  // n x d centred float32
   DevBuf<float> hn32;  // -n_j / 2
   // tcgen05
+  DevBuf<float> thr_g;    // n_pad running pass-1 bounds
   DevBuf<uint16_t> a_op;  // n_pad x kp bf16, row operand
   DevBuf<uint16_t> b_op;  // n_pad x kp bf16, column operand (carries -n_j/2 in its tail columns)
   alignas(64) unsigned char tmap_a[128];

@@ -165,6 +165,7 @@ int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, int
 void search_release(SearchState *st) {
   st->xc32.release();
   st->hn32.release();
+  st->thr_g.release();
   st->a_op.release();
   st->b_op.release();
 }

@@ -22,13 +22,11 @@
 namespace meld {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;
 constexpr int kTcThreads = 192;
 constexpr int kABytes = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;   // 32 KB
 constexpr int kMaxResidentKb = 6;      // A resident up to K' = 384
-constexpr int kARegion = kMaxResidentKb * kABytes;  // 96 KB
-constexpr int kBRegion = kStages * kBBytes;         // 96 KB
 constexpr float kPadSentinel = -1e30f;
 
 // ---- operand preparation ------------------------------------------------------------------------
@@ -72,6 +70,10 @@ __global__ void tc_prep_kernel(const double *__restrict__ X, const double *__res
   }
 }
 
+__global__ void fill_float_kernel(float *p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,6 +105,30 @@ __device__ __forceinline__ void tma_load_2d(const void *tmap, uint64_t *bar, voi
           s32(dst)),
       "l"(tmap), "r"(s32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const void *tmap, uint64_t *bar, void *dst, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(s32(dst)),
+      "l"(tmap), "r"(s32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          s32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -151,6 +177,10 @@ struct TcArgs {
   int mode;  // 1: top-k1 lists, 2: emit candidates
   int64_t n;
   int n_row_tiles, n_col_tiles, nseg, nkb, a_resident, k1;
+  int mc;         // 1: launched as 2-CTA clusters, B tiles are multicast between the pair
+  int n_stages;   // B (or A+B) ring depth
+  int a_region;   // bytes reserved for the A operand (resident k-blocks, or one A tile per stage)
+  float *thr_g;   // pass 1: per-row running lower bound of the k1-th largest s (carried across segments)
   float *lists;
   const float *key2;
   int32_t *cand;
@@ -159,8 +189,8 @@ struct TcArgs {
 };
 
 struct Bars {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t a_full, a_empty;
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
@@ -171,13 +201,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                      const TcArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int kStages = a.n_stages;
   unsigned char *smA = smem;                   // resident A (nkb x 16 KB) or A stages
-  unsigned char *smB = smem + kARegion;        // B stages
-  float *lst = reinterpret_cast<float *>(smem + kARegion + kBRegion);  // [k1][128] (pass 1)
-  Bars *bars = reinterpret_cast<Bars *>(smem + kARegion + kBRegion + (size_t)(a.mode == 1 ? a.k1 : 0) * BM * 4);
+  unsigned char *smB = smem + a.a_region;      // B stages
+  float *lst = reinterpret_cast<float *>(smB + (size_t)kStages * kBBytes);  // [k1][128] (pass 1)
+  Bars *bars = reinterpret_cast<Bars *>(reinterpret_cast<unsigned char *>(lst) + (size_t)(a.mode == 1 ? a.k1 : 0) * BM * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Work units are (segment, row tile), segment-major.  With multicast the two CTAs of a cluster take
+  // adjacent row tiles of the same segment and walk identical column-tile sequences in lockstep.
   const int n_units = a.n_row_tiles * a.nseg;
+  const uint32_t crank = a.mc ? cluster_ctarank() : 0u;
+  const int u_first = a.mc ? 2 * (int)(blockIdx.x >> 1) + (int)crank : (int)blockIdx.x;
+  const int u_step = (int)gridDim.x;  // even when clustered
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -187,7 +223,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         bar_init(&bars->full[s], 1);
-        bar_init(&bars->empty[s], 1);
+        bar_init(&bars->empty[s], a.mc ? 2 : 1);  // clustered: both CTAs' MMAs must release a stage
       }
       bar_init(&bars->a_full, 1);
       bar_init(&bars->a_empty, 1);
@@ -205,6 +241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (a.mc) cluster_sync_all();  // peer barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -213,8 +250,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, uphase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int rt = u / a.nseg, seg = u % a.nseg;
+      for (int u = u_first; u < n_units; u += u_step) {
+        const int seg = u / a.n_row_tiles, rt = u % a.n_row_tiles;  // segment-major: concurrent CTAs share B's L2 slice
         const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
         const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
         if (a.a_resident) {
@@ -226,7 +263,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           for (int kb = 0; kb < a.nkb; ++kb) {
             bar_wait(&bars->empty[stage], phase ^ 1u);
             bar_expect_tx(&bars->full[stage], a.a_resident ? kBBytes : kBBytes + kABytes);
-            tma_load_2d(&tmap_b, &bars->full[stage], smB + stage * kBBytes, kb * BK, ct * BN);
+            if (a.mc) {  // my half of the B tile, delivered to both CTAs of the pair
+              tma_load_2d_mc(&tmap_b, &bars->full[stage], smB + stage * kBBytes + crank * (kBBytes / 2), kb * BK,
+                             ct * BN + (int)crank * (BN / 2), (uint16_t)0x3);
+            } else {
+              tma_load_2d(&tmap_b, &bars->full[stage], smB + stage * kBBytes, kb * BK, ct * BN);
+              tma_load_2d(&tmap_b, &bars->full[stage], smB + stage * kBBytes + kBBytes / 2, kb * BK, ct * BN + BN / 2);
+            }
             if (!a.a_resident) tma_load_2d(&tmap_a, &bars->full[stage], smA + stage * kABytes, kb * BK, rt * BM);
             if (++stage == kStages) {
               stage = 0;
@@ -243,8 +286,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0, buf = 0;
       uint32_t phase = 0, bphase = 0, uphase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int seg = u % a.nseg;
+      for (int u = u_first; u < n_units; u += u_step) {
+        const int seg = u / a.n_row_tiles;
         const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
         const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
         if (a.a_resident) {
@@ -265,7 +308,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               tc_mma_bf16(tmem_d, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
                           (uint32_t)((kb | k) != 0));
             }
-            tc_commit(&bars->empty[stage]);  // stage reusable once these MMAs retire
+            if (a.mc)
+              tc_commit_mc(&bars->empty[stage], (uint16_t)0x3);  // releases the stage in both CTAs
+            else
+              tc_commit(&bars->empty[stage]);  // stage reusable once these MMAs retire
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
@@ -285,15 +331,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int rin = q * 32 + lane;
     int buf = 0;
     uint32_t bphase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int rt = u / a.nseg, seg = u % a.nseg;
+    for (int u = u_first; u < n_units; u += u_step) {
+      const int seg = u / a.n_row_tiles, rt = u % a.n_row_tiles;
       const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
       const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
       const int64_t row = (int64_t)rt * BM + rin;
       float thr;
       if (a.mode == 1) {
         for (int s = 0; s < a.k1; ++s) lst[s * BM + rin] = -INFINITY;
-        thr = -INFINITY;
+        // start from the bound earlier segments of this row have published: values below it cannot be
+        // among the k1 largest of the union, so this list only needs what beats it
+        thr = row < a.n ? __ldcg(a.thr_g + row) : INFINITY;
       } else {
         thr = row < a.n ? a.key2[row] : INFINITY;
       }
@@ -301,36 +349,53 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         bar_wait(&bars->tmem_full[buf], bphase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
-          uint32_t v[32];
-          tmem_ld32(tbase + chunk * 32, v);
-          tmem_ld_wait();
+        // Branch-free fast path: one max over the 32 columns of a chunk and a single compare; only a
+        // chunk that holds a hit is scanned element by element.  Two chunks are kept in flight so the
+        // TMEM load of the next one overlaps the scan of the current one.
+        auto scan = [&](const uint32_t (&v)[32], int chunk) {
+          float mx = __uint_as_float(v[0]);
+#pragma unroll
+          for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
           const int col0 = ct * BN + chunk * 32;
           if (a.mode == 1) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float s = __uint_as_float(v[c]);
-              if (s > thr) {
-                int pos = a.k1 - 1;
-                while (pos > 0 && lst[(pos - 1) * BM + rin] < s) {
-                  lst[pos * BM + rin] = lst[(pos - 1) * BM + rin];
-                  --pos;
+            if (mx > thr) {
+#pragma unroll  // static register indices (a dynamic index would spill v to local memory)
+              for (int c = 0; c < 32; ++c) {
+                const float s = __uint_as_float(v[c]);
+                if (s > thr) {
+                  int pos = a.k1 - 1;
+                  while (pos > 0 && lst[(pos - 1) * BM + rin] < s) {
+                    lst[pos * BM + rin] = lst[(pos - 1) * BM + rin];
+                    --pos;
+                  }
+                  lst[pos * BM + rin] = s;
+                  thr = fmaxf(thr, lst[(a.k1 - 1) * BM + rin]);
                 }
-                lst[pos * BM + rin] = s;
-                thr = lst[(a.k1 - 1) * BM + rin];
               }
             }
           } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float s = __uint_as_float(v[c]);
-              if (s >= thr) {
-                const int pos = atomicAdd(a.cnt + row, 1);
-                if (pos < a.cap) a.cand[(size_t)row * a.cap + pos] = col0 + c;
+            if (mx >= thr) {
+#pragma unroll  // static register indices (a dynamic index would spill v to local memory)
+              for (int c = 0; c < 32; ++c) {
+                const float s = __uint_as_float(v[c]);
+                if (s >= thr) {
+                  const int pos = atomicAdd(a.cnt + row, 1);
+                  if (pos < a.cap) a.cand[(size_t)row * a.cap + pos] = col0 + c;
+                }
               }
             }
           }
+        };
+        uint32_t va[32], vb[32];
+        tmem_ld32(tbase, va);
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; chunk += 2) {
+          tmem_ld_wait();
+          tmem_ld32(tbase + (chunk + 1) * 32, vb);
+          scan(va, chunk);
+          tmem_ld_wait();
+          if (chunk + 2 < BN / 32) tmem_ld32(tbase + (chunk + 2) * 32, va);
+          scan(vb, chunk + 1);
         }
         tc_fence_before();
         __syncwarp();
@@ -341,12 +406,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (a.mode == 1 && row < a.n) {
         float *out = a.lists + ((size_t)row * a.nseg + seg) * a.k1;
         for (int s = 0; s < a.k1; ++s) out[s] = lst[s * BM + rin];
+        // publish (monotone max; floats >= 0 and < 0 both ordered through the signed/unsigned trick)
+        const float mine = lst[(a.k1 - 1) * BM + rin];
+        if (mine > -INFINITY) {
+          if (mine >= 0.f)
+            atomicMax(reinterpret_cast<int *>(a.thr_g + row), __float_as_int(mine));
+          else
+            atomicMin(reinterpret_cast<unsigned int *>(a.thr_g + row), __float_as_uint(mine));
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (a.mc) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA until it is done too
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -398,8 +472,13 @@ int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan) {
   plan->kp = (int)kp;
   plan->n_pad = round_up(n, BN);
   const int64_t row_tiles = plan->n_pad / BM, col_tiles = plan->n_pad / BN;
-  // enough (row tile, segment) units for ~4 waves of the SMs, never more segments than column tiles
+  // enough (row tile, segment) units for ~4 waves of the SMs, never more segments than column tiles;
+  // and a segment's slice of the column operand (n_seg x K' bf16) should stay L2 resident while the
+  // CTAs of that segment stream it (units are issued segment-major)
   int64_t nseg = ceil_div(4 * (int64_t)sm_count(), row_tiles);
+  const int64_t l2_slice = (int64_t)40 << 20;
+  const int64_t nseg_l2 = ceil_div(plan->n_pad * kp * 2, l2_slice);
+  if (nseg < nseg_l2) nseg = nseg_l2;
   if (nseg > kMaxLists) nseg = kMaxLists;
   if (nseg > col_tiles) nseg = col_tiles;
   if (nseg < 1) nseg = 1;
@@ -412,6 +491,13 @@ int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan) {
 
 int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
                SearchState *st) {
+  MELD_CHECK(st->thr_g.alloc((size_t)plan.n_pad));
+  {
+    // -inf bit pattern 0xff800000 in every float
+    MELD_CUDA(cudaMemsetAsync(st->thr_g.p, 0, (size_t)plan.n_pad * sizeof(float), stream));
+    fill_float_kernel<<<sm_count() * 4, 256, 0, stream>>>(st->thr_g.p, plan.n_pad, -INFINITY);
+    MELD_LAUNCH_CHECK();
+  }
   MELD_CHECK(st->a_op.alloc((size_t)plan.n_pad * plan.kp));
   MELD_CHECK(st->b_op.alloc((size_t)plan.n_pad * plan.kp));
   tc_prep_kernel<<<sm_count() * 8, 256, 0, stream>>>(X, mu, norm, plan.n, plan.n_pad, plan.d, plan.kp,
@@ -419,7 +505,7 @@ int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const 
                                                      reinterpret_cast<__nv_bfloat16 *>(st->b_op.p));
   MELD_LAUNCH_CHECK();
   MELD_CHECK(encode_operand_map(st->a_op.p, plan.n_pad, plan.kp, BM, st->tmap_a));
-  MELD_CHECK(encode_operand_map(st->b_op.p, plan.n_pad, plan.kp, BN, st->tmap_b));
+  MELD_CHECK(encode_operand_map(st->b_op.p, plan.n_pad, plan.kp, BN / 2, st->tmap_b));  // half tiles
   return 0;
 }
 
@@ -435,20 +521,46 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   a.a_resident = a.nkb <= kMaxResidentKb ? 1 : 0;
   a.k1 = plan.k1;
   a.lists = lists;
+  a.thr_g = st.thr_g.p;
   a.key2 = key2;
   a.cand = cand;
   a.cnt = cnt;
   a.cap = cap;
-  const size_t smem = 1024 + (size_t)kARegion + kBRegion + (mode == 1 ? (size_t)plan.k1 * BM * 4 : 0) + sizeof(Bars);
-  MELD_REQUIRE(smem <= 227 * 1024, "tc_search: %zu bytes of shared memory (knn too large)", smem);
+  const size_t list_bytes = mode == 1 ? (size_t)plan.k1 * BM * 4 : 0;
+  const size_t fixed = 1024 + list_bytes + sizeof(Bars);
+  const size_t budget = 227 * 1024;
+  if (a.a_resident) {
+    a.a_region = a.nkb * kABytes;
+    a.n_stages = (int)((budget - fixed - a.a_region) / kBBytes);
+  } else {
+    a.n_stages = (int)((budget - fixed) / (kBBytes + kABytes));
+    a.a_region = a.n_stages * kABytes;
+  }
+  if (a.n_stages > kMaxStages) a.n_stages = kMaxStages;
+  MELD_REQUIRE(a.n_stages >= 2, "tc_search: shared memory too small for a pipeline (knn too large)");
+  const size_t smem = fixed + a.a_region + (size_t)a.n_stages * kBBytes;
   MELD_CUDA(cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUtensorMap ma, mb;
   memcpy(&ma, st.tmap_a, sizeof(ma));
   memcpy(&mb, st.tmap_b, sizeof(mb));
   int grid = sm_count();
-  const int units = a.n_row_tiles * a.nseg;
+  const int units = a.n_row_tiles * a.nseg;  // n_row_tiles is even (n_pad is a multiple of 256)
   if (grid > units) grid = units;
-  tc_search_kernel<<<grid, kTcThreads, smem, stream>>>(ma, mb, a);
+  a.mc = tuning().tc_multicast && grid >= 2 ? 1 : 0;
+  if (a.mc) grid &= ~1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = a.mc ? 1 : 0;
+  MELD_CUDA(cudaLaunchKernelEx(&cfg, tc_search_kernel, ma, mb, a));
   MELD_LAUNCH_CHECK();
   return 0;
 }

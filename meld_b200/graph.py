@@ -130,7 +130,23 @@ class DeviceGraph:
             (data[:nnz].cpu().numpy(), indices[:nnz].cpu().numpy(), indptr.cpu().numpy()),
             shape=(self.n_rows, self.n_cols),
         )
+        perm = self.permutation()
+        if perm is not None:  # rows / columns back to the caller's cell order
+            coo = M.tocoo()
+            M = sparse.csr_matrix((coo.data, (perm[coo.row], perm[coo.col])), shape=M.shape)
+        M.sort_indices()
         return M
+
+    def permutation(self):
+        """Internal cell order: graph row a is the caller's cell ``perm[a]`` (None = identity)."""
+        torch = nv.require_cuda()
+        ident = C.c_int(1)
+        perm = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
+        nv.check(nv.lib().meld_b200_graph_permutation(self._h, nv.ptr(perm), C.byref(ident), nv.current_stream_ptr()),
+                 "graph_permutation")
+        if ident.value:
+            return None
+        return perm.cpu().numpy().astype(np.int64)
 
     def to_scipy_L(self):
         return self._export(self.nnz, nv.lib().meld_b200_graph_export_csr, "graph_export_csr")
@@ -154,7 +170,8 @@ class DeviceGraph:
     def build_stats(self):
         arr = (C.c_int64 * 8)()
         nv.check(nv.lib().meld_b200_graph_build_stats(self._h, arr), "graph_build_stats")
-        keys = ["search_passes", "max_candidates", "candidate_cap", "overflow_rows", "search_impl"]
+        keys = ["search_passes", "max_candidates", "candidate_cap", "overflow_rows", "search_impl", "dict_total",
+                "direct_blocks", "row_blocks"]
         return {k: int(arr[i]) for i, k in enumerate(keys)}
 
     # ---- lifetime ------------------------------------------------------------------------

@@ -30,6 +30,8 @@ def main():
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     knn = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     only_tc = len(sys.argv) > 4 and sys.argv[4] == "tc"
+    if len(sys.argv) > 5:
+        nv.set_tuning(tc_multicast=int(sys.argv[5]))
     Xh, _ = synthetic.make_blobs(n, d, 8, 3, 10.0, seed=3)
     X = torch.from_numpy(Xh).cuda()
     k_tc, c_tc, cap_tc, t_tc = search(X, knn, False)

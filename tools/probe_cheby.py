@@ -78,7 +78,8 @@ def main():
     ]
     if args.configs:
         configs = json.loads(args.configs)
-    base = dict(blk_chunk=1536, stage_cap=2048, n_stage=3, threads=128, ctas_per_sm=3, group=0)
+    base = dict(blk_chunk=1024, stage_cap=1280, dict_cap=640, row_cap=128, n_stage=0, threads=512, gather_warps=3,
+                ctas_per_sm=1, group=0, use_dict=1)
     for cfg in configs:
         full = dict(base)
         full.update(cfg)
