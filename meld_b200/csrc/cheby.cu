@@ -95,6 +95,7 @@ struct StepArgs {
   int rows_cap;    // rows whose T/R slices are staged
   int n_stage;     // pipeline depth
   int gather_warps;
+  int team_warps;  // compute warps per team (one team per in-flight block)
   int stage_epi;   // 1: the T/R arrays are library workspace (padded), slices may be bulk-copied
   int stage_bytes;
 };
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
     for (int s = 0; s < ns; ++s) {
       mbar_init(&full_mat[s], 1);
       mbar_init(&full_x[s], (uint32_t)a.gather_warps * 32u);
-      mbar_init(&empty[s], (uint32_t)n_compute_warps);
+      mbar_init(&empty[s], (uint32_t)a.team_warps);
     }
     fence_barrier_init();
   }
@@ -339,60 +340,67 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
       if (g.staged) {
         const int32_t *sd = reinterpret_cast<const int32_t *>(st + off_d);
         double *xs = reinterpret_cast<double *>(st + off_x);
-        for (int t = gt; t < g.u; t += ngt) {
+        // consecutive lanes copy consecutive chunks of the same row, so the lanes of one row hit one
+        // 128-byte line (one L1 wavefront) instead of one line per chunk
+        constexpr int CH = (P % 2 == 0) ? P / 2 : P;   // chunks per row: 16 B (even P) or 8 B (odd P)
+        const int ch = gt % CH, row_lanes = ngt / CH;  // lanes beyond row_lanes * CH sit out (odd P only)
+        for (int t = gt / CH; t < g.u && gt < row_lanes * CH; t += row_lanes) {
           const double *src = a.Tcur + (size_t)sd[t] * P;
           double *dst = xs + (size_t)t * P;
-          if constexpr (P % 2 == 0) {
-#pragma unroll
-            for (int k = 0; k < P; k += 2) cp_async16(dst + k, src + k);
-          } else {
-#pragma unroll
-            for (int k = 0; k < P; ++k) cp_async8(dst + k, src + k);
-          }
+          if constexpr (P % 2 == 0)
+            cp_async16(dst + 2 * ch, src + 2 * ch);
+          else
+            cp_async8(dst + ch, src + ch);
         }
       }
       cp_async_arrive_noinc(&full_x[s]);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
   } else {
-    // ===== compute warps =====
-    const int ct = (warp - 1 - a.gather_warps) * 32 + lane;
-    const int ngroups = n_compute_warps * 32 / G;
+    // ===== compute warps, in teams: team j owns blocks it = j, j + n_teams, ... so several stages are
+    // multiplied concurrently and a small block (a dozen rows) still keeps every lane of its team busy
+    const int cw = warp - 1 - a.gather_warps;
+    const int team = cw / a.team_warps, wit = cw % a.team_warps;
+    const int n_teams = n_compute_warps / a.team_warps;
+    const int ct = wit * 32 + lane;
+    const int ngroups = a.team_warps * 32 / G;
     const int gid = ct / G, gl = ct % G;
-    int it = 0;
-    for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
-      const int s = it % ns;
-      const uint32_t ph = (uint32_t)(it / ns) & 1u;
-      unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
-      const BlockGeom g = block_geom<P>(a, b);
-      mbar_wait(&full_mat[s], ph);
-      mbar_wait(&full_x[s], ph);
-      BlockView bv;
-      if (g.staged) {
-        bv.vs = reinterpret_cast<const double *>(st) - g.a0;
-        bv.ls = reinterpret_cast<const uint16_t *>(st + off_l) - g.a0;
-        bv.cs = nullptr;
-        bv.rp = reinterpret_cast<const int32_t *>(st + off_r) - g.ra;
-        bv.xs = reinterpret_cast<const double *>(st + off_x);
-        if (g.epi_staged) {
-          bv.tc = reinterpret_cast<const double *>(st + off_tc) - g.sc0 + (size_t)a.row0 * P;  // indexed by local row
-          bv.told = (a.gamma != 0.0) ? reinterpret_cast<const double *>(st + off_to) - g.sl0 : nullptr;
-          bv.rold = (a.R != nullptr && a.r_acc) ? reinterpret_cast<const double *>(st + off_ro) - g.sl0 : nullptr;
+    if (team < n_teams) {
+      for (int it = team; blockIdx.x + (long long)it * stride < a.n_blk; it += n_teams) {
+        const int b = blockIdx.x + it * stride;
+        const int s = it % ns;
+        const uint32_t ph = (uint32_t)(it / ns) & 1u;
+        unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
+        const BlockGeom g = block_geom<P>(a, b);
+        mbar_wait(&full_mat[s], ph);
+        mbar_wait(&full_x[s], ph);
+        BlockView bv;
+        if (g.staged) {
+          bv.vs = reinterpret_cast<const double *>(st) - g.a0;
+          bv.ls = reinterpret_cast<const uint16_t *>(st + off_l) - g.a0;
+          bv.cs = nullptr;
+          bv.rp = reinterpret_cast<const int32_t *>(st + off_r) - g.ra;
+          bv.xs = reinterpret_cast<const double *>(st + off_x);
+          if (g.epi_staged) {
+            bv.tc = reinterpret_cast<const double *>(st + off_tc) - g.sc0 + (size_t)a.row0 * P;  // indexed by local row
+            bv.told = (a.gamma != 0.0) ? reinterpret_cast<const double *>(st + off_to) - g.sl0 : nullptr;
+            bv.rold = (a.R != nullptr && a.r_acc) ? reinterpret_cast<const double *>(st + off_ro) - g.sl0 : nullptr;
+          } else {
+            bv.tc = bv.told = bv.rold = nullptr;
+          }
+          process_rows<P, G, true>(a, bv, g.r0, g.r1, gid, gl, ngroups);
         } else {
+          bv.vs = a.val;
+          bv.ls = nullptr;
+          bv.cs = a.col;
+          bv.rp = a.row_ptr;
+          bv.xs = nullptr;
           bv.tc = bv.told = bv.rold = nullptr;
+          process_rows<P, G, false>(a, bv, g.r0, g.r1, gid, gl, ngroups);
         }
-        process_rows<P, G, true>(a, bv, g.r0, g.r1, gid, gl, ngroups);
-      } else {
-        bv.vs = a.val;
-        bv.ls = nullptr;
-        bv.cs = a.col;
-        bv.rp = a.row_ptr;
-        bv.xs = nullptr;
-        bv.tc = bv.told = bv.rold = nullptr;
-        process_rows<P, G, false>(a, bv, g.r0, g.r1, gid, gl, ngroups);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
     }
   }
 }
@@ -457,10 +465,12 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
   a.rcap = g->row_cap + 8;
   a.rows_cap = g->row_cap;
   a.gather_warps = t.gather_warps;
+  a.team_warps = t.team_warps;
   a.stage_epi = stage_epi;
   const int threads = t.threads;
   MELD_REQUIRE(threads % 32 == 0 && threads >= 96 && threads <= 512 && t.gather_warps >= 1 &&
-                   threads / 32 - 1 - t.gather_warps >= 1,
+                   t.team_warps >= 1 && threads / 32 - 1 - t.gather_warps >= t.team_warps &&
+                   (t.gather_warps * 32) % 8 == 0,
                "cheby_step: bad tuning (threads=%d gather_warps=%d)", threads, t.gather_warps);
   const size_t epi_len = (size_t)a.rows_cap * P + 2;
   size_t stage = (size_t)a.cap * 10 + (size_t)a.rcap * 4 + (size_t)a.ucap * 4 + (size_t)a.ucap * P * 8 + 3 * epi_len * 8;

@@ -54,13 +54,14 @@ int sm_count();
 // Launch configuration of the Chebyshev SpMM kernel (see cheby.cu).  The defaults are
 // the shipped configuration; meld_b200_set_tuning changes them for bench sweeps.
 struct Tuning {
-  int blk_chunk = 1024;   // target CSR entries per row block (C)
-  int stage_cap = 1280;   // CSR entries of shared memory per pipeline stage (multiple of 8, <= 2048)
-  int dict_cap = 640;     // distinct columns (dictionary entries) per stage (multiple of 4)
-  int row_cap = 128;      // rows per stage whose own T / R slices are staged (multiple of 8)
+  int blk_chunk = 768;    // target CSR entries per row block (C)
+  int stage_cap = 1024;   // CSR entries of shared memory per pipeline stage (multiple of 8, <= 2048)
+  int dict_cap = 768;     // distinct columns (dictionary entries) per stage (multiple of 4)
+  int row_cap = 64;       // rows per stage whose own T / R slices are staged (multiple of 8)
   int n_stage = 0;        // TMA pipeline depth per CTA (0 = as many as fit in shared memory)
   int threads = 512;      // threads per CTA: 1 producer warp + gather warps + compute warps
   int gather_warps = 3;
+  int team_warps = 4;     // compute warps per team; teams take alternate blocks
   int ctas_per_sm = 1;    // persistent CTAs per SM
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)
   int use_dict = 1;       // 0: every block takes the direct (global-memory) path

@@ -28,6 +28,7 @@ constexpr int kABytes = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;   // 32 KB
 constexpr int kMaxResidentKb = 6;      // A resident up to K' = 384
 constexpr float kPadSentinel = -1e30f;
+constexpr int kEmitSlots = 16;         // pass 2: hits staged per row before one atomicAdd reserves their slots
 
 // ---- operand preparation ------------------------------------------------------------------------
 __global__ void tc_prep_kernel(const double *__restrict__ X, const double *__restrict__ mu,
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   unsigned char *smA = smem;                   // resident A (nkb x 16 KB) or A stages
   unsigned char *smB = smem + a.a_region;      // B stages
   float *lst = reinterpret_cast<float *>(smB + (size_t)kStages * kBBytes);  // [k1][128] (pass 1)
-  Bars *bars = reinterpret_cast<Bars *>(reinterpret_cast<unsigned char *>(lst) + (size_t)(a.mode == 1 ? a.k1 : 0) * BM * 4);
+  Bars *bars = reinterpret_cast<Bars *>(reinterpret_cast<unsigned char *>(lst) + (size_t)(a.mode == 1 ? a.k1 : kEmitSlots) * BM * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work units are (segment, row tile), segment-major.  With multicast the two CTAs of a cluster take
@@ -345,6 +346,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       } else {
         thr = row < a.n ? a.key2[row] : INFINITY;
       }
+      int32_t *ebuf = reinterpret_cast<int32_t *>(lst);  // pass 2: [kEmitSlots][128] staged hits
+      int n_e = 0;
+      auto flush_hits = [&]() {
+        const int base = atomicAdd(a.cnt + row, n_e);
+        for (int i = 0; i < n_e; ++i)
+          if (base + i < a.cap) a.cand[(size_t)row * a.cap + base + i] = ebuf[i * BM + rin];
+        n_e = 0;
+      };
       for (int ct = ct0; ct < ct1; ++ct) {
         bar_wait(&bars->tmem_full[buf], bphase);
         tc_fence_after();
@@ -375,12 +384,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           } else {
             if (mx >= thr) {
-#pragma unroll  // static register indices (a dynamic index would spill v to local memory)
+#pragma unroll  // static register indices
               for (int c = 0; c < 32; ++c) {
                 const float s = __uint_as_float(v[c]);
                 if (s >= thr) {
-                  const int pos = atomicAdd(a.cnt + row, 1);
-                  if (pos < a.cap) a.cand[(size_t)row * a.cap + pos] = col0 + c;
+                  // stage the hit in this row's shared-memory slots; the global counter is touched once
+                  // per kEmitSlots hits, so the scan never waits on an atomic's round trip
+                  ebuf[n_e * BM + rin] = col0 + c;
+                  if (++n_e == kEmitSlots) {
+                    flush_hits();
+                  }
                 }
               }
             }
@@ -403,6 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         buf ^= 1;
         if (buf == 0) bphase ^= 1u;
       }
+      if (a.mode == 2 && n_e > 0) flush_hits();
       if (a.mode == 1 && row < a.n) {
         float *out = a.lists + ((size_t)row * a.nseg + seg) * a.k1;
         for (int s = 0; s < a.k1; ++s) out[s] = lst[s * BM + rin];
@@ -526,7 +540,7 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   a.cand = cand;
   a.cnt = cnt;
   a.cap = cap;
-  const size_t list_bytes = mode == 1 ? (size_t)plan.k1 * BM * 4 : 0;
+  const size_t list_bytes = (size_t)(mode == 1 ? plan.k1 : kEmitSlots) * BM * 4;
   const size_t fixed = 1024 + list_bytes + sizeof(Bars);
   const size_t budget = 227 * 1024;
   if (a.a_resident) {
