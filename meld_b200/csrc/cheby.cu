@@ -96,6 +96,7 @@ struct StepArgs {
   int n_stage;     // pipeline depth
   int gather_warps;
   int team_warps;  // compute warps per team (one team per in-flight block)
+  int gather_rows; // dictionary rows fetched per warp-level cp.async instruction
   int stage_epi;   // 1: the T/R arrays are library workspace (padded), slices may be bulk-copied
   int stage_bytes;
 };
@@ -329,7 +330,6 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
     }
   } else if (warp <= a.gather_warps) {
     // ===== gather warps: dictionary -> cp.async of the T_cur rows into the stage =====
-    const int gt = (warp - 1) * 32 + lane, ngt = a.gather_warps * 32;
     int it = 0;
     for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
       const int s = it % ns;
@@ -340,17 +340,23 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
       if (g.staged) {
         const int32_t *sd = reinterpret_cast<const int32_t *>(st + off_d);
         double *xs = reinterpret_cast<double *>(st + off_x);
-        // consecutive lanes copy consecutive chunks of the same row, so the lanes of one row hit one
-        // 128-byte line (one L1 wavefront) instead of one line per chunk
+        // Consecutive lanes copy consecutive chunks of the same row.  Only the first gather_rows * CH lanes
+        // of a warp are active per instruction: every distinct 128-byte line inside ONE warp-level request
+        // is replayed at ~2 L1 cycles, while separate requests stream at ~1 cycle each, so few rows per
+        // instruction keep the L1 pipe (the real bound of this kernel) at its best rate.
         constexpr int CH = (P % 2 == 0) ? P / 2 : P;   // chunks per row: 16 B (even P) or 8 B (odd P)
-        const int ch = gt % CH, row_lanes = ngt / CH;  // lanes beyond row_lanes * CH sit out (odd P only)
-        for (int t = gt / CH; t < g.u && gt < row_lanes * CH; t += row_lanes) {
-          const double *src = a.Tcur + (size_t)sd[t] * P;
-          double *dst = xs + (size_t)t * P;
-          if constexpr (P % 2 == 0)
-            cp_async16(dst + 2 * ch, src + 2 * ch);
-          else
-            cp_async8(dst + ch, src + ch);
+        const int rpi = min(a.gather_rows, 32 / CH);   // rows per warp instruction
+        const int gw = warp - 1;
+        if (lane < rpi * CH) {
+          const int ch = lane % CH;
+          for (int t = gw * rpi + lane / CH; t < g.u; t += a.gather_warps * rpi) {
+            const double *src = a.Tcur + (size_t)sd[t] * P;
+            double *dst = xs + (size_t)t * P;
+            if constexpr (P % 2 == 0)
+              cp_async16(dst + 2 * ch, src + 2 * ch);
+            else
+              cp_async8(dst + ch, src + ch);
+          }
         }
       }
       cp_async_arrive_noinc(&full_x[s]);
@@ -466,6 +472,7 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
   a.rows_cap = g->row_cap;
   a.gather_warps = t.gather_warps;
   a.team_warps = t.team_warps;
+  a.gather_rows = t.gather_rows < 1 ? 1 : t.gather_rows;
   a.stage_epi = stage_epi;
   const int threads = t.threads;
   MELD_REQUIRE(threads % 32 == 0 && threads >= 96 && threads <= 512 && t.gather_warps >= 1 &&

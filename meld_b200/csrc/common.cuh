@@ -61,13 +61,15 @@ struct Tuning {
   int n_stage = 0;        // TMA pipeline depth per CTA (0 = as many as fit in shared memory)
   int threads = 512;      // threads per CTA: 1 producer warp + gather warps + compute warps
   int gather_warps = 3;
+  int gather_rows = 16;   // dictionary rows per warp-level cp.async instruction (1..16)
   int team_warps = 4;     // compute warps per team; teams take alternate blocks
   int ctas_per_sm = 1;    // persistent CTAs per SM
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)
   int use_dict = 1;       // 0: every block takes the direct (global-memory) path
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
-  int tc_multicast = 1;   // candidate search: 2-CTA clusters sharing B tiles by TMA multicast
+  int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast
+  int p1_segments = 0;    // candidate search pass 1 scans this many column segments per row (own first; 0 = all)
 };
 Tuning &tuning();
 

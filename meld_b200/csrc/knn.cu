@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <vector>
 #include <float.h>
+#include <stdlib.h>
 #include <math.h>
 
 namespace meld {
@@ -167,17 +168,18 @@ __global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t n, i
 }
 
 // ---- 2. exact float64 distances of the candidates, eps_i ----------------------------------------
-// One warp per row.  d2buf[i*cap + t] receives the exact squared distance of candidate t.
+// One warp per row.  Candidates of row i are cand[cptr[i] .. cptr[i+1]); d2buf (same indexing) receives
+// the exact squared distances.
 __global__ void refine_dist_kernel(const double *__restrict__ X, int64_t n, int64_t d, const int32_t *__restrict__ cand,
-                                   const int32_t *__restrict__ cnt, int cap, int k1, double bandwidth_scale,
+                                   const int64_t *__restrict__ cptr, int k1, double bandwidth_scale,
                                    double *__restrict__ d2buf, double *__restrict__ eps, int *__restrict__ err_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp; i < n; i += nwarps) {
-    const int c = min(cnt[i], cap);
-    const int32_t *ci = cand + (size_t)i * cap;
-    double *di = d2buf + (size_t)i * cap;
+    const int c = (int)(cptr[i + 1] - cptr[i]);
+    const int32_t *ci = cand + cptr[i];
+    double *di = d2buf + cptr[i];
     const double *xi = X + i * d;
     for (int t = lane; t < c; t += 32) {
       const double *xj = X + (int64_t)ci[t] * d;
@@ -236,7 +238,7 @@ __device__ __forceinline__ double alpha_decay(double dist, double eps, double de
 // below thresh).  When K_ji is zero the mirrored entry (j, i) does not exist in row j's own list and
 // must be appended there: the slot is flagged (column stored as ~j) and extra[j] is bumped.
 // kraw (optional) keeps the un-symmetrised K_ij for export.
-__global__ void kernel_values_kernel(int64_t n, int32_t *__restrict__ cand, const int32_t *__restrict__ cnt, int cap,
+__global__ void kernel_values_kernel(int64_t n, int32_t *__restrict__ cand, const int64_t *__restrict__ cptr,
                                      double *__restrict__ d2buf, const double *__restrict__ eps, double decay,
                                      double thresh, int32_t *__restrict__ kept, int32_t *__restrict__ extra,
                                      double *__restrict__ kraw) {
@@ -244,9 +246,9 @@ __global__ void kernel_values_kernel(int64_t n, int32_t *__restrict__ cand, cons
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp; i < n; i += nwarps) {
-    const int c = min(cnt[i], cap);
-    int32_t *ci = cand + (size_t)i * cap;
-    double *di = d2buf + (size_t)i * cap;
+    const int c = (int)(cptr[i + 1] - cptr[i]);
+    int32_t *ci = cand + cptr[i];
+    double *di = d2buf + cptr[i];
     const double ei = eps[i];
     int nk = 0;
     for (int t = lane; t < c; t += 32) {
@@ -257,7 +259,7 @@ __global__ void kernel_values_kernel(int64_t n, int32_t *__restrict__ cand, cons
         double kji = (j == (int32_t)i) ? kij : alpha_decay(dist, eps[j], decay);
         if (kji < thresh) kji = 0.0;
         di[t] = (kij + kji) / 2;
-        if (kraw) kraw[(size_t)i * cap + t] = kij;
+        if (kraw) kraw[cptr[i] + t] = kij;
         if (kji == 0.0) {
           ci[t] = ~j;
           atomicAdd(extra + j, 1);
@@ -281,7 +283,7 @@ __global__ void add_counts_kernel(const int32_t *__restrict__ a, const int32_t *
 
 // Scatter the kept slots into the CSR rows: own entries first (compacted in slot order), mirrored
 // entries of flagged slots appended behind row j's own entries through an atomic cursor.
-__global__ void fill_sym_kernel(int64_t n, const int32_t *__restrict__ cand, const int32_t *__restrict__ cnt, int cap,
+__global__ void fill_sym_kernel(int64_t n, const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr,
                                 const double *__restrict__ vbuf, const int32_t *__restrict__ row_ptr,
                                 const int32_t *__restrict__ kept, int32_t *__restrict__ cursor,
                                 int32_t *__restrict__ col, double *__restrict__ val) {
@@ -289,9 +291,9 @@ __global__ void fill_sym_kernel(int64_t n, const int32_t *__restrict__ cand, con
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp; i < n; i += nwarps) {
-    const int c = min(cnt[i], cap);
-    const int32_t *ci = cand + (size_t)i * cap;
-    const double *vi = vbuf + (size_t)i * cap;
+    const int c = (int)(cptr[i + 1] - cptr[i]);
+    const int32_t *ci = cand + cptr[i];
+    const double *vi = vbuf + cptr[i];
     int base = row_ptr[i];
     for (int t0 = 0; t0 < c; t0 += 32) {
       const int t = t0 + lane;
@@ -321,25 +323,25 @@ __global__ void fill_sym_kernel(int64_t n, const int32_t *__restrict__ cand, con
 }
 
 // Compact the un-symmetrised kernel (slot order -> sorted later on the host side of the test).
-__global__ void fill_raw_kernel(int64_t n, const int32_t *__restrict__ cand, const int32_t *__restrict__ cnt, int cap,
+__global__ void fill_raw_kernel(int64_t n, const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr,
                                 const double *__restrict__ kraw, const int64_t *__restrict__ out_ptr,
                                 int32_t *__restrict__ col, double *__restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp; i < n; i += nwarps) {
-    const int c = min(cnt[i], cap);
+    const int c = (int)(cptr[i + 1] - cptr[i]);
     int64_t base = out_ptr[i];
     for (int t0 = 0; t0 < c; t0 += 32) {
       const int t = t0 + lane;
       int32_t j = INT32_MIN;
-      if (t < c) j = cand[(size_t)i * cap + t];
+      if (t < c) j = cand[cptr[i] + t];
       const bool live = j != INT32_MIN;
       const unsigned m = __ballot_sync(0xffffffffu, live);
       if (live) {
         const int64_t pos = base + __popc(m & ((1u << lane) - 1u));
         col[pos] = j < 0 ? ~j : j;
-        val[pos] = kraw[(size_t)i * cap + t];
+        val[pos] = kraw[cptr[i] + t];
       }
       base += __popc(m);
     }
@@ -392,22 +394,69 @@ __global__ void laplacian_kernel(int64_t n, const int32_t *__restrict__ row_ptr,
   }
 }
 
-__global__ void max_count_kernel(const int32_t *__restrict__ cnt, int64_t n, int cap, int32_t *out2) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int32_t m = 0, over = 0;
-  for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    m = max(m, cnt[i]);
-    over += cnt[i] > cap ? 1 : 0;
+// candidate pairs (row << 32 | col), sorted: cptr[r] = first pair of row r (lower bound), cptr[n] = total
+__global__ void pair_row_ptr_kernel(const unsigned long long *__restrict__ keys, int64_t total, int64_t n,
+                                    int64_t *__restrict__ cptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  const unsigned long long target = (unsigned long long)r << 32;
+  int64_t lo = 0, hi = total;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    over += __shfl_xor_sync(0xffffffffu, over, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMax(out2, m);
-    if (over) atomicAdd(out2 + 1, over);
-  }
+  cptr[r] = lo;
 }
+
+__global__ void pair_cols_kernel(const unsigned long long *__restrict__ keys, int64_t total, int32_t *__restrict__ col) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    col[i] = (int32_t)(keys[i] & 0xffffffffull);
+}
+
+__global__ void row_counts_kernel(const int64_t *__restrict__ cptr, int64_t n, int32_t *__restrict__ cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt[i] = (int32_t)(cptr[i + 1] - cptr[i]);
+}
+
+__global__ void max_count_kernel(const int64_t *__restrict__ cptr, int64_t n, int32_t *out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t m = 0;
+  for (; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, (int32_t)(cptr[i + 1] - cptr[i]));
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// MELD_B200_TIMING=1: print per-stage wall times of a build to stderr (synchronises after each stage).
+struct StageTimer {
+  bool on;
+  cudaStream_t stream;
+  cudaEvent_t e0, e1;
+  explicit StageTimer(cudaStream_t s) : on(getenv("MELD_B200_TIMING") != nullptr), stream(s) {
+    if (on) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, stream);
+    }
+  }
+  void lap(const char *what) {
+    if (!on) return;
+    cudaEventRecord(e1, stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[meld_b200 timing] %-28s %9.3f ms\n", what, ms);
+    cudaEventRecord(e0, stream);
+  }
+  ~StageTimer() {
+    if (on) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
+  }
+};
 
 static int warp_grid(int64_t n_rows, int threads) {
   const int64_t warps_per_block = threads / 32;
@@ -475,10 +524,21 @@ static int morton_order(const double *X, int64_t n, int64_t d, cudaStream_t stre
   return 0;
 }
 
-// Steps 0 and 1: centred norms, pass 1 (eps upper bounds), pass 2 (candidate lists).
+// Steps 0 and 1: centred norms, pass 1 (eps upper bounds), pass 2 (candidate pairs), pairs sorted into a
+// CSR of candidates: cand[cptr[i] .. cptr[i+1]) = candidate columns of row i, ascending.
+struct Candidates {
+  DevBuf<float> key2;
+  DevBuf<int64_t> cptr;   // n + 1
+  DevBuf<int32_t> cand;   // total
+  int64_t total = 0;
+  int64_t pair_cap = 0;
+  int passes = 0;
+  int32_t max_per_row = 0;
+  int64_t retries = 0;
+};
+
 static int candidate_search(const double *X, int64_t n, int64_t d, int k1, double radius_factor, bool simt,
-                            cudaStream_t stream, DevBuf<float> &key2, DevBuf<int32_t> &cand, DevBuf<int32_t> &cnt,
-                            int64_t &cap, int &passes, int64_t &overflow_rows, int32_t (&h_max)[2]) {
+                            cudaStream_t stream, Candidates &out) {
   // -- 0. means / norms
   DevBuf<double> partial, mu, norm;
   DevBuf<unsigned long long> ymax2;
@@ -501,44 +561,76 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
   MELD_CHECK(search_prepare(plan, X, mu.p, norm.p, stream, &st));
   DevBuf<float> lists;
   MELD_CHECK(lists.alloc((size_t)n * plan.nlists * k1));
-  MELD_CHECK(key2.alloc((size_t)n));
+  MELD_CHECK(out.key2.alloc((size_t)n));
+  StageTimer tm(stream);
   MELD_CHECK(search_pass1(plan, st, lists.p, stream));
+  tm.lap("search pass 1 (top-k)");
   merge_lists_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(lists.p, n, plan.nlists, k1, norm.p, ymax2.p,
-                                                                      plan.margin_c, radius_factor, key2.p);
+                                                                      plan.margin_c, radius_factor, out.key2.p);
   MELD_LAUNCH_CHECK();
   lists.release();
+  out.passes = 1;
 
-  // candidate capacity per row: generous (memory is cheap), retried with the exact maximum on overflow
-  cap = k1 <= 8 ? 256 : 512;
-  while (cap * 12 * n > (int64_t)24e9 && cap > 64) cap /= 2;
-  if (cap > round_up(n, 32)) cap = round_up(n, 32);
-  DevBuf<int32_t> maxcnt;
-  MELD_CHECK(cnt.alloc((size_t)n));
-  MELD_CHECK(maxcnt.alloc(2));
-  passes = 1;
-  overflow_rows = 0;
+  // pass 2 appends (row, col) pairs to one global buffer; sized generously, retried with the exact
+  // total if it overflows
+  int64_t pair_cap = n * (k1 <= 8 ? 96 : 192);
+  if (pair_cap > n * n) pair_cap = n * n;
+  DevBuf<unsigned long long> pairs, pairs_sorted, gcount;
+  MELD_CHECK(gcount.alloc(1));
+  unsigned long long h_total = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    MELD_CHECK(cand.alloc((size_t)n * cap));
-    MELD_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)n * sizeof(int32_t), stream));
-    MELD_CUDA(cudaMemsetAsync(maxcnt.p, 0, 2 * sizeof(int32_t), stream));
-    MELD_CHECK(search_pass2(plan, st, key2.p, cand.p, cnt.p, (int)cap, stream));
-    ++passes;
-    max_count_kernel<<<296, 256, 0, stream>>>(cnt.p, n, (int)cap, maxcnt.p);
-    MELD_LAUNCH_CHECK();
-    MELD_CUDA(cudaMemcpyAsync(h_max, maxcnt.p, sizeof(h_max), cudaMemcpyDeviceToHost, stream));
+    MELD_CHECK(pairs.alloc((size_t)pair_cap));
+    MELD_CUDA(cudaMemsetAsync(gcount.p, 0, sizeof(unsigned long long), stream));
+    tm.lap("merge + alloc");
+    MELD_CHECK(search_pass2(plan, st, out.key2.p, pairs.p, gcount.p, pair_cap, stream));
+    tm.lap("search pass 2 (emit)");
+    ++out.passes;
+    MELD_CUDA(cudaMemcpyAsync(&h_total, gcount.p, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));
-    if (h_max[0] <= cap) break;
+    if ((int64_t)h_total <= pair_cap) break;
     if (attempt == 1) {
-      set_error("knn_graph_build: candidate overflow persisted (max %d > cap %lld)", h_max[0], (long long)cap);
+      set_error("knn_graph_build: candidate overflow persisted (%llu pairs > capacity %lld)", h_total,
+                (long long)pair_cap);
       return MELD_B200_ERR_INTERNAL;
     }
-    overflow_rows = h_max[1];
-    cap = round_up(h_max[0], 32);
+    out.retries = 1;
+    pair_cap = (int64_t)h_total + 1024;
   }
   search_release(&st);
+  out.total = (int64_t)h_total;
+  out.pair_cap = pair_cap;
+  MELD_REQUIRE(out.total < (int64_t)2147483647, "knn_graph_build: %lld candidate pairs overflow int32 sort size",
+               (long long)out.total);
+
+  // sort the pairs by (row, col) and cut them into rows
+  MELD_CHECK(pairs_sorted.alloc((size_t)out.total));
+  {
+    int end_bit = 33;
+    while (end_bit < 64 && ((unsigned long long)n >> (end_bit - 32)) != 0) ++end_bit;
+    size_t tmp_bytes = 0;
+    MELD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, pairs.p, pairs_sorted.p, (int)out.total, 0, end_bit,
+                                             stream));
+    DevBuf<unsigned char> tmp;
+    MELD_CHECK(tmp.alloc(tmp_bytes));
+    MELD_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, pairs.p, pairs_sorted.p, (int)out.total, 0, end_bit,
+                                             stream));
+    MELD_CHECK(out.cptr.alloc((size_t)n + 1));
+    MELD_CHECK(out.cand.alloc((size_t)out.total));
+    pair_row_ptr_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(pairs_sorted.p, out.total, n, out.cptr.p);
+    MELD_LAUNCH_CHECK();
+    pair_cols_kernel<<<sm_count() * 8, 256, 0, stream>>>(pairs_sorted.p, out.total, out.cand.p);
+    MELD_LAUNCH_CHECK();
+    DevBuf<int32_t> mx;
+    MELD_CHECK(mx.alloc(1));
+    MELD_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int32_t), stream));
+    max_count_kernel<<<296, 256, 0, stream>>>(out.cptr.p, n, mx.p);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaMemcpyAsync(&out.max_per_row, mx.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
+  }
+  tm.lap("sort pairs -> candidate CSR");
   return 0;
 }
-
 
 extern "C" {
 
@@ -565,6 +657,7 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   const bool simt = (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0;
   const bool keep_raw = (flags & MELD_B200_FLAG_KEEP_KNN_KERNEL) != 0;
 
+  StageTimer tm(stream);
   // -- 0a. internal cell order (Morton curve over the highest-variance features)
   DevBuf<double> Xp;
   DevBuf<int32_t> perm;
@@ -573,35 +666,36 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     X = Xp.p;
   }
 
+  tm.lap("morton order");
   // -- 0./1. means, norms, candidate search
-  DevBuf<float> key2;
-  DevBuf<int32_t> cand, cnt;
-  int64_t cap = 0, overflow_rows = 0;
-  int passes = 0;
-  int32_t h_max[2] = {0, 0};
-  MELD_CHECK(candidate_search(X, n, d, k1, radius_factor, simt, stream, key2, cand, cnt, cap, passes, overflow_rows,
-                              h_max));
-  key2.release();
+  Candidates cs;
+  MELD_CHECK(candidate_search(X, n, d, k1, radius_factor, simt, stream, cs));
+  cs.key2.release();
+  tm.lap("candidate search total");
+  DevBuf<int32_t> &cand = cs.cand;
+  const int64_t *cptr = cs.cptr.p;
+  const int passes = cs.passes;
 
   // -- 2. exact distances, eps
   DevBuf<double> vbuf, eps, kraw;
   DevBuf<int> err;
-  MELD_CHECK(vbuf.alloc((size_t)n * cap));
+  MELD_CHECK(vbuf.alloc((size_t)cs.total));
   MELD_CHECK(eps.alloc((size_t)n));
   MELD_CHECK(err.alloc(1));
   MELD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
-  refine_dist_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(X, n, d, cand.p, cnt.p, (int)cap, k1, bandwidth_scale,
+  refine_dist_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(X, n, d, cand.p, cptr, k1, bandwidth_scale,
                                                             vbuf.p, eps.p, err.p);
   MELD_LAUNCH_CHECK();
 
+  tm.lap("refine (exact distances)");
   // -- 3. kernel values + symmetrisation
   DevBuf<int32_t> kept, extra, total;
   MELD_CHECK(kept.alloc((size_t)n));
   MELD_CHECK(extra.alloc((size_t)n));
   MELD_CHECK(total.alloc((size_t)n + 1));
   MELD_CUDA(cudaMemsetAsync(extra.p, 0, (size_t)n * sizeof(int32_t), stream));
-  if (keep_raw) MELD_CHECK(kraw.alloc((size_t)n * cap));
-  kernel_values_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cnt.p, (int)cap, vbuf.p, eps.p, decay,
+  if (keep_raw) MELD_CHECK(kraw.alloc((size_t)cs.total));
+  kernel_values_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cptr, vbuf.p, eps.p, decay,
                                                               thresh_eff, kept.p, extra.p, keep_raw ? kraw.p : nullptr);
   MELD_LAUNCH_CHECK();
   add_counts_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(kept.p, extra.p, n, total.p);
@@ -648,7 +742,7 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     MELD_CHECK(uval.alloc((size_t)g->nnz));
     MELD_CHECK(cursor.alloc((size_t)n));
     MELD_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)n * sizeof(int32_t), stream));
-    fill_sym_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cnt.p, (int)cap, vbuf.p, g->row_ptr.p, kept.p,
+    fill_sym_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cptr, vbuf.p, g->row_ptr.p, kept.p,
                                                            cursor.p, ucol.p, uval.p);
     MELD_LAUNCH_CHECK();
     MELD_CHECK(g->col.alloc((size_t)g->nnz + kCsrPad));
@@ -665,6 +759,7 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
   }
 
+  tm.lap("kernel values, fill, sort");
   // optional export copy of the un-symmetrised kernel
   if (keep_raw) {
     DevBuf<int64_t> rp64;
@@ -685,7 +780,7 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     MELD_CHECK(g->knn_val.alloc((size_t)h_raw));
     MELD_CHECK(g->knn_ptr.alloc((size_t)n + 1));
     MELD_CUDA(cudaMemcpyAsync(g->knn_ptr.p, rp64.p, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
-    fill_raw_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cnt.p, (int)cap, kraw.p, g->knn_ptr.p,
+    fill_raw_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cptr, kraw.p, g->knn_ptr.p,
                                                            g->knn_col.p, g->knn_val.p);
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaStreamSynchronize(stream));
@@ -701,7 +796,9 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaStreamSynchronize(stream));
   }
+  tm.lap("anisotropy + laplacian");
   MELD_CHECK(graph_finalize(g, stream));
+  tm.lap("finalize (block dictionaries)");
   if (perm.p) {
     g->perm.p = perm.p;  // hand the buffer over to the graph
     g->perm.n = perm.n;
@@ -709,9 +806,9 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     perm.n = 0;
   }
   g->stats[0] = passes;
-  g->stats[1] = h_max[0];
-  g->stats[2] = cap;
-  g->stats[3] = overflow_rows;
+  g->stats[1] = cs.max_per_row;
+  g->stats[2] = cs.total;
+  g->stats[3] = cs.retries;
   g->stats[4] = simt ? 1 : 0;
   guard.g = nullptr;
   *graph_out = g;
@@ -728,17 +825,13 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   const double rho = pow(-log(thresh_eff), 1.0 / decay);
   double radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
   if (radius_factor < 1.0) radius_factor = 1.0;
-  DevBuf<float> key2;
-  DevBuf<int32_t> cand, cnt;
-  int64_t cap = 0, overflow_rows = 0;
-  int passes = 0;
-  int32_t h_max[2] = {0, 0};
-  MELD_CHECK(candidate_search(X, n, d, knn + 1, radius_factor, (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0, stream, key2,
-                              cand, cnt, cap, passes, overflow_rows, h_max));
-  MELD_CUDA(cudaMemcpyAsync(key2_out, key2.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-  MELD_CUDA(cudaMemcpyAsync(cnt_out, cnt.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  Candidates cs;
+  MELD_CHECK(candidate_search(X, n, d, knn + 1, radius_factor, (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0, stream, cs));
+  MELD_CUDA(cudaMemcpyAsync(key2_out, cs.key2.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  row_counts_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(cs.cptr.p, n, cnt_out);
+  MELD_LAUNCH_CHECK();
   MELD_CUDA(cudaStreamSynchronize(stream));
-  if (cap_host) *cap_host = cap;
+  if (cap_host) *cap_host = cs.total;
   return 0;
 }
 

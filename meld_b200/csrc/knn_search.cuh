@@ -4,7 +4,8 @@
 // d_ij^2 = n_i - 2 s_ij and a larger s means a closer neighbour.
 //   pass 1: for every row, nlists sorted (descending) lists of the k1 largest s seen by each
 //           (column segment x epilogue half) -> merged by merge_lists_kernel into key2_i;
-//   pass 2: append every column j with s_ij >= key2_i to the row's candidate buffer.
+//   pass 2: append a pair (i << 32 | j) for every column j with s_ij >= key2_i to one global buffer
+//           (unordered; *count keeps growing past the capacity so the caller can size a retry).
 // margin_c bounds the implementation's error: |d2_approx - d2_exact| <= margin_c (n_i + max_j n_j).
 #pragma once
 #include "common.cuh"
@@ -12,7 +13,7 @@
 namespace meld {
 
 constexpr int kMaxK1 = 64;     // knn + 1 limit (shared-memory top-k lists)
-constexpr int kMaxLists = 64;  // lists per row merged after pass 1
+constexpr int kMaxLists = 128;  // lists per row merged after pass 1
 
 struct SearchPlan {
   bool simt = false;
@@ -43,15 +44,15 @@ int search_plan(bool simt, int64_t n, int64_t d, int k1, SearchPlan *plan);
 int search_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
                    SearchState *st);
 int search_pass1(const SearchPlan &plan, SearchState &st, float *lists, cudaStream_t stream);
-int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, int32_t *cand, int32_t *cnt, int cap,
-                 cudaStream_t stream);
+int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, unsigned long long *pairs,
+                 unsigned long long *count, int64_t cap, cudaStream_t stream);
 void search_release(SearchState *st);
 
 // tcgen05 implementation (knn_tc.cu)
 int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan);
 int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
                SearchState *st);
-int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2, int32_t *cand,
-            int32_t *cnt, int cap, cudaStream_t stream);
+int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2,
+            unsigned long long *pairs, unsigned long long *count, int64_t cap, cudaStream_t stream);
 
 }  // namespace meld

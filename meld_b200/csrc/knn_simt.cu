@@ -25,8 +25,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restrict__ xc, const float *__restrict__ hn,
                                                            int64_t n, int64_t d, int k1, int nseg,
                                                            float *__restrict__ lists, const float *__restrict__ key2,
-                                                           int32_t *__restrict__ cand, int32_t *__restrict__ cnt,
-                                                           int cap) {
+                                                           unsigned long long *__restrict__ pairs,
+                                                           unsigned long long *__restrict__ count, int64_t cap) {
   extern __shared__ __align__(16) float sm[];
   float *Xs = sm;                           // [kChunk][kRows + 1]
   float *Ys = Xs + kChunk * (kRows + 1);    // [kCols][kYPitch]
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restr
           }
         } else {
           if (s >= thr) {
-            const int pos = atomicAdd(cnt + row, 1);
-            if (pos < cap) cand[(size_t)row * cap + pos] = (int32_t)col;
+            const unsigned long long pos = atomicAdd(count, 1ull);
+            if ((int64_t)pos < cap) pairs[pos] = ((unsigned long long)row << 32) | (unsigned long long)col;
           }
         }
       }
@@ -150,14 +150,14 @@ int search_pass1(const SearchPlan &plan, SearchState &st, float *lists, cudaStre
   return 0;
 }
 
-int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, int32_t *cand, int32_t *cnt, int cap,
-                 cudaStream_t stream) {
-  if (!plan.simt) return tc_pass(plan, st, 2, nullptr, key2, cand, cnt, cap, stream);
+int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, unsigned long long *pairs,
+                 unsigned long long *count, int64_t cap, cudaStream_t stream) {
+  if (!plan.simt) return tc_pass(plan, st, 2, nullptr, key2, pairs, count, cap, stream);
   const size_t smem = simt_smem(0);
   MELD_CUDA(cudaFuncSetAttribute(simt_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(plan.n, kRows), (unsigned)plan.nseg);
   simt_search_kernel<2><<<grid, kRows, smem, stream>>>(st.xc32.p, st.hn32.p, plan.n, plan.d, plan.k1, plan.nseg,
-                                                       nullptr, key2, cand, cnt, cap);
+                                                       nullptr, key2, pairs, count, cap);
   MELD_LAUNCH_CHECK();
   return 0;
 }

@@ -23,12 +23,13 @@ namespace meld {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;            // two per TMEM lane quadrant, each scanning half of a tile's columns
+constexpr int kTcThreads = (2 + kEpiWarps) * 32;
 constexpr int kABytes = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;   // 32 KB
 constexpr int kMaxResidentKb = 6;      // A resident up to K' = 384
 constexpr float kPadSentinel = -1e30f;
-constexpr int kEmitSlots = 16;         // pass 2: hits staged per row before one atomicAdd reserves their slots
+constexpr int kQueueCap = 128;          // pass 2: per-warp queue of hit pairs (flushed when half full)
 
 // ---- operand preparation ------------------------------------------------------------------------
 __global__ void tc_prep_kernel(const double *__restrict__ X, const double *__restrict__ mu,
@@ -178,16 +179,45 @@ struct TcArgs {
   int mode;  // 1: top-k1 lists, 2: emit candidates
   int64_t n;
   int n_row_tiles, n_col_tiles, nseg, nkb, a_resident, k1;
-  int mc;         // 1: launched as 2-CTA clusters, B tiles are multicast between the pair
+  int mc;         // cluster size (1, 2 or 4): each CTA loads 1/mc of a B tile and multicasts it to the cluster
+  int n_passes;   // segments visited per row tile (pass 1 may stop early: any subset gives a valid bound)
   int n_stages;   // B (or A+B) ring depth
   int a_region;   // bytes reserved for the A operand (resident k-blocks, or one A tile per stage)
   float *thr_g;   // pass 1: per-row running lower bound of the k1-th largest s (carried across segments)
   float *lists;
   const float *key2;
-  int32_t *cand;
-  int32_t *cnt;
-  int cap;
+  unsigned long long *pairs;   // pass 2: global append buffer of (row << 32 | col)
+  unsigned long long *count;   // its fill count (keeps growing past cap)
+  long long cap;
 };
+
+// Work unit u -> (row tile, segment, column-tile order).  Units are issued segment-major so concurrent CTAs
+// stream the same L2-resident slice of B, but every row tile visits ITS OWN segment first and, inside a
+// segment, starts at the column tile that holds its own rows and wraps around: cells are Morton-ordered, so
+// a row's true neighbours sit near its own position -- scanning outwards from there makes the running
+// top-k threshold tight after the first tile instead of after a slow monotone approach.
+struct UnitPlan {
+  int rt, seg, pass, ct0, len, start;
+};
+__device__ __forceinline__ UnitPlan unit_plan(const TcArgs &a, int u) {
+  UnitPlan p;
+  const int pass = u / a.n_row_tiles;  // 0: own segment, then the following ones cyclically
+  p.rt = u % a.n_row_tiles;
+  p.pass = pass;
+  const int own_ct = ((p.rt - p.rt % a.mc) * BM) / BN;  // identical for every CTA of a cluster (lockstep)
+  int own_seg = (int)(((int64_t)own_ct * a.nseg) / a.n_col_tiles);
+  while (own_seg + 1 < a.nseg && (int)((int64_t)a.n_col_tiles * (own_seg + 1) / a.nseg) <= own_ct) ++own_seg;
+  while (own_seg > 0 && (int)((int64_t)a.n_col_tiles * own_seg / a.nseg) > own_ct) --own_seg;
+  p.seg = (own_seg + pass) % a.nseg;
+  p.ct0 = (int)((int64_t)a.n_col_tiles * p.seg / a.nseg);
+  const int ct1 = (int)((int64_t)a.n_col_tiles * (p.seg + 1) / a.nseg);
+  p.len = ct1 - p.ct0;
+  int st = own_ct - p.ct0;
+  if (st < 0) st = 0;
+  if (st >= p.len) st = p.len - 1;
+  p.start = st;
+  return p;
+}
 
 struct Bars {
   uint64_t full[kMaxStages];
@@ -206,14 +236,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   unsigned char *smA = smem;                   // resident A (nkb x 16 KB) or A stages
   unsigned char *smB = smem + a.a_region;      // B stages
   float *lst = reinterpret_cast<float *>(smB + (size_t)kStages * kBBytes);  // [k1][128] (pass 1)
-  Bars *bars = reinterpret_cast<Bars *>(reinterpret_cast<unsigned char *>(lst) + (size_t)(a.mode == 1 ? a.k1 : kEmitSlots) * BM * 4);
+  Bars *bars = reinterpret_cast<Bars *>(reinterpret_cast<unsigned char *>(lst) + (a.mode == 1 ? (size_t)a.k1 * 2 * BM * 4 : (size_t)kEpiWarps * kQueueCap * 8 + 64));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work units are (segment, row tile), segment-major.  With multicast the two CTAs of a cluster take
   // adjacent row tiles of the same segment and walk identical column-tile sequences in lockstep.
-  const int n_units = a.n_row_tiles * a.nseg;
-  const uint32_t crank = a.mc ? cluster_ctarank() : 0u;
-  const int u_first = a.mc ? 2 * (int)(blockIdx.x >> 1) + (int)crank : (int)blockIdx.x;
+  const int n_units = a.n_row_tiles * a.n_passes;  // n_passes segments per row tile, its own first
+  const uint32_t crank = a.mc > 1 ? cluster_ctarank() : 0u;
+  const int u_first = a.mc * (int)(blockIdx.x / a.mc) + (int)crank;
   const int u_step = (int)gridDim.x;  // even when clustered
 
   if (warp == 0 && lane == 0) {
@@ -224,13 +254,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         bar_init(&bars->full[s], 1);
-        bar_init(&bars->empty[s], a.mc ? 2 : 1);  // clustered: both CTAs' MMAs must release a stage
+        bar_init(&bars->empty[s], a.mc);  // clustered: every CTA's MMAs must release a stage
       }
       bar_init(&bars->a_full, 1);
       bar_init(&bars->a_empty, 1);
       for (int b = 0; b < 2; ++b) {
         bar_init(&bars->tmem_full[b], 1);
-        bar_init(&bars->tmem_empty[b], 4);  // one arrival per epilogue warp
+        bar_init(&bars->tmem_empty[b], kEpiWarps);  // one arrival per epilogue warp
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -242,7 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (a.mc) cluster_sync_all();  // peer barriers are initialised before any multicast can target them
+  if (a.mc > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can target them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -252,24 +282,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int stage = 0;
       uint32_t phase = 0, uphase = 0;
       for (int u = u_first; u < n_units; u += u_step) {
-        const int seg = u / a.n_row_tiles, rt = u % a.n_row_tiles;  // segment-major: concurrent CTAs share B's L2 slice
-        const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
-        const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
+        const UnitPlan up = unit_plan(a, u);
+        const int rt = up.rt;
         if (a.a_resident) {
           bar_wait(&bars->a_empty, uphase ^ 1u);
           bar_expect_tx(&bars->a_full, (uint32_t)a.nkb * kABytes);
           for (int kb = 0; kb < a.nkb; ++kb) tma_load_2d(&tmap_a, &bars->a_full, smA + kb * kABytes, kb * BK, rt * BM);
         }
-        for (int ct = ct0; ct < ct1; ++ct) {
+        for (int j = 0; j < up.len; ++j) {
+          const int ct = up.ct0 + (up.start + j) % up.len;
           for (int kb = 0; kb < a.nkb; ++kb) {
             bar_wait(&bars->empty[stage], phase ^ 1u);
             bar_expect_tx(&bars->full[stage], a.a_resident ? kBBytes : kBBytes + kABytes);
-            if (a.mc) {  // my half of the B tile, delivered to both CTAs of the pair
-              tma_load_2d_mc(&tmap_b, &bars->full[stage], smB + stage * kBBytes + crank * (kBBytes / 2), kb * BK,
-                             ct * BN + (int)crank * (BN / 2), (uint16_t)0x3);
+            if (a.mc > 1) {  // my slice of the B tile, delivered to every CTA of the cluster
+              const int slice = BN / a.mc;
+              tma_load_2d_mc(&tmap_b, &bars->full[stage], smB + stage * kBBytes + crank * (kBBytes / a.mc), kb * BK,
+                             ct * BN + (int)crank * slice, (uint16_t)((1u << a.mc) - 1u));
             } else {
               tma_load_2d(&tmap_b, &bars->full[stage], smB + stage * kBBytes, kb * BK, ct * BN);
-              tma_load_2d(&tmap_b, &bars->full[stage], smB + stage * kBBytes + kBBytes / 2, kb * BK, ct * BN + BN / 2);
             }
             if (!a.a_resident) tma_load_2d(&tmap_a, &bars->full[stage], smA + stage * kABytes, kb * BK, rt * BM);
             if (++stage == kStages) {
@@ -288,14 +318,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int stage = 0, buf = 0;
       uint32_t phase = 0, bphase = 0, uphase = 0;
       for (int u = u_first; u < n_units; u += u_step) {
-        const int seg = u / a.n_row_tiles;
-        const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
-        const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
+        const UnitPlan up = unit_plan(a, u);
         if (a.a_resident) {
           bar_wait(&bars->a_full, uphase);
           tc_fence_after();
         }
-        for (int ct = ct0; ct < ct1; ++ct) {
+        for (int j = 0; j < up.len; ++j) {
           bar_wait(&bars->tmem_empty[buf], bphase ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)buf * BN;
@@ -309,8 +337,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               tc_mma_bf16(tmem_d, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
                           (uint32_t)((kb | k) != 0));
             }
-            if (a.mc)
-              tc_commit_mc(&bars->empty[stage], (uint16_t)0x3);  // releases the stage in both CTAs
+            if (a.mc > 1)
+              tc_commit_mc(&bars->empty[stage], (uint16_t)((1u << a.mc) - 1u));  // releases the stage cluster-wide
             else
               tc_commit(&bars->empty[stage]);  // stage reusable once these MMAs retire
             if (++stage == kStages) {
@@ -328,33 +356,48 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
   } else {
     // ===== epilogue: thread = row of the tile =====
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    const int rin = q * 32 + lane;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;  // which half of a tile's 256 columns this warp scans
+    const int rin = q * 32 + lane;     // row of the tile
+    const int lcol = half * BM + rin;  // this thread's column in the shared top-k lists
     int buf = 0;
     uint32_t bphase = 0;
     for (int u = u_first; u < n_units; u += u_step) {
-      const int seg = u / a.n_row_tiles, rt = u % a.n_row_tiles;
-      const int ct0 = (int)((int64_t)a.n_col_tiles * seg / a.nseg);
-      const int ct1 = (int)((int64_t)a.n_col_tiles * (seg + 1) / a.nseg);
+      const UnitPlan up = unit_plan(a, u);
+      const int rt = up.rt;
       const int64_t row = (int64_t)rt * BM + rin;
       float thr;
       if (a.mode == 1) {
-        for (int s = 0; s < a.k1; ++s) lst[s * BM + rin] = -INFINITY;
+        for (int s = 0; s < a.k1; ++s) lst[s * 2 * BM + lcol] = -INFINITY;
         // start from the bound earlier segments of this row have published: values below it cannot be
         // among the k1 largest of the union, so this list only needs what beats it
         thr = row < a.n ? __ldcg(a.thr_g + row) : INFINITY;
       } else {
         thr = row < a.n ? a.key2[row] : INFINITY;
       }
-      int32_t *ebuf = reinterpret_cast<int32_t *>(lst);  // pass 2: [kEmitSlots][128] staged hits
-      int n_e = 0;
-      auto flush_hits = [&]() {
-        const int base = atomicAdd(a.cnt + row, n_e);
-        for (int i = 0; i < n_e; ++i)
-          if (base + i < a.cap) a.cand[(size_t)row * a.cap + base + i] = ebuf[i * BM + rin];
-        n_e = 0;
+      // pass 2: hits are queued per warp in shared memory and appended to the global pair buffer 32+ at a
+      // time (one global atomic per flush), so the scan never waits on an atomic's round trip per hit
+      unsigned long long *wq = reinterpret_cast<unsigned long long *>(lst) + (size_t)(warp - 2) * kQueueCap;
+      int *wqn = reinterpret_cast<int *>(reinterpret_cast<unsigned long long *>(lst) + kEpiWarps * kQueueCap) + (warp - 2);
+      if (a.mode == 2) {
+        if (lane == 0) *wqn = 0;
+        __syncwarp();
+      }
+      auto flush_queue = [&]() {  // warp-uniform
+        __syncwarp();
+        int nq = *wqn;
+        if (nq > kQueueCap) nq = kQueueCap;
+        unsigned long long base = 0;
+        if (lane == 0 && nq > 0) base = atomicAdd(a.count, (unsigned long long)nq);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < nq; i += 32)
+          if ((long long)(base + i) < a.cap) a.pairs[base + i] = wq[i];
+        __syncwarp();
+        if (lane == 0) *wqn = 0;
+        __syncwarp();
       };
-      for (int ct = ct0; ct < ct1; ++ct) {
+      for (int j = 0; j < up.len; ++j) {
+        const int ct = up.ct0 + (up.start + j) % up.len;
         bar_wait(&bars->tmem_full[buf], bphase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
@@ -362,9 +405,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // chunk that holds a hit is scanned element by element.  Two chunks are kept in flight so the
         // TMEM load of the next one overlaps the scan of the current one.
         auto scan = [&](const uint32_t (&v)[32], int chunk) {
-          float mx = __uint_as_float(v[0]);
+          float t16[16];  // log-depth max (a serial chain of 31 dependent FMNMX would cost ~130 cycles per chunk)
 #pragma unroll
-          for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+          for (int c = 0; c < 16; ++c) t16[c] = fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 16]));
+#pragma unroll
+          for (int w = 8; w > 0; w >>= 1) {
+#pragma unroll
+            for (int c = 0; c < w; ++c) t16[c] = fmaxf(t16[c], t16[c + w]);
+          }
+          const float mx = t16[0];
           const int col0 = ct * BN + chunk * 32;
           if (a.mode == 1) {
             if (mx > thr) {
@@ -373,42 +422,49 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const float s = __uint_as_float(v[c]);
                 if (s > thr) {
                   int pos = a.k1 - 1;
-                  while (pos > 0 && lst[(pos - 1) * BM + rin] < s) {
-                    lst[pos * BM + rin] = lst[(pos - 1) * BM + rin];
+                  while (pos > 0 && lst[(pos - 1) * 2 * BM + lcol] < s) {
+                    lst[pos * 2 * BM + lcol] = lst[(pos - 1) * 2 * BM + lcol];
                     --pos;
                   }
-                  lst[pos * BM + rin] = s;
-                  thr = fmaxf(thr, lst[(a.k1 - 1) * BM + rin]);
+                  lst[pos * 2 * BM + lcol] = s;
+                  thr = fmaxf(thr, lst[(a.k1 - 1) * 2 * BM + lcol]);
                 }
               }
             }
           } else {
             if (mx >= thr) {
-#pragma unroll  // static register indices
-              for (int c = 0; c < 32; ++c) {
-                const float s = __uint_as_float(v[c]);
-                if (s >= thr) {
-                  // stage the hit in this row's shared-memory slots; the global counter is touched once
-                  // per kEmitSlots hits, so the scan never waits on an atomic's round trip
-                  ebuf[n_e * BM + rin] = col0 + c;
-                  if (++n_e == kEmitSlots) {
-                    flush_hits();
-                  }
+              unsigned m = 0;
+#pragma unroll  // branch-free hit mask (static register indices)
+              for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[c]) >= thr) ? (1u << c) : 0u;
+              while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned long long key = ((unsigned long long)row << 32) | (unsigned long long)(col0 + c);
+                const int slot = atomicAdd(wqn, 1);
+                if (slot < kQueueCap) {
+                  wq[slot] = key;
+                } else {  // queue full inside one chunk (dense hits): append directly
+                  const unsigned long long pos = atomicAdd(a.count, 1ull);
+                  if ((long long)pos < a.cap) a.pairs[pos] = key;
                 }
               }
             }
+            __syncwarp();
+            if (*wqn >= kQueueCap / 2) flush_queue();
           }
         };
         uint32_t va[32], vb[32];
-        tmem_ld32(tbase, va);
+        constexpr int kChunks = BN / 32 / 2;  // chunks per half
+        const int c0 = half * kChunks;
+        tmem_ld32(tbase + c0 * 32, va);
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; chunk += 2) {
+        for (int chunk = 0; chunk < kChunks; chunk += 2) {
           tmem_ld_wait();
-          tmem_ld32(tbase + (chunk + 1) * 32, vb);
-          scan(va, chunk);
+          tmem_ld32(tbase + (c0 + chunk + 1) * 32, vb);
+          scan(va, c0 + chunk);
           tmem_ld_wait();
-          if (chunk + 2 < BN / 32) tmem_ld32(tbase + (chunk + 2) * 32, va);
-          scan(vb, chunk + 1);
+          if (chunk + 2 < kChunks) tmem_ld32(tbase + (c0 + chunk + 2) * 32, va);
+          scan(vb, c0 + chunk + 1);
         }
         tc_fence_before();
         __syncwarp();
@@ -416,12 +472,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         buf ^= 1;
         if (buf == 0) bphase ^= 1u;
       }
-      if (a.mode == 2 && n_e > 0) flush_hits();
+      if (a.mode == 2) flush_queue();
       if (a.mode == 1 && row < a.n) {
-        float *out = a.lists + ((size_t)row * a.nseg + seg) * a.k1;
-        for (int s = 0; s < a.k1; ++s) out[s] = lst[s * BM + rin];
+        float *out = a.lists + ((size_t)row * a.n_passes * 2 + up.pass * 2 + half) * a.k1;  // list per (segment, half)
+        for (int s = 0; s < a.k1; ++s) out[s] = lst[s * 2 * BM + lcol];
         // publish (monotone max; floats >= 0 and < 0 both ordered through the signed/unsigned trick)
-        const float mine = lst[(a.k1 - 1) * BM + rin];
+        const float mine = lst[(a.k1 - 1) * 2 * BM + lcol];
         if (mine > -INFINITY) {
           if (mine >= 0.f)
             atomicMax(reinterpret_cast<int *>(a.thr_g + row), __float_as_int(mine));
@@ -434,7 +490,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (a.mc) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA until it is done too
+  if (a.mc > 1) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA until it is done too
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -484,7 +540,7 @@ int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan) {
   const int64_t kp = round_up(3 * d + 3, BK);
   MELD_REQUIRE(kp <= (1 << 20), "knn_graph_build: d=%lld too large for the tensor-core search", (long long)d);
   plan->kp = (int)kp;
-  plan->n_pad = round_up(n, BN);
+  plan->n_pad = round_up(n, 4 * BM);  // row tiles come in multiples of the largest cluster size
   const int64_t row_tiles = plan->n_pad / BM, col_tiles = plan->n_pad / BN;
   // enough (row tile, segment) units for ~4 waves of the SMs, never more segments than column tiles;
   // and a segment's slice of the column operand (n_seg x K' bf16) should stay L2 resident while the
@@ -493,11 +549,13 @@ int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan) {
   const int64_t l2_slice = (int64_t)40 << 20;
   const int64_t nseg_l2 = ceil_div(plan->n_pad * kp * 2, l2_slice);
   if (nseg < nseg_l2) nseg = nseg_l2;
-  if (nseg > kMaxLists) nseg = kMaxLists;
+  if (nseg > kMaxLists / 2) nseg = kMaxLists / 2;  // two lists per segment
   if (nseg > col_tiles) nseg = col_tiles;
   if (nseg < 1) nseg = 1;
   plan->nseg = (int)nseg;
   plan->nlists = (int)nseg;
+  if (tuning().p1_segments > 0 && tuning().p1_segments < plan->nlists) plan->nlists = tuning().p1_segments;
+  plan->nlists *= 2;  // two epilogue threads (column halves) per row keep separate lists
   // bf16 split error of x.y (~2^-15.8 |x||y|) plus fp32 accumulation, x2 for d^2, 4x safety
   plan->margin_c = ldexp(1.0, -11);
   return 0;
@@ -519,12 +577,11 @@ int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const 
                                                      reinterpret_cast<__nv_bfloat16 *>(st->b_op.p));
   MELD_LAUNCH_CHECK();
   MELD_CHECK(encode_operand_map(st->a_op.p, plan.n_pad, plan.kp, BM, st->tmap_a));
-  MELD_CHECK(encode_operand_map(st->b_op.p, plan.n_pad, plan.kp, BN / 2, st->tmap_b));  // half tiles
   return 0;
 }
 
-int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2, int32_t *cand,
-            int32_t *cnt, int cap, cudaStream_t stream) {
+int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2,
+            unsigned long long *pairs, unsigned long long *count, int64_t cap, cudaStream_t stream) {
   TcArgs a{};
   a.mode = mode;
   a.n = plan.n;
@@ -537,10 +594,10 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   a.lists = lists;
   a.thr_g = st.thr_g.p;
   a.key2 = key2;
-  a.cand = cand;
-  a.cnt = cnt;
-  a.cap = cap;
-  const size_t list_bytes = (size_t)(mode == 1 ? plan.k1 : kEmitSlots) * BM * 4;
+  a.pairs = pairs;
+  a.count = count;
+  a.cap = (long long)cap;
+  const size_t list_bytes = mode == 1 ? (size_t)plan.k1 * 2 * BM * 4 : (size_t)kEpiWarps * kQueueCap * 8 + 64;
   const size_t fixed = 1024 + list_bytes + sizeof(Bars);
   const size_t budget = 227 * 1024;
   if (a.a_resident) {
@@ -554,26 +611,50 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   MELD_REQUIRE(a.n_stages >= 2, "tc_search: shared memory too small for a pipeline (knn too large)");
   const size_t smem = fixed + a.a_region + (size_t)a.n_stages * kBBytes;
   MELD_CUDA(cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUtensorMap ma, mb;
-  memcpy(&ma, st.tmap_a, sizeof(ma));
-  memcpy(&mb, st.tmap_b, sizeof(mb));
-  int grid = sm_count();
-  const int units = a.n_row_tiles * a.nseg;  // n_row_tiles is even (n_pad is a multiple of 256)
-  if (grid > units) grid = units;
-  a.mc = tuning().tc_multicast && grid >= 2 ? 1 : 0;
-  if (a.mc) grid &= ~1;
+  a.n_passes = mode == 1 ? plan.nlists / 2 : a.nseg;  // pass 1 visits nlists/2 segments per row (own first)
+  const int units = a.n_row_tiles * a.n_passes;
+  // cluster size: B tiles are loaded once per cluster (TMA multicast), which divides the L2 -> SM traffic of
+  // the streamed operand -- the kernel's real bound at K' = 320 -- by the cluster size
+  int cs = tuning().tc_multicast;
+  if (cs != 2 && cs != 4) cs = 1;
+  while (cs > 1 && (a.n_row_tiles % cs != 0 || units < cs)) cs >>= 1;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = (unsigned)cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = a.mc ? 1 : 0;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  int grid = sm_count();
+  if (cs > 1) {
+    // a persistent kernel must be fully co-resident: ask how many clusters fit at once (GPC shapes can
+    // strand SMs for cluster size 4)
+    cfg.gridDim = dim3((unsigned)(sm_count() / cs * cs));
+    int max_clusters = 0;
+    MELD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, tc_search_kernel, &cfg));
+    if (max_clusters < 1) {
+      cs = 1;
+      cfg.numAttrs = 0;
+    } else {
+      grid = max_clusters * cs;
+      if (grid > sm_count() / cs * cs) grid = sm_count() / cs * cs;
+    }
+  }
+  if (grid > units) grid = units / cs * cs;
+  if (grid < cs) grid = cs;
+  a.mc = cs;
+  cfg.gridDim = dim3((unsigned)grid);
+  CUtensorMap ma, mb;
+  memcpy(&ma, st.tmap_a, sizeof(ma));
+  {
+    unsigned char tm[128];
+    MELD_CHECK(encode_operand_map(st.b_op.p, plan.n_pad, plan.kp, BN / cs, tm));  // one slice of a B tile per CTA
+    memcpy(&mb, tm, sizeof(mb));
+  }
   MELD_CUDA(cudaLaunchKernelEx(&cfg, tc_search_kernel, ma, mb, a));
   MELD_LAUNCH_CHECK();
   return 0;
