@@ -73,6 +73,29 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
                               double thresh, double anisotropy, double bandwidth_scale,
                               int flags, void *stream, meld_b200_graph_t **graph_out);
 
+/* ---- sharded build: the two stages of meld_b200_knn_graph_build, for one-process-per-GPU drivers ------
+ * Stage 1 is row-local: candidate search (pass 1 + pass 2 against ALL n cells), exact float64 distances
+ * and eps_i for query rows [row_begin, row_end) only -- it shards over ranks with no exchange.  Rows are
+ * in the INTERNAL cell order (every rank derives the same Morton permutation from the same X);
+ * row_begin must be a multiple of 512, row_end a multiple of 512 or n.
+ * Stage 2 needs every row: the caller all-gathers (NCCL) the per-row counts, candidate columns, squared
+ * distances and eps of all ranks, in row order, and every rank builds the same Laplacian.               */
+typedef struct meld_b200_cands meld_b200_cands_t;
+int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, double decay, double thresh,
+                             double bandwidth_scale, int64_t row_begin, int64_t row_end, int flags, void *stream,
+                             meld_b200_cands_t **cands_out);
+int meld_b200_cands_info(const meld_b200_cands_t *c, int64_t *n_rows_host, int64_t *total_host, int *has_perm_host,
+                         int64_t *max_per_row_host);
+/* counts: n_rows int64; cand: total int32; d2: total f64; eps: n_rows f64; perm: n int32 (any may be NULL) */
+int meld_b200_cands_export(const meld_b200_cands_t *c, int64_t *counts, int32_t *cand, double *d2, double *eps,
+                           int32_t *perm, void *stream);
+int meld_b200_cands_destroy(meld_b200_cands_t *c);
+/* counts: n int64 (candidates per row, row order), cand / d2: total entries, eps: n, perm: n or NULL.    */
+int meld_b200_graph_from_candidates(int64_t n, const int64_t *counts, const int32_t *cand, const double *d2,
+                                    int64_t total, const double *eps, const int32_t *perm, int knn, double decay,
+                                    double thresh, double anisotropy, double bandwidth_scale, int flags, void *stream,
+                                    meld_b200_graph_t **graph_out);
+
 /* Test hook: run only the reduced-precision candidate search of knn_graph_build and return the
  * per-row pass-2 key (float, s-space) and candidate count; used to cross-check the tcgen05 search
  * against the SIMT one.  Synchronous.                                            */

@@ -131,11 +131,11 @@ __global__ void gather_rows_kernel(const double *__restrict__ X, const int32_t *
 
 // ---- 1b. merge the per-(row, list) top-k1 lists of pass 1 into the emit threshold of pass 2 ----
 // lists: [n][nlists][k1] floats sorted descending in s-space (s = x.y - n_j/2, larger = closer).
-__global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t n, int nlists, int k1,
+__global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t row_begin, int64_t n, int nlists, int k1,
                                    const double *__restrict__ norm, const unsigned long long *ymax2_bits,
                                    double margin_c, double radius_factor, float *__restrict__ key2) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int64_t i = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;  // n = end of this call's row range
   const float *base = lists + (size_t)i * nlists * k1;
   int idx[kMaxLists];
   for (int l = 0; l < nlists; ++l) idx[l] = 0;
@@ -170,17 +170,19 @@ __global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t n, i
 // ---- 2. exact float64 distances of the candidates, eps_i ----------------------------------------
 // One warp per row.  Candidates of row i are cand[cptr[i] .. cptr[i+1]); d2buf (same indexing) receives
 // the exact squared distances.
-__global__ void refine_dist_kernel(const double *__restrict__ X, int64_t n, int64_t d, const int32_t *__restrict__ cand,
-                                   const int64_t *__restrict__ cptr, int k1, double bandwidth_scale,
+__global__ void refine_dist_kernel(const double *__restrict__ X, int64_t row_begin, int64_t n, int64_t d,
+                                   const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr, int k1,
+                                   double bandwidth_scale,
                                    double *__restrict__ d2buf, double *__restrict__ eps, int *__restrict__ err_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp; i < n; i += nwarps) {
+    // i is a LOCAL row (n = number of local rows); the query point is global row row_begin + i
     const int c = (int)(cptr[i + 1] - cptr[i]);
     const int32_t *ci = cand + cptr[i];
     double *di = d2buf + cptr[i];
-    const double *xi = X + i * d;
+    const double *xi = X + (row_begin + i) * d;
     for (int t = lane; t < c; t += 32) {
       const double *xj = X + (int64_t)ci[t] * d;
       double acc = 0.0;
@@ -395,11 +397,11 @@ __global__ void laplacian_kernel(int64_t n, const int32_t *__restrict__ row_ptr,
 }
 
 // candidate pairs (row << 32 | col), sorted: cptr[r] = first pair of row r (lower bound), cptr[n] = total
-__global__ void pair_row_ptr_kernel(const unsigned long long *__restrict__ keys, int64_t total, int64_t n,
-                                    int64_t *__restrict__ cptr) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void pair_row_ptr_kernel(const unsigned long long *__restrict__ keys, int64_t total, int64_t row_begin,
+                                    int64_t n, int64_t *__restrict__ cptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // local row; n = number of local rows
   if (r > n) return;
-  const unsigned long long target = (unsigned long long)r << 32;
+  const unsigned long long target = (unsigned long long)(row_begin + r) << 32;
   int64_t lo = 0, hi = total;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
@@ -419,6 +421,11 @@ __global__ void pair_cols_kernel(const unsigned long long *__restrict__ keys, in
 __global__ void row_counts_kernel(const int64_t *__restrict__ cptr, int64_t n, int32_t *__restrict__ cnt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) cnt[i] = (int32_t)(cptr[i + 1] - cptr[i]);
+}
+
+__global__ void row_counts64_kernel(const int64_t *__restrict__ cptr, int64_t n, int64_t *__restrict__ cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt[i] = cptr[i + 1] - cptr[i];
 }
 
 __global__ void max_count_kernel(const int64_t *__restrict__ cptr, int64_t n, int32_t *out) {
@@ -527,6 +534,7 @@ static int morton_order(const double *X, int64_t n, int64_t d, cudaStream_t stre
 // Steps 0 and 1: centred norms, pass 1 (eps upper bounds), pass 2 (candidate pairs), pairs sorted into a
 // CSR of candidates: cand[cptr[i] .. cptr[i+1]) = candidate columns of row i, ascending.
 struct Candidates {
+  int64_t row_begin = 0, row_end = 0;  // query rows of this call; cptr is local (row_end - row_begin + 1 entries)
   DevBuf<float> key2;
   DevBuf<int64_t> cptr;   // n + 1
   DevBuf<int32_t> cand;   // total
@@ -538,7 +546,10 @@ struct Candidates {
 };
 
 static int candidate_search(const double *X, int64_t n, int64_t d, int k1, double radius_factor, bool simt,
-                            cudaStream_t stream, Candidates &out) {
+                            int64_t row_begin, int64_t row_end, cudaStream_t stream, Candidates &out) {
+  const int64_t nloc = row_end - row_begin;
+  out.row_begin = row_begin;
+  out.row_end = row_end;
   // -- 0. means / norms
   DevBuf<double> partial, mu, norm;
   DevBuf<unsigned long long> ymax2;
@@ -556,7 +567,7 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
 
   // -- 1. candidate search
   SearchPlan plan;
-  MELD_CHECK(search_plan(simt, n, d, k1, &plan));
+  MELD_CHECK(search_plan(simt, n, d, k1, row_begin, row_end, &plan));
   SearchState st;
   MELD_CHECK(search_prepare(plan, X, mu.p, norm.p, stream, &st));
   DevBuf<float> lists;
@@ -565,16 +576,17 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
   StageTimer tm(stream);
   MELD_CHECK(search_pass1(plan, st, lists.p, stream));
   tm.lap("search pass 1 (top-k)");
-  merge_lists_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(lists.p, n, plan.nlists, k1, norm.p, ymax2.p,
-                                                                      plan.margin_c, radius_factor, out.key2.p);
+  merge_lists_kernel<<<(unsigned)ceil_div(nloc, 128), 128, 0, stream>>>(lists.p, row_begin, row_end, plan.nlists, k1,
+                                                                         norm.p, ymax2.p, plan.margin_c, radius_factor,
+                                                                         out.key2.p);
   MELD_LAUNCH_CHECK();
   lists.release();
   out.passes = 1;
 
   // pass 2 appends (row, col) pairs to one global buffer; sized generously, retried with the exact
   // total if it overflows
-  int64_t pair_cap = n * (k1 <= 8 ? 96 : 192);
-  if (pair_cap > n * n) pair_cap = n * n;
+  int64_t pair_cap = nloc * (k1 <= 8 ? 96 : 192);
+  if (pair_cap > nloc * n) pair_cap = nloc * n;
   DevBuf<unsigned long long> pairs, pairs_sorted, gcount;
   MELD_CHECK(gcount.alloc(1));
   unsigned long long h_total = 0;
@@ -614,16 +626,17 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
     MELD_CHECK(tmp.alloc(tmp_bytes));
     MELD_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, pairs.p, pairs_sorted.p, (int)out.total, 0, end_bit,
                                              stream));
-    MELD_CHECK(out.cptr.alloc((size_t)n + 1));
+    MELD_CHECK(out.cptr.alloc((size_t)nloc + 1));
     MELD_CHECK(out.cand.alloc((size_t)out.total));
-    pair_row_ptr_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(pairs_sorted.p, out.total, n, out.cptr.p);
+    pair_row_ptr_kernel<<<(unsigned)ceil_div(nloc + 1, 256), 256, 0, stream>>>(pairs_sorted.p, out.total, row_begin, nloc,
+                                                                              out.cptr.p);
     MELD_LAUNCH_CHECK();
     pair_cols_kernel<<<sm_count() * 8, 256, 0, stream>>>(pairs_sorted.p, out.total, out.cand.p);
     MELD_LAUNCH_CHECK();
     DevBuf<int32_t> mx;
     MELD_CHECK(mx.alloc(1));
     MELD_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int32_t), stream));
-    max_count_kernel<<<296, 256, 0, stream>>>(out.cptr.p, n, mx.p);
+    max_count_kernel<<<296, 256, 0, stream>>>(out.cptr.p, nloc, mx.p);
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaMemcpyAsync(&out.max_per_row, mx.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
@@ -632,78 +645,86 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
   return 0;
 }
 
-extern "C" {
+// ---- the two stages of a build ------------------------------------------------------------------------
+struct BuildParams {
+  int knn = 0, k1 = 0;
+  double decay = 0, thresh_eff = 0, anisotropy = 0, bandwidth_scale = 1, radius_factor = 1;
+  bool simt = false, keep_raw = false;
+};
 
-int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay, double thresh,
-                              double anisotropy, double bandwidth_scale, int flags, void *stream_,
-                              meld_b200_graph_t **graph_out) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  MELD_REQUIRE(graph_out != nullptr, "knn_graph_build: graph_out is NULL");
-  *graph_out = nullptr;
-  MELD_REQUIRE(X != nullptr && n >= 2 && d >= 1, "knn_graph_build: bad data shape (%lld, %lld)", (long long)n,
-               (long long)d);
-  MELD_REQUIRE(n < (int64_t)2000000000, "knn_graph_build: n too large for int32 columns");
-  MELD_REQUIRE(knn >= 1 && (int64_t)knn + 1 <= n, "knn_graph_build: knn=%d with n=%lld", knn, (long long)n);
-  MELD_REQUIRE(knn + 1 <= kMaxK1, "knn_graph_build: knn + 1 = %d exceeds the engine limit %d", knn + 1, kMaxK1);
-  MELD_REQUIRE(decay > 0 && isfinite(decay), "knn_graph_build: decay=%g (decay=None is not supported)", decay);
-  MELD_REQUIRE(thresh > 0 && thresh < 1, "knn_graph_build: thresh=%g outside (0, 1)", thresh);
-  MELD_REQUIRE(anisotropy >= 0 && anisotropy <= 1, "knn_graph_build: anisotropy=%g outside [0, 1]", anisotropy);
-  MELD_REQUIRE(bandwidth_scale > 0, "knn_graph_build: bandwidth_scale=%g", bandwidth_scale);
-  const int k1 = knn + 1;
-  const double thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
-  const double rho = pow(-log(thresh_eff), 1.0 / decay);  // kernel radius in units of eps_i
-  double radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
-  if (radius_factor < 1.0) radius_factor = 1.0;  // the k1 nearest must be candidates to get eps_i
-  const bool simt = (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0;
-  const bool keep_raw = (flags & MELD_B200_FLAG_KEEP_KNN_KERNEL) != 0;
+static int parse_build_params(const char *who, int64_t n, int64_t d, int knn, double decay, double thresh,
+                              double anisotropy, double bandwidth_scale, int flags, BuildParams *bp) {
+  MELD_REQUIRE(n >= 2 && d >= 1, "%s: bad data shape (%lld, %lld)", who, (long long)n, (long long)d);
+  MELD_REQUIRE(n < (int64_t)2000000000, "%s: n too large for int32 columns", who);
+  MELD_REQUIRE(knn >= 1 && (int64_t)knn + 1 <= n, "%s: knn=%d with n=%lld", who, knn, (long long)n);
+  MELD_REQUIRE(knn + 1 <= kMaxK1, "%s: knn + 1 = %d exceeds the engine limit %d", who, knn + 1, kMaxK1);
+  MELD_REQUIRE(decay > 0 && isfinite(decay), "%s: decay=%g (decay=None is not supported)", who, decay);
+  MELD_REQUIRE(thresh > 0 && thresh < 1, "%s: thresh=%g outside (0, 1)", who, thresh);
+  MELD_REQUIRE(anisotropy >= 0 && anisotropy <= 1, "%s: anisotropy=%g outside [0, 1]", who, anisotropy);
+  MELD_REQUIRE(bandwidth_scale > 0, "%s: bandwidth_scale=%g", who, bandwidth_scale);
+  bp->knn = knn;
+  bp->k1 = knn + 1;
+  bp->decay = decay;
+  bp->anisotropy = anisotropy;
+  bp->bandwidth_scale = bandwidth_scale;
+  bp->thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
+  const double rho = pow(-log(bp->thresh_eff), 1.0 / decay);  // kernel radius in units of eps_i
+  bp->radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
+  if (bp->radius_factor < 1.0) bp->radius_factor = 1.0;  // the k1 nearest must be candidates to get eps_i
+  bp->simt = (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0;
+  bp->keep_raw = (flags & MELD_B200_FLAG_KEEP_KNN_KERNEL) != 0;
+  return 0;
+}
 
+// Stage 1 (row-local, shards over query rows with no exchange): candidate search + exact distances + eps
+// for rows [row_begin, row_end) of X (already in internal cell order).
+static int build_stage1(const double *X, int64_t n, int64_t d, const BuildParams &bp, int64_t row_begin,
+                        int64_t row_end, cudaStream_t stream, Candidates &cs, DevBuf<double> &d2, DevBuf<double> &eps) {
   StageTimer tm(stream);
-  // -- 0a. internal cell order (Morton curve over the highest-variance features)
-  DevBuf<double> Xp;
-  DevBuf<int32_t> perm;
-  if (tuning().reorder && n >= 4096) {
-    MELD_CHECK(morton_order(X, n, d, stream, perm, Xp));
-    X = Xp.p;
-  }
-
-  tm.lap("morton order");
-  // -- 0./1. means, norms, candidate search
-  Candidates cs;
-  MELD_CHECK(candidate_search(X, n, d, k1, radius_factor, simt, stream, cs));
+  MELD_CHECK(candidate_search(X, n, d, bp.k1, bp.radius_factor, bp.simt, row_begin, row_end, stream, cs));
   cs.key2.release();
   tm.lap("candidate search total");
-  DevBuf<int32_t> &cand = cs.cand;
-  const int64_t *cptr = cs.cptr.p;
-  const int passes = cs.passes;
-
-  // -- 2. exact distances, eps
-  DevBuf<double> vbuf, eps, kraw;
+  const int64_t nloc = row_end - row_begin;
   DevBuf<int> err;
-  MELD_CHECK(vbuf.alloc((size_t)cs.total));
-  MELD_CHECK(eps.alloc((size_t)n));
+  MELD_CHECK(d2.alloc((size_t)cs.total));
+  MELD_CHECK(eps.alloc((size_t)nloc));
   MELD_CHECK(err.alloc(1));
   MELD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
-  refine_dist_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(X, n, d, cand.p, cptr, k1, bandwidth_scale,
-                                                            vbuf.p, eps.p, err.p);
+  refine_dist_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(X, row_begin, nloc, d, cs.cand.p, cs.cptr.p, bp.k1,
+                                                               bp.bandwidth_scale, d2.p, eps.p, err.p);
   MELD_LAUNCH_CHECK();
-
+  int h_err = 0;
+  MELD_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  MELD_CUDA(cudaStreamSynchronize(stream));
+  if (h_err) {
+    set_error("knn graph build: a row has fewer than knn+1 candidates (candidate search failed)");
+    return MELD_B200_ERR_INTERNAL;
+  }
   tm.lap("refine (exact distances)");
-  // -- 3. kernel values + symmetrisation
-  DevBuf<int32_t> kept, extra, total;
+  return 0;
+}
+
+// Stage 2 (needs every row's candidates and eps): kernel values, symmetrisation, sort, anisotropy, Laplacian.
+// cand / vbuf are consumed (flags and values are written in place); perm is handed to the graph.
+static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *vbuf, int64_t total, const double *eps,
+                        const BuildParams &bp, DevBuf<int32_t> &perm, cudaStream_t stream, meld_b200_graph **graph_out) {
+  StageTimer tm(stream);
+  DevBuf<double> kraw;
+  DevBuf<int32_t> kept, extra, tot;
   MELD_CHECK(kept.alloc((size_t)n));
   MELD_CHECK(extra.alloc((size_t)n));
-  MELD_CHECK(total.alloc((size_t)n + 1));
+  MELD_CHECK(tot.alloc((size_t)n + 1));
   MELD_CUDA(cudaMemsetAsync(extra.p, 0, (size_t)n * sizeof(int32_t), stream));
-  if (keep_raw) MELD_CHECK(kraw.alloc((size_t)cs.total));
-  kernel_values_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cptr, vbuf.p, eps.p, decay,
-                                                              thresh_eff, kept.p, extra.p, keep_raw ? kraw.p : nullptr);
+  if (bp.keep_raw) MELD_CHECK(kraw.alloc((size_t)total));
+  kernel_values_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand, cptr, vbuf, eps, bp.decay, bp.thresh_eff, kept.p,
+                                                              extra.p, bp.keep_raw ? kraw.p : nullptr);
   MELD_LAUNCH_CHECK();
-  add_counts_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(kept.p, extra.p, n, total.p);
+  add_counts_kernel<<<(unsigned)ceil_div(n + 1, 256), 256, 0, stream>>>(kept.p, extra.p, n, tot.p);
   MELD_LAUNCH_CHECK();
 
   meld_b200_graph *g = new (std::nothrow) meld_b200_graph();
   if (!g) {
-    set_error("knn_graph_build: host allocation failed");
+    set_error("knn graph build: host allocation failed");
     return MELD_B200_ERR_NOMEM;
   }
   struct Guard {
@@ -716,21 +737,15 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   MELD_CUDA(cudaMemsetAsync(g->row_ptr.p + n + 1, 0, kCsrPad * sizeof(int32_t), stream));
   {
     size_t tmp_bytes = 0;
-    MELD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, total.p, g->row_ptr.p, (int)(n + 1), stream));
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tot.p, g->row_ptr.p, (int)(n + 1), stream));
     DevBuf<unsigned char> tmp;
     MELD_CHECK(tmp.alloc(tmp_bytes));
-    MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, total.p, g->row_ptr.p, (int)(n + 1), stream));
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, tot.p, g->row_ptr.p, (int)(n + 1), stream));
     int32_t h_nnz = 0;
-    int h_err = 0;
     MELD_CUDA(cudaMemcpyAsync(&h_nnz, g->row_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));
-    if (h_err) {
-      set_error("knn_graph_build: a row has fewer than knn+1 candidates (candidate search failed)");
-      return MELD_B200_ERR_INTERNAL;
-    }
     if (h_nnz < 0) {
-      set_error("knn_graph_build: nnz overflows int32");
+      set_error("knn graph build: nnz overflows int32");
       return MELD_B200_ERR_UNSUPPORTED;
     }
     g->nnz = h_nnz;
@@ -742,8 +757,8 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     MELD_CHECK(uval.alloc((size_t)g->nnz));
     MELD_CHECK(cursor.alloc((size_t)n));
     MELD_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)n * sizeof(int32_t), stream));
-    fill_sym_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cptr, vbuf.p, g->row_ptr.p, kept.p,
-                                                           cursor.p, ucol.p, uval.p);
+    fill_sym_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand, cptr, vbuf, g->row_ptr.p, kept.p, cursor.p, ucol.p,
+                                                           uval.p);
     MELD_LAUNCH_CHECK();
     MELD_CHECK(g->col.alloc((size_t)g->nnz + kCsrPad));
     MELD_CHECK(g->val.alloc((size_t)g->nnz + kCsrPad));
@@ -758,10 +773,9 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
                                                   (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
   }
-
   tm.lap("kernel values, fill, sort");
-  // optional export copy of the un-symmetrised kernel
-  if (keep_raw) {
+
+  if (bp.keep_raw) {  // export copy of the un-symmetrised kernel
     DevBuf<int64_t> rp64;
     MELD_CHECK(rp64.alloc((size_t)n + 1));
     MELD_CHECK(g->knn_cnt.alloc((size_t)n + 1));
@@ -780,19 +794,18 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     MELD_CHECK(g->knn_val.alloc((size_t)h_raw));
     MELD_CHECK(g->knn_ptr.alloc((size_t)n + 1));
     MELD_CUDA(cudaMemcpyAsync(g->knn_ptr.p, rp64.p, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
-    fill_raw_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand.p, cptr, kraw.p, g->knn_ptr.p,
-                                                           g->knn_col.p, g->knn_val.p);
+    fill_raw_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand, cptr, kraw.p, g->knn_ptr.p, g->knn_col.p,
+                                                           g->knn_val.p);
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaStreamSynchronize(stream));
   }
 
-  // -- 4. anisotropy + Laplacian
-  {
+  {  // anisotropy + Laplacian
     DevBuf<double> q;
     MELD_CHECK(q.alloc((size_t)n));
     row_sum_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(n, g->row_ptr.p, g->val.p, q.p);
     MELD_LAUNCH_CHECK();
-    laplacian_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(n, g->row_ptr.p, g->col.p, g->val.p, q.p, anisotropy);
+    laplacian_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(n, g->row_ptr.p, g->col.p, g->val.p, q.p, bp.anisotropy);
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaStreamSynchronize(stream));
   }
@@ -805,12 +818,181 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
     perm.p = nullptr;
     perm.n = 0;
   }
-  g->stats[0] = passes;
-  g->stats[1] = cs.max_per_row;
-  g->stats[2] = cs.total;
-  g->stats[3] = cs.retries;
-  g->stats[4] = simt ? 1 : 0;
+  g->stats[2] = total;
+  g->stats[4] = bp.simt ? 1 : 0;
   guard.g = nullptr;
+  *graph_out = g;
+  return 0;
+}
+
+// Opaque result of stage 1 for a row range (include/meld_b200.h: meld_b200_cands_t).
+struct meld_b200_cands {
+  int64_t n = 0, d = 0, row_begin = 0, row_end = 0, total = 0;
+  meld::DevBuf<int64_t> cptr;  // local rows + 1
+  meld::DevBuf<int32_t> cand;  // total
+  meld::DevBuf<double> d2;     // total
+  meld::DevBuf<double> eps;    // local rows
+  meld::DevBuf<int32_t> perm;  // n, or empty (identity)
+  int32_t max_per_row = 0;
+  int passes = 0;
+};
+
+extern "C" {
+
+int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay, double thresh,
+                              double anisotropy, double bandwidth_scale, int flags, void *stream_,
+                              meld_b200_graph_t **graph_out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(graph_out != nullptr, "knn_graph_build: graph_out is NULL");
+  *graph_out = nullptr;
+  MELD_REQUIRE(X != nullptr, "knn_graph_build: X is NULL");
+  BuildParams bp;
+  MELD_CHECK(parse_build_params("knn_graph_build", n, d, knn, decay, thresh, anisotropy, bandwidth_scale, flags, &bp));
+  StageTimer tm(stream);
+  // internal cell order (Morton curve over the highest-variance features)
+  DevBuf<double> Xp;
+  DevBuf<int32_t> perm;
+  if (tuning().reorder && n >= 4096) {
+    MELD_CHECK(morton_order(X, n, d, stream, perm, Xp));
+    X = Xp.p;
+  }
+  tm.lap("morton order");
+  Candidates cs;
+  DevBuf<double> d2, eps;
+  MELD_CHECK(build_stage1(X, n, d, bp, 0, n, stream, cs, d2, eps));
+  Xp.release();
+  meld_b200_graph *g = nullptr;
+  MELD_CHECK(build_stage2(n, cs.cptr.p, cs.cand.p, d2.p, cs.total, eps.p, bp, perm, stream, &g));
+  g->stats[0] = cs.passes;
+  g->stats[1] = cs.max_per_row;
+  g->stats[3] = cs.retries;
+  *graph_out = g;
+  return 0;
+}
+
+int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, double decay, double thresh,
+                             double bandwidth_scale, int64_t row_begin, int64_t row_end, int flags, void *stream_,
+                             meld_b200_cands_t **cands_out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(cands_out != nullptr && X != nullptr, "knn_candidates: NULL argument");
+  *cands_out = nullptr;
+  BuildParams bp;
+  MELD_CHECK(parse_build_params("knn_candidates", n, d, knn, decay, thresh, 1.0, bandwidth_scale, flags, &bp));
+  MELD_REQUIRE(row_begin >= 0 && row_begin < row_end && row_end <= n, "knn_candidates: bad row range [%lld, %lld)",
+               (long long)row_begin, (long long)row_end);
+  meld_b200_cands *c = new (std::nothrow) meld_b200_cands();
+  if (!c) {
+    set_error("knn_candidates: host allocation failed");
+    return MELD_B200_ERR_NOMEM;
+  }
+  struct Guard {
+    meld_b200_cands *c;
+    ~Guard() { delete c; }
+  } guard{c};
+  c->n = n;
+  c->d = d;
+  c->row_begin = row_begin;
+  c->row_end = row_end;
+  DevBuf<double> Xp;
+  if (tuning().reorder && n >= 4096) {  // every rank derives the same order from the same data
+    MELD_CHECK(morton_order(X, n, d, stream, c->perm, Xp));
+    X = Xp.p;
+  }
+  Candidates cs;
+  MELD_CHECK(build_stage1(X, n, d, bp, row_begin, row_end, stream, cs, c->d2, c->eps));
+  c->total = cs.total;
+  c->max_per_row = cs.max_per_row;
+  c->passes = cs.passes;
+  c->cptr.p = cs.cptr.p;
+  c->cptr.n = cs.cptr.n;
+  cs.cptr.p = nullptr;
+  cs.cptr.n = 0;
+  c->cand.p = cs.cand.p;
+  c->cand.n = cs.cand.n;
+  cs.cand.p = nullptr;
+  cs.cand.n = 0;
+  guard.c = nullptr;
+  *cands_out = c;
+  return 0;
+}
+
+int meld_b200_cands_info(const meld_b200_cands_t *c, int64_t *n_rows_host, int64_t *total_host, int *has_perm_host,
+                         int64_t *max_per_row_host) {
+  MELD_REQUIRE(c != nullptr, "cands_info: NULL handle");
+  if (n_rows_host) *n_rows_host = c->row_end - c->row_begin;
+  if (total_host) *total_host = c->total;
+  if (has_perm_host) *has_perm_host = c->perm.p ? 1 : 0;
+  if (max_per_row_host) *max_per_row_host = c->max_per_row;
+  return 0;
+}
+
+int meld_b200_cands_export(const meld_b200_cands_t *c, int64_t *counts, int32_t *cand, double *d2, double *eps,
+                           int32_t *perm, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(c != nullptr, "cands_export: NULL handle");
+  const int64_t nloc = c->row_end - c->row_begin;
+  if (counts) {
+    row_counts64_kernel<<<(unsigned)ceil_div(nloc, 256), 256, 0, stream>>>(c->cptr.p, nloc, counts);
+    MELD_LAUNCH_CHECK();
+  }
+  if (cand && c->total)
+    MELD_CUDA(cudaMemcpyAsync(cand, c->cand.p, (size_t)c->total * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  if (d2 && c->total)
+    MELD_CUDA(cudaMemcpyAsync(d2, c->d2.p, (size_t)c->total * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  if (eps) MELD_CUDA(cudaMemcpyAsync(eps, c->eps.p, (size_t)nloc * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  if (perm && c->perm.p)
+    MELD_CUDA(cudaMemcpyAsync(perm, c->perm.p, (size_t)c->n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+int meld_b200_cands_destroy(meld_b200_cands_t *c) {
+  delete c;
+  return 0;
+}
+
+int meld_b200_graph_from_candidates(int64_t n, const int64_t *counts, const int32_t *cand, const double *d2,
+                                    int64_t total, const double *eps, const int32_t *perm, int knn, double decay,
+                                    double thresh, double anisotropy, double bandwidth_scale, int flags, void *stream_,
+                                    meld_b200_graph_t **graph_out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MELD_REQUIRE(graph_out && counts && cand && d2 && eps, "graph_from_candidates: NULL argument");
+  *graph_out = nullptr;
+  BuildParams bp;
+  MELD_CHECK(parse_build_params("graph_from_candidates", n, 1, knn, decay, thresh, anisotropy, bandwidth_scale, flags,
+                                &bp));
+  MELD_REQUIRE(total >= n && total < (int64_t)2147483647, "graph_from_candidates: total=%lld", (long long)total);
+  // private, mutable copies (stage 2 rewrites candidates and distances in place)
+  DevBuf<int64_t> cptr;
+  DevBuf<int32_t> ccand, cperm;
+  DevBuf<double> vbuf;
+  MELD_CHECK(cptr.alloc((size_t)n + 1));
+  MELD_CHECK(ccand.alloc((size_t)total));
+  MELD_CHECK(vbuf.alloc((size_t)total));
+  {
+    size_t tmp_bytes = 0;
+    DevBuf<int64_t> cnt1;
+    MELD_CHECK(cnt1.alloc((size_t)n + 1));
+    MELD_CUDA(cudaMemcpyAsync(cnt1.p, counts, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+    MELD_CUDA(cudaMemsetAsync(cnt1.p + n, 0, sizeof(int64_t), stream));
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt1.p, cptr.p, (int)(n + 1), stream));
+    DevBuf<unsigned char> tmp;
+    MELD_CHECK(tmp.alloc(tmp_bytes));
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt1.p, cptr.p, (int)(n + 1), stream));
+    int64_t h_total = 0;
+    MELD_CUDA(cudaMemcpyAsync(&h_total, cptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_REQUIRE(h_total == total, "graph_from_candidates: counts sum to %lld, total says %lld", (long long)h_total,
+                 (long long)total);
+  }
+  MELD_CUDA(cudaMemcpyAsync(ccand.p, cand, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  MELD_CUDA(cudaMemcpyAsync(vbuf.p, d2, (size_t)total * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  if (perm) {
+    MELD_CHECK(cperm.alloc((size_t)n));
+    MELD_CUDA(cudaMemcpyAsync(cperm.p, perm, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  }
+  meld_b200_graph *g = nullptr;
+  MELD_CHECK(build_stage2(n, cptr.p, ccand.p, vbuf.p, total, eps, bp, cperm, stream, &g));
+  g->stats[0] = 2;
   *graph_out = g;
   return 0;
 }
@@ -826,7 +1008,8 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   double radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
   if (radius_factor < 1.0) radius_factor = 1.0;
   Candidates cs;
-  MELD_CHECK(candidate_search(X, n, d, knn + 1, radius_factor, (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0, stream, cs));
+  MELD_CHECK(candidate_search(X, n, d, knn + 1, radius_factor, (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0, 0, n, stream,
+                              cs));
   MELD_CUDA(cudaMemcpyAsync(key2_out, cs.key2.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   row_counts_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(cs.cptr.p, n, cnt_out);
   MELD_LAUNCH_CHECK();

@@ -18,6 +18,7 @@ constexpr int kMaxLists = 128;  // lists per row merged after pass 1
 struct SearchPlan {
   bool simt = false;
   int64_t n = 0, d = 0;
+  int64_t row_begin = 0, row_end = 0;  // query rows handled by this call (columns are always all n cells)
   int k1 = 0;
   int nseg = 1;    // column segments (independent work units per row tile)
   int nlists = 1;  // lists per row written by pass 1
@@ -40,7 +41,7 @@ struct SearchState {
   alignas(64) unsigned char tmap_b[128];
 };
 
-int search_plan(bool simt, int64_t n, int64_t d, int k1, SearchPlan *plan);
+int search_plan(bool simt, int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, SearchPlan *plan);
 int search_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
                    SearchState *st);
 int search_pass1(const SearchPlan &plan, SearchState &st, float *lists, cudaStream_t stream);
@@ -49,7 +50,7 @@ int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, uns
 void search_release(SearchState *st);
 
 // tcgen05 implementation (knn_tc.cu)
-int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan);
+int tc_plan(int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, SearchPlan *plan);
 int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
                SearchState *st);
 int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2,

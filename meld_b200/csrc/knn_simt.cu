@@ -23,7 +23,8 @@ __global__ void simt_prep_kernel(const double *__restrict__ X, const double *__r
 
 template <int MODE>
 __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restrict__ xc, const float *__restrict__ hn,
-                                                           int64_t n, int64_t d, int k1, int nseg,
+                                                           int64_t n, int64_t d, int64_t row_begin, int64_t row_end,
+                                                           int k1, int nseg,
                                                            float *__restrict__ lists, const float *__restrict__ key2,
                                                            unsigned long long *__restrict__ pairs,
                                                            unsigned long long *__restrict__ count, int64_t cap) {
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restr
   float *Ys = Xs + kChunk * (kRows + 1);    // [kCols][kYPitch]
   float *lst = Ys + kCols * kYPitch;        // [k1][kRows] (MODE 1)
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int64_t row0 = (int64_t)blockIdx.x * kRows;
+  const int64_t row0 = row_begin + (int64_t)blockIdx.x * kRows;
   const int64_t row = row0 + t;
   const int seg = blockIdx.y;
   const int64_t ntile = (n + kCols - 1) / kCols;
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restr
   if (MODE == 1) {
     for (int s = 0; s < k1; ++s) lst[s * kRows + t] = -INFINITY;
   } else {
-    thr = row < n ? key2[row] : INFINITY;
+    thr = row < row_end ? key2[row] : INFINITY;
   }
   for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
     const int64_t col0 = tile * kCols;
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restr
       for (int r = 0; r < 32; ++r) {  // warp w stages rows w*32 .. w*32+31, lane = feature
         const int64_t rr = row0 + w * 32 + r;
         const int64_t kk = k0 + lane;
-        Xs[lane * (kRows + 1) + w * 32 + r] = (rr < n && kk < d) ? xc[rr * d + kk] : 0.f;
+        Xs[lane * (kRows + 1) + w * 32 + r] = (rr < row_end && kk < d) ? xc[rr * d + kk] : 0.f;
       }
       for (int q = t; q < kCols * kChunk; q += kRows) {
         const int c = q / kChunk, k = q % kChunk;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restr
         }
       }
     }
-    if (row < n) {
+    if (row < row_end) {
 #pragma unroll
       for (int j = 0; j < kCols; ++j) {
         const int64_t col = col0 + j;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kRows) simt_search_kernel(const float *__restr
       }
     }
   }
-  if (MODE == 1 && row < n) {
+  if (MODE == 1 && row < row_end) {
     float *out = lists + ((size_t)row * nseg + seg) * k1;
     for (int s = 0; s < k1; ++s) out[s] = lst[s * kRows + t];
   }
@@ -112,13 +113,15 @@ static size_t simt_smem(int k1) {
   return sizeof(float) * ((size_t)kChunk * (kRows + 1) + (size_t)kCols * kYPitch + (size_t)k1 * kRows);
 }
 
-int search_plan(bool simt, int64_t n, int64_t d, int k1, SearchPlan *plan) {
-  if (!simt) return tc_plan(n, d, k1, plan);
+int search_plan(bool simt, int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, SearchPlan *plan) {
+  if (!simt) return tc_plan(n, d, k1, row_begin, row_end, plan);
   plan->simt = true;
   plan->n = n;
   plan->d = d;
   plan->k1 = k1;
-  const int64_t row_tiles = ceil_div(n, kRows), col_tiles = ceil_div(n, kCols);
+  plan->row_begin = row_begin;
+  plan->row_end = row_end;
+  const int64_t row_tiles = ceil_div(row_end - row_begin, kRows), col_tiles = ceil_div(n, kCols);
   int64_t nseg = ceil_div(4 * (int64_t)sm_count(), row_tiles);
   if (nseg > kMaxLists) nseg = kMaxLists;
   if (nseg > col_tiles) nseg = col_tiles;
@@ -143,8 +146,9 @@ int search_pass1(const SearchPlan &plan, SearchState &st, float *lists, cudaStre
   if (!plan.simt) return tc_pass(plan, st, 1, lists, nullptr, nullptr, nullptr, 0, stream);
   const size_t smem = simt_smem(plan.k1);
   MELD_CUDA(cudaFuncSetAttribute(simt_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(plan.n, kRows), (unsigned)plan.nseg);
-  simt_search_kernel<1><<<grid, kRows, smem, stream>>>(st.xc32.p, st.hn32.p, plan.n, plan.d, plan.k1, plan.nseg, lists,
+  dim3 grid((unsigned)ceil_div(plan.row_end - plan.row_begin, kRows), (unsigned)plan.nseg);
+  simt_search_kernel<1><<<grid, kRows, smem, stream>>>(st.xc32.p, st.hn32.p, plan.n, plan.d, plan.row_begin, plan.row_end,
+                                                       plan.k1, plan.nseg, lists,
                                                        nullptr, nullptr, nullptr, 0);
   MELD_LAUNCH_CHECK();
   return 0;
@@ -155,8 +159,9 @@ int search_pass2(const SearchPlan &plan, SearchState &st, const float *key2, uns
   if (!plan.simt) return tc_pass(plan, st, 2, nullptr, key2, pairs, count, cap, stream);
   const size_t smem = simt_smem(0);
   MELD_CUDA(cudaFuncSetAttribute(simt_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(plan.n, kRows), (unsigned)plan.nseg);
-  simt_search_kernel<2><<<grid, kRows, smem, stream>>>(st.xc32.p, st.hn32.p, plan.n, plan.d, plan.k1, plan.nseg,
+  dim3 grid((unsigned)ceil_div(plan.row_end - plan.row_begin, kRows), (unsigned)plan.nseg);
+  simt_search_kernel<2><<<grid, kRows, smem, stream>>>(st.xc32.p, st.hn32.p, plan.n, plan.d, plan.row_begin, plan.row_end,
+                                                       plan.k1, plan.nseg,
                                                        nullptr, key2, pairs, count, cap);
   MELD_LAUNCH_CHECK();
   return 0;

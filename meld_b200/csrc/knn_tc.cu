@@ -178,7 +178,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct TcArgs {
   int mode;  // 1: top-k1 lists, 2: emit candidates
   int64_t n;
-  int n_row_tiles, n_col_tiles, nseg, nkb, a_resident, k1;
+  int n_row_tiles, n_col_tiles, nseg, nkb, a_resident, k1;  // n_row_tiles: row tiles of THIS call
+  int rt_begin;        // first (global) row tile of this call
+  long long row_end;   // rows at or beyond it are not this call's
   int mc;         // cluster size (1, 2 or 4): each CTA loads 1/mc of a B tile and multicasts it to the cluster
   int n_passes;   // segments visited per row tile (pass 1 may stop early: any subset gives a valid bound)
   int n_stages;   // B (or A+B) ring depth
@@ -202,7 +204,7 @@ struct UnitPlan {
 __device__ __forceinline__ UnitPlan unit_plan(const TcArgs &a, int u) {
   UnitPlan p;
   const int pass = u / a.n_row_tiles;  // 0: own segment, then the following ones cyclically
-  p.rt = u % a.n_row_tiles;
+  p.rt = a.rt_begin + u % a.n_row_tiles;
   p.pass = pass;
   const int own_ct = ((p.rt - p.rt % a.mc) * BM) / BN;  // identical for every CTA of a cluster (lockstep)
   int own_seg = (int)(((int64_t)own_ct * a.nseg) / a.n_col_tiles);
@@ -371,9 +373,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int s = 0; s < a.k1; ++s) lst[s * 2 * BM + lcol] = -INFINITY;
         // start from the bound earlier segments of this row have published: values below it cannot be
         // among the k1 largest of the union, so this list only needs what beats it
-        thr = row < a.n ? __ldcg(a.thr_g + row) : INFINITY;
+        thr = row < a.row_end ? __ldcg(a.thr_g + row) : INFINITY;
       } else {
-        thr = row < a.n ? a.key2[row] : INFINITY;
+        thr = row < a.row_end ? a.key2[row] : INFINITY;
       }
       // pass 2: hits are queued per warp in shared memory and appended to the global pair buffer 32+ at a
       // time (one global atomic per flush), so the scan never waits on an atomic's round trip per hit
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (buf == 0) bphase ^= 1u;
       }
       if (a.mode == 2) flush_queue();
-      if (a.mode == 1 && row < a.n) {
+      if (a.mode == 1 && row < a.row_end) {
         float *out = a.lists + ((size_t)row * a.n_passes * 2 + up.pass * 2 + half) * a.k1;  // list per (segment, half)
         for (int s = 0; s < a.k1; ++s) out[s] = lst[s * 2 * BM + lcol];
         // publish (monotone max; floats >= 0 and < 0 both ordered through the signed/unsigned trick)
@@ -531,8 +533,13 @@ static int encode_operand_map(void *base, int64_t rows, int kp, int box_rows, un
   return 0;
 }
 
-int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan) {
+int tc_plan(int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, SearchPlan *plan) {
+  MELD_REQUIRE(row_begin % BM == 0 && (row_end % BM == 0 || row_end == n) && row_begin < row_end && row_end <= n,
+               "candidate search: row range [%lld, %lld) must be aligned to %d rows", (long long)row_begin,
+               (long long)row_end, BM);
   plan->simt = false;
+  plan->row_begin = row_begin;
+  plan->row_end = row_end;
   plan->n = n;
   plan->d = d;
   plan->k1 = k1;
@@ -541,7 +548,7 @@ int tc_plan(int64_t n, int64_t d, int k1, SearchPlan *plan) {
   MELD_REQUIRE(kp <= (1 << 20), "knn_graph_build: d=%lld too large for the tensor-core search", (long long)d);
   plan->kp = (int)kp;
   plan->n_pad = round_up(n, 4 * BM);  // row tiles come in multiples of the largest cluster size
-  const int64_t row_tiles = plan->n_pad / BM, col_tiles = plan->n_pad / BN;
+  const int64_t row_tiles = ceil_div(row_end - row_begin, BM), col_tiles = plan->n_pad / BN;
   // enough (row tile, segment) units for ~4 waves of the SMs, never more segments than column tiles;
   // and a segment's slice of the column operand (n_seg x K' bf16) should stay L2 resident while the
   // CTAs of that segment stream it (units are issued segment-major)
@@ -585,7 +592,10 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   TcArgs a{};
   a.mode = mode;
   a.n = plan.n;
-  a.n_row_tiles = (int)(plan.n_pad / BM);
+  a.rt_begin = (int)(plan.row_begin / BM);
+  a.row_end = (long long)plan.row_end;
+  // whole-data calls cover the padded tiles too (keeps tile counts even for clusters)
+  a.n_row_tiles = (int)((plan.row_end == plan.n ? plan.n_pad - plan.row_begin : plan.row_end - plan.row_begin) / BM);
   a.n_col_tiles = (int)(plan.n_pad / BN);
   a.nseg = plan.nseg;
   a.nkb = plan.kp / BK;
@@ -617,7 +627,7 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   // the streamed operand -- the kernel's real bound at K' = 320 -- by the cluster size
   int cs = tuning().tc_multicast;
   if (cs != 2 && cs != 4) cs = 1;
-  while (cs > 1 && (a.n_row_tiles % cs != 0 || units < cs)) cs >>= 1;
+  while (cs > 1 && (a.n_row_tiles % cs != 0 || a.rt_begin % cs != 0 || units < cs)) cs >>= 1;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;

@@ -62,6 +62,110 @@ class DeviceGraph:
         params = dict(knn=knn, decay=decay, thresh=thresh, anisotropy=anisotropy, bandwidth_scale=bandwidth_scale)
         return cls(out.value, params, device=X.device)
 
+    # ---- sharded construction (one process per GPU) ------------------------------------------------
+    @staticmethod
+    def shard_bounds(n, world, align=512):
+        """Row ranges of the candidate search per rank: contiguous runs of ``align``-row tiles."""
+        tiles = (n + align - 1) // align
+        base, rem = divmod(tiles, world)
+        bounds, t = [0], 0
+        for r in range(world):
+            t += base + (1 if r < rem else 0)
+            bounds.append(min(n, t * align))
+        return bounds
+
+    @staticmethod
+    def candidates(X, row_begin, row_end, knn, decay, thresh, bandwidth_scale=1.0, simt_search=False):
+        """Stage 1 of a build for query rows [row_begin, row_end) in the internal cell order: returns
+        CUDA tensors (counts int64, cand int32, d2 float64, eps float64, perm int32 or None)."""
+        torch = nv.require_cuda()
+        N, d = X.shape
+        dev = X.device
+        if row_end <= row_begin:
+            e = lambda dt: torch.empty(0, dtype=dt, device=dev)  # noqa: E731
+            return e(torch.int64), e(torch.int32), e(torch.float64), e(torch.float64), None
+        h = C.c_void_p()
+        nv.check(
+            nv.lib().meld_b200_knn_candidates(nv.ptr(X), N, d, int(knn), float(decay), float(thresh),
+                                              float(bandwidth_scale), int(row_begin), int(row_end),
+                                              nv.FLAG_SIMT_SEARCH if simt_search else 0, nv.current_stream_ptr(),
+                                              C.byref(h)),
+            "knn_candidates",
+        )
+        try:
+            nloc, total, has_perm, mx = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+            nv.check(nv.lib().meld_b200_cands_info(h, C.byref(nloc), C.byref(total), C.byref(has_perm), C.byref(mx)),
+                     "cands_info")
+            counts = torch.empty(nloc.value, dtype=torch.int64, device=dev)
+            cand = torch.empty(total.value, dtype=torch.int32, device=dev)
+            d2 = torch.empty(total.value, dtype=torch.float64, device=dev)
+            eps = torch.empty(nloc.value, dtype=torch.float64, device=dev)
+            perm = torch.empty(N, dtype=torch.int32, device=dev) if has_perm.value else None
+            nv.check(nv.lib().meld_b200_cands_export(h, nv.ptr(counts), nv.ptr(cand), nv.ptr(d2), nv.ptr(eps),
+                                                     nv.ptr(perm), nv.current_stream_ptr()), "cands_export")
+            torch.cuda.current_stream().synchronize()
+        finally:
+            nv.lib().meld_b200_cands_destroy(h)
+        return counts, cand, d2, eps, perm
+
+    @classmethod
+    def from_candidates(cls, N, counts, cand, d2, eps, perm, knn, decay, thresh, anisotropy, bandwidth_scale=1.0,
+                        keep_knn_kernel=False, device=None):
+        """Stage 2 of a build from the candidates of ALL rows (row order)."""
+        out = C.c_void_p()
+        nv.check(
+            nv.lib().meld_b200_graph_from_candidates(
+                int(N), nv.ptr(counts.contiguous()), nv.ptr(cand.contiguous()), nv.ptr(d2.contiguous()),
+                int(cand.shape[0]), nv.ptr(eps.contiguous()), nv.ptr(perm), int(knn), float(decay), float(thresh),
+                float(anisotropy), float(bandwidth_scale), nv.FLAG_KEEP_KNN_KERNEL if keep_knn_kernel else 0,
+                nv.current_stream_ptr(), C.byref(out)),
+            "graph_from_candidates",
+        )
+        params = dict(knn=knn, decay=decay, thresh=thresh, anisotropy=anisotropy, bandwidth_scale=bandwidth_scale)
+        return cls(out.value, params, device=device if device is not None else cand.device)
+
+    @classmethod
+    def from_data_sharded(cls, data_nu, knn=5, decay=40.0, thresh=1e-4, anisotropy=1.0, bandwidth_scale=1.0, group=None):
+        """Build the graph with the candidate search (the dominant stage) sharded over the ranks of
+        ``torch.distributed`` by query rows; one NCCL all-gather of the per-row candidate lists follows,
+        then every rank assembles the same Laplacian.  Every rank passes the same data."""
+        torch = nv.require_cuda()
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        X = _as_device_f64(torch, data_nu)
+        N, d = X.shape
+        if knn + 1 > N:
+            raise ValueError("knn + 1 = {} exceeds the number of cells {}".format(knn + 1, N))
+        bounds = cls.shard_bounds(N, world)
+        counts, cand, d2, eps, perm = cls.candidates(X, bounds[rank], bounds[rank + 1], knn, decay, thresh,
+                                                     bandwidth_scale)
+        sizes = torch.tensor([counts.shape[0], cand.shape[0]], dtype=torch.int64, device=X.device)
+        all_sizes = torch.empty(2 * world, dtype=torch.int64, device=X.device)
+        dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+        all_sizes = all_sizes.cpu().view(world, 2)
+
+        def gather_var(local, lens):
+            longest = int(max(lens))
+            pad = torch.zeros(longest, dtype=local.dtype, device=local.device)
+            pad[: local.shape[0]] = local
+            out = torch.empty(world * longest, dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(out, pad, group=group)
+            return torch.cat([out[r * longest: r * longest + int(lens[r])] for r in range(world)])
+
+        rows, tots = all_sizes[:, 0].tolist(), all_sizes[:, 1].tolist()
+        counts = gather_var(counts, rows)
+        eps = gather_var(eps, rows)
+        cand = gather_var(cand, tots)
+        d2 = gather_var(d2, tots)
+        if perm is None and N >= 4096:  # a rank with an empty row range did not compute the order
+            perm = torch.empty(N, dtype=torch.int32, device=X.device)
+        if N >= 4096:
+            src = next(r for r in range(world) if rows[r] > 0)
+            dist.broadcast(perm, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+        return cls.from_candidates(N, counts, cand, d2, eps, perm, knn, decay, thresh, anisotropy, bandwidth_scale,
+                                   device=X.device)
+
     @classmethod
     def from_scipy(cls, L, row0=0, n_cols=None, params=None):
         """Adopt a Laplacian (or a row slice of one) built elsewhere, e.g. by the test oracle."""

@@ -96,6 +96,8 @@ class MELD(object):
         self.n_jobs = kwargs.pop("n_jobs", 1)
         self.random_state = kwargs.pop("random_state", None)
         self.verbose = kwargs.pop("verbose", 1)
+        # engine extension: shard the graph build over torch.distributed ranks (one process per GPU)
+        self.distributed = bool(kwargs.pop("distributed", False))
         self.anisotropy = anisotropy
         self.n_landmark = n_landmark
         self.kwargs = kwargs  # remaining graphtools.Graph keywords, checked at fit time
@@ -258,7 +260,10 @@ class MELD(object):
         data_nu = self._reduce_data(X)
         self._log("Calculating graph and diffusion operator...")
         t1 = time.perf_counter()
-        self.graph = DeviceGraph.from_data(
+        build = DeviceGraph.from_data
+        if self.distributed:  # candidate search sharded over the ranks of torch.distributed (same data on every rank)
+            build = DeviceGraph.from_data_sharded
+        self.graph = build(
             data_nu, knn=self.knn, decay=self.decay, thresh=self.thresh, anisotropy=self.anisotropy,
             bandwidth_scale=extra.get("bandwidth_scale", 1.0),
         )

@@ -128,3 +128,28 @@ def test_duplicate_points_and_small_n(mb):
     L = graph.to_scipy_L()
     assert _same_pattern(L, ref["L"])
     assert np.abs(L.data - ref["L"].data).max() <= 1e-10 * np.abs(ref["L"].data).max()
+
+
+def test_two_stage_build_over_row_ranges_matches_single_call(mb):
+    """The sharded build's C-ABI stages, driven on one GPU: stage 1 over two row ranges, concatenated,
+    then stage 2, reproduces meld_b200_knn_graph_build exactly (same graph, bit for bit)."""
+    import torch
+    from meld_b200.graph import DeviceGraph, _as_device_f64
+
+    X, _ = mb.synthetic.make_blobs(6000, 30, 6, 3, 8.0, seed=5)  # >= 4096 cells: Morton order is active
+    kw = dict(knn=9, decay=40.0, thresh=1e-4)
+    ref = DeviceGraph.from_data(X, anisotropy=1.0, **kw).to_scipy_L()
+    Xd = _as_device_f64(torch, X)
+    bounds = DeviceGraph.shard_bounds(X.shape[0], 3)
+    assert bounds == [0, 2048, 4096, 6000]
+    parts = [DeviceGraph.candidates(Xd, a, b, **kw) for a, b in zip(bounds[:-1], bounds[1:])]
+    counts = torch.cat([p[0] for p in parts])
+    cand = torch.cat([p[1] for p in parts])
+    d2 = torch.cat([p[2] for p in parts])
+    eps = torch.cat([p[3] for p in parts])
+    perm = parts[0][4]
+    assert perm is not None and all(torch.equal(p[4], perm) for p in parts)
+    g = DeviceGraph.from_candidates(X.shape[0], counts, cand, d2, eps, perm, anisotropy=1.0, **kw)
+    L = g.to_scipy_L()
+    assert _same_pattern(L, ref)
+    assert np.array_equal(L.data, ref.data)
