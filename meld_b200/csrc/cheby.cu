@@ -95,6 +95,7 @@ struct StepArgs {
   int rows_cap;    // rows whose T/R slices are staged
   int n_stage;     // pipeline depth
   int gather_warps;
+  int x_mode;      // 0: dictionary + cp.async gathers; 1: staged (val, col) and direct register gathers
   int team_warps;  // compute warps per team (one team per in-flight block)
   int gather_rows; // dictionary rows fetched per warp-level cp.async instruction
   int stage_epi;   // 1: the T/R arrays are library workspace (padded), slices may be bulk-copied
@@ -163,7 +164,7 @@ struct BlockView {
   const double *tc, *told, *rold;  // per-row slices indexed by (row * P + k), or nullptr -> global
 };
 
-template <int P, int G, bool STAGED>
+template <int P, int G, int MODE>  // 0: all from global, 1: dictionary stage, 2: staged (val, col) + direct gathers
 __device__ __forceinline__ void process_rows(const StepArgs &a, const BlockView &bv, int r0, int r1, int gid, int gl,
                                              int ngroups) {
   for (int rb = r0; rb < r1; rb += ngroups) {  // uniform trip count for all compute warps (full-mask shuffles)
@@ -193,7 +194,7 @@ __device__ __forceinline__ void process_rows(const StepArgs &a, const BlockView 
         const int eu = e + u * G;
         if (eu < ee) {
           v[u] = bv.vs[eu];
-          if constexpr (STAGED)
+          if constexpr (MODE == 1)
             smem_row<P>(bv.xs, (int)bv.ls[eu], x[u]);
           else
             gather_row<P>(a.Tcur, bv.cs[eu], x[u]);
@@ -254,7 +255,7 @@ __device__ __forceinline__ BlockGeom block_geom(const StepArgs &a, int b) {
   g.ra = g.r0 & ~3;
   g.nr = ((g.r1 + 1 - g.ra) + 3) & ~3;
   g.u = __ldg(a.dcnt + b);
-  g.staged = g.u >= 0 && g.nal <= a.cap && g.nr <= a.rcap && g.u <= a.ucap && g.e1 > g.e0;
+  g.staged = g.u >= 0 && g.nal <= a.cap && g.nr <= a.rcap && g.u <= a.ucap && g.e1 > g.e0;  // x_mode 1: u == 0
   g.epi_staged = g.staged && a.stage_epi && (g.r1 - g.r0) <= a.rows_cap;
   const size_t c0 = (size_t)(a.row0 + g.r0) * P, c1 = (size_t)(a.row0 + g.r1) * P;
   const size_t l0 = (size_t)g.r0 * P, l1 = (size_t)g.r1 * P;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
   const int ns = a.n_stage;
   // stage layout (bytes): values | local indices | row pointers | dictionary | gathered rows | tc | told | rold
   const int off_l = a.cap * 8;
-  const int off_r = off_l + a.cap * 2;
+  const int off_r = off_l + a.cap * (a.x_mode == 1 ? 4 : 2);  // uint16 dictionary positions or int32 columns
   const int off_d = off_r + a.rcap * 4;
   const int off_x = off_d + a.ucap * 4;
   const int epi_len = a.rows_cap * P + 2;
@@ -309,8 +310,9 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
           mbar_arrive(&full_mat[s]);  // direct block: nothing staged, the phase still advances
           continue;
         }
-        const uint32_t ub = (uint32_t)((g.u + 3) & ~3) * 4u;
-        uint32_t bytes = (uint32_t)g.nal * 10u + (uint32_t)g.nr * 4u + ub;
+        const uint32_t ub = a.x_mode == 1 ? 0u : (uint32_t)((g.u + 3) & ~3) * 4u;
+        const uint32_t ib = (uint32_t)g.nal * (a.x_mode == 1 ? 4u : 2u);
+        uint32_t bytes = (uint32_t)g.nal * 8u + ib + (uint32_t)g.nr * 4u + ub;
         if (g.epi_staged) {
           bytes += (uint32_t)g.nc * 8u;
           if (a.gamma != 0.0) bytes += (uint32_t)g.nl * 8u;
@@ -318,7 +320,10 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
         }
         mbar_arrive_expect_tx(&full_mat[s], bytes);
         bulk_g2s(st, a.val + g.a0, (uint32_t)g.nal * 8u, &full_mat[s]);
-        bulk_g2s(st + off_l, a.lidx + g.a0, (uint32_t)g.nal * 2u, &full_mat[s]);
+        if (a.x_mode == 1)
+          bulk_g2s(st + off_l, a.col + g.a0, ib, &full_mat[s]);
+        else
+          bulk_g2s(st + off_l, a.lidx + g.a0, ib, &full_mat[s]);
         bulk_g2s(st + off_r, a.row_ptr + g.ra, (uint32_t)g.nr * 4u, &full_mat[s]);
         if (ub) bulk_g2s(st + off_d, a.dict + (size_t)b * a.ucap, ub, &full_mat[s]);
         if (g.epi_staged) {
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
       unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
       mbar_wait(&full_mat[s], ph);
       const BlockGeom g = block_geom<P>(a, b);
-      if (g.staged) {
+      if (g.staged && a.x_mode == 0) {
         const int32_t *sd = reinterpret_cast<const int32_t *>(st + off_d);
         double *xs = reinterpret_cast<double *>(st + off_x);
         // Consecutive lanes copy consecutive chunks of the same row.  Only the first gather_rows * CH lanes
@@ -394,7 +399,12 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
           } else {
             bv.tc = bv.told = bv.rold = nullptr;
           }
-          process_rows<P, G, true>(a, bv, g.r0, g.r1, gid, gl, ngroups);
+          if (a.x_mode == 1) {
+            bv.cs = reinterpret_cast<const int32_t *>(st + off_l) - g.a0;
+            process_rows<P, G, 2>(a, bv, g.r0, g.r1, gid, gl, ngroups);
+          } else {
+            process_rows<P, G, 1>(a, bv, g.r0, g.r1, gid, gl, ngroups);
+          }
         } else {
           bv.vs = a.val;
           bv.ls = nullptr;
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
           bv.rp = a.row_ptr;
           bv.xs = nullptr;
           bv.tc = bv.told = bv.rold = nullptr;
-          process_rows<P, G, false>(a, bv, g.r0, g.r1, gid, gl, ngroups);
+          process_rows<P, G, 0>(a, bv, g.r0, g.r1, gid, gl, ngroups);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -480,7 +490,10 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
                    (t.gather_warps * 32) % 8 == 0,
                "cheby_step: bad tuning (threads=%d gather_warps=%d)", threads, t.gather_warps);
   const size_t epi_len = (size_t)a.rows_cap * P + 2;
-  size_t stage = (size_t)a.cap * 10 + (size_t)a.rcap * 4 + (size_t)a.ucap * 4 + (size_t)a.ucap * P * 8 + 3 * epi_len * 8;
+  a.x_mode = g->x_mode;
+  if (a.x_mode == 1) a.ucap = 0;  // no dictionary / gathered-row area in the stage
+  size_t stage = (size_t)a.cap * (a.x_mode == 1 ? 12 : 10) + (size_t)a.rcap * 4 + (size_t)a.ucap * 4 +
+                 (size_t)a.ucap * P * 8 + 3 * epi_len * 8;
   stage = (stage + 127) & ~(size_t)127;
   const size_t budget = 227 * 1024 - 256;
   int ns = t.n_stage > 0 ? t.n_stage : (int)(budget / stage);

@@ -66,6 +66,7 @@ struct Tuning {
   int ctas_per_sm = 1;    // persistent CTAs per SM
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)
   int use_dict = 1;       // 0: every block takes the direct (global-memory) path
+  int x_mode = 0;         // 0: dictionary + cp.async gathers into the stage; 1: staged matrix, direct register gathers
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast
@@ -125,7 +126,7 @@ struct meld_b200_graph {
   meld::DevBuf<int32_t> dict;
   meld::DevBuf<int32_t> dcnt;
   meld::DevBuf<uint16_t> lidx;  // nnz + kCsrPad
-  int32_t stage_cap = 0, dict_cap = 0, row_cap = 0;
+  int32_t stage_cap = 0, dict_cap = 0, row_cap = 0, x_mode = 0;
   int64_t dict_total = 0, direct_blocks = 0;  // statistics
   // Cell order used internally (graph row a = caller's cell perm[a]); null = identity.
   meld::DevBuf<int32_t> perm;

@@ -68,7 +68,8 @@ constexpr int kDictMax = 2048;  // stage_cap limit
 __global__ void __launch_bounds__(kDictThreads) build_dict_kernel(const int32_t *__restrict__ row_ptr,
                                                                  const int32_t *__restrict__ col,
                                                                  const int32_t *__restrict__ blk, int cap, int ucap,
-                                                                 int rcap, int use_dict, int32_t *__restrict__ dict,
+                                                                 int rcap, int use_dict, int x_mode,
+                                                                 int32_t *__restrict__ dict,
                                                                  int32_t *__restrict__ dcnt,
                                                                  uint16_t *__restrict__ lidx) {
   __shared__ int32_t keys[kDictMax];
@@ -82,6 +83,10 @@ __global__ void __launch_bounds__(kDictThreads) build_dict_kernel(const int32_t 
   const int ra = r0 & ~3, nr = ((r1 + 1 - ra) + 3) & ~3;
   if (n == 0 || !use_dict || nal > cap || nr > rcap || n > kDictMax) {  // block-uniform
     if (tid == 0) dcnt[b] = n == 0 ? 0 : -1;
+    return;
+  }
+  if (x_mode == 1) {  // staged matrix with direct gathers: no dictionary, the stage holds the int32 columns
+    if (tid == 0) dcnt[b] = 0;
     return;
   }
   int size = 1;
@@ -169,6 +174,7 @@ int graph_finalize(meld_b200_graph *g, cudaStream_t stream) {
   g->stage_cap = t.stage_cap;
   g->dict_cap = t.dict_cap;
   g->row_cap = t.row_cap;
+  g->x_mode = t.x_mode;
   g->blk_chunk = chunk;
   g->n_blk = (int32_t)(g->nnz > 0 ? ceil_div(g->nnz, chunk) : 1);
   MELD_CHECK(g->blk.alloc((size_t)g->n_blk + 1));
@@ -190,7 +196,7 @@ int graph_finalize(meld_b200_graph *g, cudaStream_t stream) {
   MELD_CHECK(g->lidx.alloc((size_t)g->nnz + kCsrPad));
   MELD_CUDA(cudaMemsetAsync(g->lidx.p, 0, ((size_t)g->nnz + kCsrPad) * sizeof(uint16_t), stream));
   build_dict_kernel<<<g->n_blk, kDictThreads, 0, stream>>>(g->row_ptr.p, g->col.p, g->blk.p, g->stage_cap, g->dict_cap,
-                                                          g->row_cap + 8, t.use_dict, g->dict.p, g->dcnt.p, g->lidx.p);
+                                                          g->row_cap + 8, t.use_dict, t.x_mode, g->dict.p, g->dcnt.p, g->lidx.p);
   MELD_LAUNCH_CHECK();
   DevBuf<unsigned long long> st2;
   MELD_CHECK(st2.alloc(2));
@@ -254,6 +260,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "gather_rows")) t.gather_rows = value;
   else if (!strcmp(key, "p1_segments")) t.p1_segments = value;
   else if (!strcmp(key, "use_dict")) t.use_dict = value;
+  else if (!strcmp(key, "x_mode")) t.x_mode = value;
   else if (!strcmp(key, "reorder")) t.reorder = value;
   else if (!strcmp(key, "n_stage")) t.n_stage = value;
   else if (!strcmp(key, "threads")) t.threads = value;
