@@ -372,7 +372,9 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
     // multiplied concurrently and a small block (a dozen rows) still keeps every lane of its team busy
     const int cw = warp - 1 - a.gather_warps;
     const int team = cw / a.team_warps, wit = cw % a.team_warps;
-    const int n_teams = n_compute_warps / a.team_warps;
+    // never more teams than stages: a team waiting for use k of a stage must not be able to get a whole
+    // ring ahead of the slowest team (an mbarrier parity wait cannot tell "two phases behind" from "done")
+    const int n_teams = min(n_compute_warps / a.team_warps, ns);
     const int ct = wit * 32 + lane;
     const int ngroups = a.team_warps * 32 / G;
     const int gid = ct / G, gl = ct % G;
@@ -383,6 +385,10 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
         const uint32_t ph = (uint32_t)(it / ns) & 1u;
         unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
         const BlockGeom g = block_geom<P>(a, b);
+        // Teams consume stages out of order.  Before trusting a parity wait on use k of this stage, make
+        // sure use k-1 was released (then the "full" barriers really are in phase k, not still in k-1,
+        // where a wait for parity k would pass immediately and read the previous block's data).
+        if (it >= ns) mbar_wait(&empty[s], (uint32_t)(it / ns - 1) & 1u);
         mbar_wait(&full_mat[s], ph);
         mbar_wait(&full_x[s], ph);
         BlockView bv;

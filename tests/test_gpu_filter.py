@@ -196,3 +196,31 @@ def test_api_contract_on_device(mb):
     assert op.graph is None and op.sample_densities is None
     with pytest.raises(NotImplementedError):
         mb.MELD(verbose=0, solver="exact").fit(graph).transform(labels)
+
+
+@pytest.mark.parametrize("tuning", [
+    dict(x_mode=1, gather_warps=1, team_warps=7),        # staged matrix + direct register gathers
+    dict(use_dict=0),                                      # every block on the direct global-memory path
+    dict(blk_chunk=256, stage_cap=512, dict_cap=256, row_cap=16),  # tiny stages: oversize / direct blocks mix in
+    dict(group=16), dict(group=4), dict(team_warps=6), dict(gather_rows=4, gather_warps=4),
+])
+def test_filter_kernel_variants_agree(mb, tuning):
+    """Every launch configuration of the Chebyshev kernel computes the same filter (1e-12)."""
+    from meld_b200 import _native as nv
+
+    cheby, _, _ = _oracle()
+    defaults = dict(blk_chunk=768, stage_cap=1024, dict_cap=768, row_cap=64, n_stage=0, threads=512, gather_warps=3,
+                    team_warps=4, gather_rows=16, ctas_per_sm=1, group=0, use_dict=1, x_mode=0)
+    g = load_golden("blobs2k5_wagner")
+    S = np.random.default_rng(9).normal(size=(g["L"].shape[0], 4))
+    ref = cheby.cheby_filter(g["L"], g["lmax"], S, "heat", beta=60, chebyshev_order=32)
+    try:
+        nv.set_tuning(**dict(defaults, **tuning))
+        graph = mb.DeviceGraph.from_scipy(g["L"])
+        graph.lmax = g["lmax"]
+        out = mb.filter.filter(S, graph, "heat", beta=60, solver="chebyshev", chebyshev_order=32)
+        assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+        own = graph.__class__.from_scipy(g["L"]).estimate_lmax()
+        assert abs(own - g["lmax"]) <= 3e-4 * g["lmax"]
+    finally:
+        nv.set_tuning(**defaults)
