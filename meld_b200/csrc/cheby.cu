@@ -713,6 +713,7 @@ extern "C" {
 int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double *T_old, double *T_new, double *R,
                          int p, double alpha, double shift, double gamma, double c, double c_cur, int r_accumulate,
                          void *stream_) {
+  meld::use_stream((cudaStream_t)stream_);
   MELD_REQUIRE(g && T_cur, "cheby_step: NULL argument");
   MELD_REQUIRE(p >= 1 && p <= 8, "cheby_step: p=%d outside 1..8", p);
   MELD_REQUIRE(gamma == 0.0 || T_old != nullptr, "cheby_step: gamma != 0 needs T_old");
@@ -736,6 +737,7 @@ int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double
 int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coeffs_host, int n_coeffs, const double *S,
                            int p, double *R, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(g && coeffs_host && S && R, "cheby_filter: NULL argument");
   MELD_REQUIRE(n_coeffs >= 2, "cheby_filter: need at least 2 coefficients (got %d)", n_coeffs);
   MELD_REQUIRE(p >= 1 && p <= 8, "cheby_filter: p=%d outside 1..8 (split the signal into column chunks)", p);
@@ -789,6 +791,7 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
 int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol, void *stream_, double *lmax_host,
                             int *iters_host) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(g && lmax_host, "estimate_lmax: NULL argument");
   MELD_REQUIRE(g->row0 == 0 && g->n_rows == g->n_cols, "estimate_lmax: needs the full operator");
   const int64_t n = g->n_rows;
@@ -862,6 +865,7 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
 int meld_b200_indicator_matrix(const int32_t *codes, int64_t n, int p, int sample_normalize, double *S,
                                void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(codes && S && n > 0 && p > 0, "indicator_matrix: bad argument");
   DevBuf<unsigned long long> cnt;
   MELD_CHECK(cnt.alloc((size_t)p));
@@ -875,6 +879,7 @@ int meld_b200_indicator_matrix(const int32_t *codes, int64_t n, int p, int sampl
 }
 
 int meld_b200_l1_normalize_rows(const double *in, int64_t n, int p, double *out, void *stream_) {
+  meld::use_stream((cudaStream_t)stream_);
   MELD_REQUIRE(in && out && n >= 0 && p > 0, "l1_normalize_rows: bad argument");
   if (n == 0) return 0;
   l1_normalize_rows_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(in, n, p, out);

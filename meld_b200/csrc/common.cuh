@@ -75,6 +75,13 @@ struct Tuning {
 Tuning &tuning();
 
 // ---- device buffer with explicit ownership -----------------------------------------
+// Allocations are stream-ordered (cudaMallocAsync from the device's default pool, which is told to keep
+// its memory): a build allocates ~20 temporaries of up to a GB, and plain cudaMalloc / cudaFree cost
+// milliseconds each -- tens of milliseconds once NCCL has enabled peer access, because every allocation
+// is then mapped into every peer.  The stream is the one of the API call in progress on this thread.
+cudaStream_t &current_stream();
+void use_stream(cudaStream_t s);  // also configures the pool on first use
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -82,10 +89,10 @@ struct DevBuf {
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), current_stream());
     if (e != cudaSuccess) {
       p = nullptr;
-      set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      set_error("cudaMallocAsync(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
       cudaGetLastError();
       return MELD_B200_ERR_NOMEM;
     }
@@ -93,7 +100,7 @@ struct DevBuf {
     return 0;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, current_stream());  // ordered after the kernels already queued on that stream
     p = nullptr;
     n = 0;
   }

@@ -16,6 +16,24 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+static thread_local cudaStream_t g_stream = nullptr;
+cudaStream_t &current_stream() { return g_stream; }
+
+void use_stream(cudaStream_t s) {
+  g_stream = s;
+  static thread_local int configured_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != configured_dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;  // never hand memory back to the OS between calls
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured_dev = dev;
+  }
+  cudaGetLastError();
+}
+
 int sm_count() {
   static int cached = 0;
   if (cached) return cached;
@@ -278,6 +296,7 @@ int meld_b200_set_tuning(const char *key, int value) {
 int meld_b200_graph_from_csr(int64_t n_rows, int64_t n_cols, int64_t row0, int64_t nnz, const int64_t *indptr,
                              const int32_t *indices, const double *data, void *stream_, meld_b200_graph_t **out) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(out != nullptr, "graph_from_csr: graph_out is NULL");
   *out = nullptr;
   MELD_REQUIRE(n_rows >= 0 && n_cols > 0 && row0 >= 0 && row0 + n_rows <= n_cols,
@@ -334,6 +353,7 @@ int meld_b200_graph_info(const meld_b200_graph_t *g, int64_t *n_rows, int64_t *n
 int meld_b200_graph_export_csr(const meld_b200_graph_t *g, int64_t *indptr, int32_t *indices, double *data,
                                void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(g && indptr && indices && data, "graph_export_csr: NULL argument");
   indptr32_to_64_kernel<<<(unsigned)ceil_div(g->n_rows + 1, 256), 256, 0, stream>>>(g->row_ptr.p, g->n_rows + 1,
                                                                                   indptr);
@@ -352,6 +372,12 @@ int meld_b200_graph_build_stats(const meld_b200_graph_t *g, int64_t *stats8_host
 }
 
 int meld_b200_graph_destroy(meld_b200_graph_t *g) {
+  // buffers are returned to the pool in stream order on the stream of this thread's last call; make sure
+  // nothing that may still run on another stream reads them
+  if (g) {
+    cudaDeviceSynchronize();
+    meld::use_stream(nullptr);  // free on the legacy default stream
+  }
   delete g;
   return 0;
 }

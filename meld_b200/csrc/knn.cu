@@ -843,6 +843,7 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
                               double anisotropy, double bandwidth_scale, int flags, void *stream_,
                               meld_b200_graph_t **graph_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(graph_out != nullptr, "knn_graph_build: graph_out is NULL");
   *graph_out = nullptr;
   MELD_REQUIRE(X != nullptr, "knn_graph_build: X is NULL");
@@ -874,6 +875,7 @@ int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, dou
                              double bandwidth_scale, int64_t row_begin, int64_t row_end, int flags, void *stream_,
                              meld_b200_cands_t **cands_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(cands_out != nullptr && X != nullptr, "knn_candidates: NULL argument");
   *cands_out = nullptr;
   BuildParams bp;
@@ -929,6 +931,7 @@ int meld_b200_cands_info(const meld_b200_cands_t *c, int64_t *n_rows_host, int64
 int meld_b200_cands_export(const meld_b200_cands_t *c, int64_t *counts, int32_t *cand, double *d2, double *eps,
                            int32_t *perm, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(c != nullptr, "cands_export: NULL handle");
   const int64_t nloc = c->row_end - c->row_begin;
   if (counts) {
@@ -946,6 +949,10 @@ int meld_b200_cands_export(const meld_b200_cands_t *c, int64_t *counts, int32_t 
 }
 
 int meld_b200_cands_destroy(meld_b200_cands_t *c) {
+  if (c) {
+    cudaDeviceSynchronize();
+    meld::use_stream(nullptr);  // free on the legacy default stream
+  }
   delete c;
   return 0;
 }
@@ -955,6 +962,7 @@ int meld_b200_graph_from_candidates(int64_t n, const int64_t *counts, const int3
                                     double thresh, double anisotropy, double bandwidth_scale, int flags, void *stream_,
                                     meld_b200_graph_t **graph_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(graph_out && counts && cand && d2 && eps, "graph_from_candidates: NULL argument");
   *graph_out = nullptr;
   BuildParams bp;
@@ -1001,6 +1009,7 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
                                      double bandwidth_scale, int flags, void *stream_, float *key2_out,
                                      int32_t *cnt_out, int64_t *cap_host) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(X && key2_out && cnt_out && n >= 2 && d >= 1 && knn >= 1 && knn + 1 <= n && knn + 1 <= kMaxK1,
                "debug_candidate_search: bad argument");
   const double thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
@@ -1037,6 +1046,7 @@ int meld_b200_graph_knn_kernel_nnz(const meld_b200_graph_t *g, int64_t *nnz_host
 int meld_b200_graph_export_knn_kernel(const meld_b200_graph_t *g, int64_t *indptr, int32_t *indices, double *data,
                                       void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
   MELD_REQUIRE(g && indptr && indices && data, "graph_export_knn_kernel: NULL argument");
   MELD_REQUIRE(g->knn_nnz >= 0, "graph_export_knn_kernel: graph was built without MELD_B200_FLAG_KEEP_KNN_KERNEL");
   MELD_CUDA(cudaMemcpyAsync(indptr, g->knn_ptr.p, ((size_t)g->n_rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice,

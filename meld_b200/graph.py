@@ -132,14 +132,30 @@ class DeviceGraph:
         torch = nv.require_cuda()
         import torch.distributed as dist
 
+        import os
+        import time
+
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        timing = os.environ.get("MELD_B200_TIMING") and rank == 0
+        t0 = time.perf_counter()
+
+        def lap(what):
+            nonlocal t0
+            if timing:
+                torch.cuda.synchronize()
+                print("[meld_b200 timing] sharded: {:24s} {:9.3f} ms".format(what, 1e3 * (time.perf_counter() - t0)),
+                      flush=True)
+                t0 = time.perf_counter()
+
         X = _as_device_f64(torch, data_nu)
         N, d = X.shape
         if knn + 1 > N:
             raise ValueError("knn + 1 = {} exceeds the number of cells {}".format(knn + 1, N))
         bounds = cls.shard_bounds(N, world)
+        lap("input to device")
         counts, cand, d2, eps, perm = cls.candidates(X, bounds[rank], bounds[rank + 1], knn, decay, thresh,
                                                      bandwidth_scale)
+        lap("stage 1 (local rows)")
         sizes = torch.tensor([counts.shape[0], cand.shape[0]], dtype=torch.int64, device=X.device)
         all_sizes = torch.empty(2 * world, dtype=torch.int64, device=X.device)
         dist.all_gather_into_tensor(all_sizes, sizes, group=group)
@@ -163,8 +179,11 @@ class DeviceGraph:
         if N >= 4096:
             src = next(r for r in range(world) if rows[r] > 0)
             dist.broadcast(perm, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
-        return cls.from_candidates(N, counts, cand, d2, eps, perm, knn, decay, thresh, anisotropy, bandwidth_scale,
-                                   device=X.device)
+        lap("all-gather")
+        g = cls.from_candidates(N, counts, cand, d2, eps, perm, knn, decay, thresh, anisotropy, bandwidth_scale,
+                                device=X.device)
+        lap("stage 2 (replicated)")
+        return g
 
     @classmethod
     def from_scipy(cls, L, row0=0, n_cols=None, params=None):
