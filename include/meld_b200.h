@@ -132,6 +132,9 @@ int meld_b200_graph_export_knn_kernel(const meld_b200_graph_t *g, int64_t *indpt
  * [4] search implementation (0 tcgen05, 1 SIMT), [5] sum of block dictionary sizes,
  * [6] row blocks on the direct path, [7] row blocks.                */
 int meld_b200_graph_build_stats(const meld_b200_graph_t *g, int64_t *stats8_host);
+/* CUDA-event timings of the last build (host): [0] ms of search pass 1, [1] ms of pass 2,
+ * [2] flops of ONE pass (2 x rows x padded columns x K'), [3] reserved.               */
+int meld_b200_graph_build_times(const meld_b200_graph_t *g, double *times4_host);
 int meld_b200_graph_destroy(meld_b200_graph_t *g);
 
 /* ---- filter ------------------------------------------------------------------- */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "meld_b200_graph_knn_kernel_nnz": (C.c_int, [_vp, _pi64]),
     "meld_b200_graph_export_knn_kernel": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "meld_b200_graph_build_stats": (C.c_int, [_vp, _pi64]),
+    "meld_b200_graph_build_times": (C.c_int, [_vp, _pdbl]),
     "meld_b200_graph_destroy": (C.c_int, [_vp]),
     "meld_b200_estimate_lmax": (C.c_int, [_vp, _i32, _dbl, _vp, _pdbl, _pint]),
     "meld_b200_cheby_filter": (C.c_int, [_vp, _dbl, _pdbl, _i32, _vp, _i32, _vp, _vp]),

@@ -70,6 +70,7 @@ struct Tuning {
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast
+  int tc_cg2 = 0;         // candidate search: CTA pairs issue tcgen05.mma.cta_group::2 (needs tc_multicast = 2)
   int p1_segments = 0;    // candidate search pass 1 scans this many column segments per row (own first; 0 = all)
 };
 Tuning &tuning();
@@ -81,6 +82,7 @@ Tuning &tuning();
 // is then mapped into every peer.  The stream is the one of the API call in progress on this thread.
 cudaStream_t &current_stream();
 void use_stream(cudaStream_t s);  // also configures the pool on first use
+bool use_pool();                  // MELD_B200_NO_POOL=1 falls back to cudaMalloc / cudaFree (diagnosis)
 
 template <typename T>
 struct DevBuf {
@@ -89,7 +91,8 @@ struct DevBuf {
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), current_stream());
+    cudaError_t e = use_pool() ? cudaMallocAsync((void **)&p, count * sizeof(T), current_stream())
+                               : cudaMalloc((void **)&p, count * sizeof(T));
     if (e != cudaSuccess) {
       p = nullptr;
       set_error("cudaMallocAsync(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
@@ -100,7 +103,12 @@ struct DevBuf {
     return 0;
   }
   void release() {
-    if (p) cudaFreeAsync(p, current_stream());  // ordered after the kernels already queued on that stream
+    if (p) {
+      if (use_pool())
+        cudaFreeAsync(p, current_stream());  // ordered after the kernels already queued on that stream
+      else
+        cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
@@ -146,6 +154,7 @@ struct meld_b200_graph {
   meld::DevBuf<double> knn_val;    // knn_nnz
   int64_t knn_nnz = -1;
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double times[4] = {0, 0, 0, 0};  // ms of search pass 1 / pass 2, flops of one pass, reserved
 };
 
 namespace meld {

@@ -543,6 +543,7 @@ struct Candidates {
   int passes = 0;
   int32_t max_per_row = 0;
   int64_t retries = 0;
+  double pass1_ms = 0, pass2_ms = 0, gemm_flops_per_pass = 0;  // CUDA-event times of the two GEMM passes
 };
 
 static int candidate_search(const double *X, int64_t n, int64_t d, int k1, double radius_factor, bool simt,
@@ -574,7 +575,19 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
   MELD_CHECK(lists.alloc((size_t)n * plan.nlists * k1));
   MELD_CHECK(out.key2.alloc((size_t)n));
   StageTimer tm(stream);
+  // the two GEMM passes are always timed with CUDA events (bench.py reports their tensor throughput);
+  // reading the timers costs nothing extra: the stream is synchronised after pass 2 anyway
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i) MELD_CUDA(cudaEventCreate(&ev[i]));
+  struct EvGuard {
+    cudaEvent_t *e;
+    ~EvGuard() {
+      for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]);
+    }
+  } ev_guard{ev};
+  MELD_CUDA(cudaEventRecord(ev[0], stream));
   MELD_CHECK(search_pass1(plan, st, lists.p, stream));
+  MELD_CUDA(cudaEventRecord(ev[1], stream));
   tm.lap("search pass 1 (top-k)");
   merge_lists_kernel<<<(unsigned)ceil_div(nloc, 128), 128, 0, stream>>>(lists.p, row_begin, row_end, plan.nlists, k1,
                                                                          norm.p, ymax2.p, plan.margin_c, radius_factor,
@@ -594,11 +607,21 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
     MELD_CHECK(pairs.alloc((size_t)pair_cap));
     MELD_CUDA(cudaMemsetAsync(gcount.p, 0, sizeof(unsigned long long), stream));
     tm.lap("merge + alloc");
+    MELD_CUDA(cudaEventRecord(ev[2], stream));
     MELD_CHECK(search_pass2(plan, st, out.key2.p, pairs.p, gcount.p, pair_cap, stream));
+    MELD_CUDA(cudaEventRecord(ev[3], stream));
     tm.lap("search pass 2 (emit)");
     ++out.passes;
     MELD_CUDA(cudaMemcpyAsync(&h_total, gcount.p, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));
+    {
+      float ms1 = 0.f, ms2 = 0.f;
+      cudaEventElapsedTime(&ms1, ev[0], ev[1]);
+      cudaEventElapsedTime(&ms2, ev[2], ev[3]);
+      out.pass1_ms = ms1;
+      out.pass2_ms = ms2;
+      out.gemm_flops_per_pass = 2.0 * (double)nloc * (double)plan.n_pad_cols * (double)plan.kp_used;
+    }
     if ((int64_t)h_total <= pair_cap) break;
     if (attempt == 1) {
       set_error("knn_graph_build: candidate overflow persisted (%llu pairs > capacity %lld)", h_total,
@@ -867,6 +890,9 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   g->stats[0] = cs.passes;
   g->stats[1] = cs.max_per_row;
   g->stats[3] = cs.retries;
+  g->times[0] = cs.pass1_ms;
+  g->times[1] = cs.pass2_ms;
+  g->times[2] = cs.gemm_flops_per_pass;
   *graph_out = g;
   return 0;
 }
@@ -1024,6 +1050,12 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   MELD_LAUNCH_CHECK();
   MELD_CUDA(cudaStreamSynchronize(stream));
   if (cap_host) *cap_host = cs.total;
+  return 0;
+}
+
+int meld_b200_graph_build_times(const meld_b200_graph_t *g, double *times4_host) {
+  MELD_REQUIRE(g && times4_host, "graph_build_times: NULL argument");
+  for (int i = 0; i < 4; ++i) times4_host[i] = g->times[i];
   return 0;
 }
 

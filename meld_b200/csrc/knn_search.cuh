@@ -22,6 +22,8 @@ struct SearchPlan {
   int k1 = 0;
   int nseg = 1;    // column segments (independent work units per row tile)
   int nlists = 1;  // lists per row written by pass 1
+  int64_t n_pad_cols = 0;  // columns actually multiplied per pass (padded) and K used, for flop accounting
+  int kp_used = 0;
   double margin_c = 0.0;
   // tcgen05 path
   int64_t n_pad = 0;  // rows padded to the tile size

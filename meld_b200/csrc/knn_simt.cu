@@ -129,6 +129,8 @@ int search_plan(bool simt, int64_t n, int64_t d, int k1, int64_t row_begin, int6
   plan->nseg = (int)nseg;
   plan->nlists = (int)nseg;
   plan->margin_c = (double)(d + 16) * ldexp(1.0, -22);
+  plan->n_pad_cols = n;
+  plan->kp_used = (int)d;
   return 0;
 }
 

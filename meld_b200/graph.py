@@ -297,6 +297,11 @@ class DeviceGraph:
                 "direct_blocks", "row_blocks"]
         return {k: int(arr[i]) for i, k in enumerate(keys)}
 
+    def build_times(self):
+        arr = (C.c_double * 4)()
+        nv.check(nv.lib().meld_b200_graph_build_times(self._h, arr), "graph_build_times")
+        return {"pass1_ms": arr[0], "pass2_ms": arr[1], "flops_per_pass": arr[2]}
+
     # ---- lifetime ------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
