@@ -70,7 +70,6 @@ struct Tuning {
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast
-  int tc_cg2 = 0;         // candidate search: CTA pairs issue tcgen05.mma.cta_group::2 (needs tc_multicast = 2)
   int p1_segments = 0;    // candidate search pass 1 scans this many column segments per row (own first; 0 = all)
 };
 Tuning &tuning();

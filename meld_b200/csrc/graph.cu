@@ -53,15 +53,7 @@ int sm_count() {
 // ---- tuning knobs (bench / tests only; defaults are the shipped configuration) ------
 Tuning g_tuning;
 
-Tuning &tuning() {
-  static bool env_read = false;
-  if (!env_read) {  // MELD_B200_TC_CG2=0/1 overrides the default of the pair-MMA mode (A/B runs of the test suite)
-    env_read = true;
-    const char *e = getenv("MELD_B200_TC_CG2");
-    if (e) g_tuning.tc_cg2 = atoi(e);
-  }
-  return g_tuning;
-}
+Tuning &tuning() { return g_tuning; }
 
 // blk[b] = first row whose first entry is at or after b * chunk.
 __global__ void partition_rows_kernel(const int32_t *__restrict__ row_ptr, int64_t n_rows, int32_t chunk,
@@ -300,7 +292,6 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "group")) t.group = value;
   else if (!strcmp(key, "use_graph")) t.use_graph = value;
   else if (!strcmp(key, "tc_multicast")) t.tc_multicast = value;
-  else if (!strcmp(key, "tc_cg2")) t.tc_cg2 = value;
   else {
     set_error("set_tuning: unknown key '%s'", key);
     return MELD_B200_ERR_INVALID;

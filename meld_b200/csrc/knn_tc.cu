@@ -123,41 +123,6 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
       "h"(cta_mask)
       : "memory");
 }
-// --- cta_group::2 (CTA pair) forms --------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
-  return r;
-}
-// TMA load whose completion is signalled on an mbarrier that may live in the pair's other CTA
-__device__ __forceinline__ void tma_load_2d_cg2(const void *tmap, uint32_t bar_cluster_addr, void *dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4}], [%2];" ::"r"(s32(dst)),
-      "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_cg2(uint64_t *bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          s32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void bar_arrive_remote(uint64_t *bar, uint32_t cta) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(s32(bar), cta))
-               : "memory");
-}
-
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -217,8 +182,6 @@ struct TcArgs {
   int rt_begin;        // first (global) row tile of this call
   long long row_end;   // rows at or beyond it are not this call's
   int mc;         // cluster size (1, 2 or 4): each CTA loads 1/mc of a B tile and multicasts it to the cluster
-  int cg2;        // 1: CTA pairs run ONE tcgen05.mma.cta_group::2 (M = 256) per step: each SM feeds its own A and
-                  //    half of B from shared memory, which halves the operand traffic per MAC (mc == 2 then)
   int n_passes;   // segments visited per row tile (pass 1 may stop early: any subset gives a valid bound)
   int n_stages;   // B (or A+B) ring depth
   int a_region;   // bytes reserved for the A operand (resident k-blocks, or one A tile per stage)
@@ -293,28 +256,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         bar_init(&bars->full[s], 1);
-        bar_init(&bars->empty[s], a.cg2 ? 1 : a.mc);  // multicast: every CTA's MMAs must release a stage
+        bar_init(&bars->empty[s], a.mc);  // clustered: every CTA's MMAs must release a stage
       }
       bar_init(&bars->a_full, 1);
       bar_init(&bars->a_empty, 1);
       for (int b = 0; b < 2; ++b) {
         bar_init(&bars->tmem_full[b], 1);
-        bar_init(&bars->tmem_empty[b], a.cg2 ? 2 * kEpiWarps : kEpiWarps);  // per epilogue warp (of both CTAs)
+        bar_init(&bars->tmem_empty[b], kEpiWarps);  // one arrival per epilogue warp
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if (a.cg2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_base)),
-                   "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_base)),
-                   "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&bars->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -330,34 +286,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (int u = u_first; u < n_units; u += u_step) {
         const UnitPlan up = unit_plan(a, u);
         const int rt = up.rt;
-        // pair mode: completions of both CTAs' loads are counted on the LEADER's barriers (its MMA thread waits)
-        const uint32_t lead_a_full = a.cg2 ? mapa_u32(s32(&bars->a_full), 0) : 0u;
         if (a.a_resident) {
           bar_wait(&bars->a_empty, uphase ^ 1u);
-          if (a.cg2) {
-            if (crank == 0) bar_expect_tx(&bars->a_full, 2u * (uint32_t)a.nkb * kABytes);
-            for (int kb = 0; kb < a.nkb; ++kb)
-              tma_load_2d_cg2(&tmap_a, lead_a_full, smA + kb * kABytes, kb * BK, rt * BM);
-          } else {
-            bar_expect_tx(&bars->a_full, (uint32_t)a.nkb * kABytes);
-            for (int kb = 0; kb < a.nkb; ++kb)
-              tma_load_2d(&tmap_a, &bars->a_full, smA + kb * kABytes, kb * BK, rt * BM);
-          }
+          bar_expect_tx(&bars->a_full, (uint32_t)a.nkb * kABytes);
+          for (int kb = 0; kb < a.nkb; ++kb) tma_load_2d(&tmap_a, &bars->a_full, smA + kb * kABytes, kb * BK, rt * BM);
         }
         for (int j = 0; j < up.len; ++j) {
           const int ct = up.ct0 + (up.start + j) % up.len;
           for (int kb = 0; kb < a.nkb; ++kb) {
             bar_wait(&bars->empty[stage], phase ^ 1u);
-            if (a.cg2) {  // my half of the B tile stays in MY shared memory; the pair's MMA reads both halves
-              if (crank == 0) bar_expect_tx(&bars->full[stage], (uint32_t)kBBytes);  // 2 x half a tile
-              tma_load_2d_cg2(&tmap_b, mapa_u32(s32(&bars->full[stage]), 0), smB + stage * kBBytes, kb * BK,
-                              ct * BN + (int)crank * (BN / 2));
-              if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1u;
-              }
-              continue;
-            }
             bar_expect_tx(&bars->full[stage], a.a_resident ? kBBytes : kBBytes + kABytes);
             if (a.mc > 1) {  // my slice of the B tile, delivered to every CTA of the cluster
               const int slice = BN / a.mc;
@@ -377,9 +314,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread; in pair mode only the leader CTA issues, for both) =====
-    if (lane == 0 && (!a.cg2 || crank == 0)) {
-      const uint32_t idesc = a.cg2 ? umma_idesc_bf16(2 * BM, BN) : umma_idesc_bf16(BM, BN);
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0, buf = 0;
       uint32_t phase = 0, bphase = 0, uphase = 0;
       for (int u = u_first; u < n_units; u += u_step) {
@@ -399,16 +336,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const uint32_t b_base = s32(smB + stage * kBBytes);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              if (a.cg2)
-                tc_mma_bf16_cg2(tmem_d, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
-                                (uint32_t)((kb | k) != 0));
-              else
-                tc_mma_bf16(tmem_d, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
-                            (uint32_t)((kb | k) != 0));
+              tc_mma_bf16(tmem_d, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
+                          (uint32_t)((kb | k) != 0));
             }
-            if (a.cg2)
-              tc_commit_cg2(&bars->empty[stage], (uint16_t)0x3);
-            else if (a.mc > 1)
+            if (a.mc > 1)
               tc_commit_mc(&bars->empty[stage], (uint16_t)((1u << a.mc) - 1u));  // releases the stage cluster-wide
             else
               tc_commit(&bars->empty[stage]);  // stage reusable once these MMAs retire
@@ -417,19 +348,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               phase ^= 1u;
             }
           }
-          if (a.cg2)
-            tc_commit_cg2(&bars->tmem_full[buf], (uint16_t)0x3);  // both CTAs' epilogues read their own TMEM
-          else
-            tc_commit(&bars->tmem_full[buf]);
+          tc_commit(&bars->tmem_full[buf]);
           buf ^= 1;
           if (buf == 0) bphase ^= 1u;
         }
-        if (a.a_resident) {
-          if (a.cg2)
-            tc_commit_cg2(&bars->a_empty, (uint16_t)0x3);
-          else
-            tc_commit(&bars->a_empty);
-        }
+        if (a.a_resident) tc_commit(&bars->a_empty);
         uphase ^= 1u;
       }
     }
@@ -547,12 +470,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if (a.cg2)
-            bar_arrive_remote(&bars->tmem_empty[buf], 0);  // the leader's MMA thread waits for both CTAs
-          else
-            bar_arrive(&bars->tmem_empty[buf]);
-        }
+        if (lane == 0) bar_arrive(&bars->tmem_empty[buf]);
         buf ^= 1;
         if (buf == 0) bphase ^= 1u;
       }
@@ -577,10 +495,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (a.mc > 1) cluster_sync_all();  // the peer may still multicast into / arrive on this CTA until it is done too
   if (warp == 1) {
     tc_fence_after();
-    if (a.cg2)
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    else
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -744,7 +659,6 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   if (grid > units) grid = units / cs * cs;
   if (grid < cs) grid = cs;
   a.mc = cs;
-  a.cg2 = (tuning().tc_cg2 && cs == 2 && a.a_resident) ? 1 : 0;
   cfg.gridDim = dim3((unsigned)grid);
   CUtensorMap ma, mb;
   memcpy(&ma, st.tmap_a, sizeof(ma));

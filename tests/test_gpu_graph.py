@@ -155,9 +155,9 @@ def test_two_stage_build_over_row_ranges_matches_single_call(mb):
     assert np.array_equal(L.data, ref.data)
 
 
-@pytest.mark.parametrize("tuning", [dict(tc_cg2=1), dict(tc_multicast=1), dict(tc_multicast=4)])
+@pytest.mark.parametrize("tuning", [dict(tc_multicast=1), dict(tc_multicast=4)])
 def test_search_kernel_variants_build_the_same_graph(mb, tuning):
-    """CTA-pair MMA (cta_group::2), no multicast and 4-CTA multicast clusters all give the golden graph."""
+    """No multicast and 4-CTA multicast clusters give the same golden graph as the default CTA pairs."""
     from meld_b200 import _native as nv
 
     g = load_golden("blobs2k_k15")
@@ -168,4 +168,4 @@ def test_search_kernel_variants_build_the_same_graph(mb, tuning):
         assert _same_pattern(L, g["L"])
         assert np.abs(L.data - g["L"].data).max() <= 1e-10 * np.abs(g["L"].data).max()
     finally:
-        nv.set_tuning(tc_cg2=0, tc_multicast=2)
+        nv.set_tuning(tc_multicast=2)
