@@ -65,6 +65,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_cg(void *dst, const void *src) {  // L2 only, no L1 allocation
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -98,6 +101,7 @@ struct StepArgs {
   int x_mode;      // 0: dictionary + cp.async gathers; 1: staged (val, col) and direct register gathers
   int team_warps;  // compute warps per team (one team per in-flight block)
   int gather_rows; // dictionary rows fetched per warp-level cp.async instruction
+  int gather_cg;   // 1: cp.async.cg (bypass L1) for the gathers
   int stage_epi;   // 1: the T/R arrays are library workspace (padded), slices may be bulk-copied
   int stage_bytes;
 };
@@ -125,14 +129,25 @@ __device__ __forceinline__ void gather_row(const double *__restrict__ T, int32_t
     for (int k = 0; k < P; ++k) x[k] = __ldg(t + k);
   }
 }
+// The gathered rows are read back at random positions with 128-bit shared-memory loads, 8 lanes per
+// wavefront.  Chunk c of row t sits in 16-byte bank group (t * CH + c) mod 8, so for CH = 2 (p = 4) the
+// eight lanes of a wavefront can only hit four groups, for CH = 4 (p = 8) only two.  XOR-ing the chunk
+// index with a few higher bits of t spreads a wavefront over all eight groups.
+template <int P>
+__device__ __forceinline__ int chunk_swizzle(int t) {
+  if constexpr (P == 4) return (t >> 2) & 1;
+  if constexpr (P == 8) return (t >> 1) & 3;
+  return 0;
+}
 // Same row out of the stage's shared-memory copy.
 template <int P>
 __device__ __forceinline__ void smem_row(const double *xs, int li, double (&x)[P]) {
   const double *t = xs + (size_t)li * P;
   if constexpr (P % 2 == 0) {
+    const int sw = chunk_swizzle<P>(li);
 #pragma unroll
     for (int k = 0; k < P; k += 2) {
-      const double2 v = *reinterpret_cast<const double2 *>(t + k);
+      const double2 v = *reinterpret_cast<const double2 *>(t + 2 * ((k >> 1) ^ sw));
       x[k] = v.x;
       x[k + 1] = v.y;
     }
@@ -350,17 +365,22 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
         // is replayed at ~2 L1 cycles, while separate requests stream at ~1 cycle each, so few rows per
         // instruction keep the L1 pipe (the real bound of this kernel) at its best rate.
         constexpr int CH = (P % 2 == 0) ? P / 2 : P;   // chunks per row: 16 B (even P) or 8 B (odd P)
-        const int rpi = min(a.gather_rows, 32 / CH);   // rows per warp instruction
+        const int rpi = a.gather_rows > 0 ? min(a.gather_rows, 32 / CH) : 32 / CH;  // rows per warp instruction (0 = all lanes)
         const int gw = warp - 1;
         if (lane < rpi * CH) {
           const int ch = lane % CH;
           for (int t = gw * rpi + lane / CH; t < g.u; t += a.gather_warps * rpi) {
             const double *src = a.Tcur + (size_t)sd[t] * P;
             double *dst = xs + (size_t)t * P;
-            if constexpr (P % 2 == 0)
-              cp_async16(dst + 2 * ch, src + 2 * ch);
-            else
+            if constexpr (P % 2 == 0) {
+              double *d16 = dst + 2 * (ch ^ chunk_swizzle<P>(t));
+              if (a.gather_cg)
+                cp_async16_cg(d16, src + 2 * ch);
+              else
+                cp_async16(d16, src + 2 * ch);
+            } else {
               cp_async8(dst + ch, src + ch);
+            }
           }
         }
       }
@@ -488,7 +508,8 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
   a.rows_cap = g->row_cap;
   a.gather_warps = t.gather_warps;
   a.team_warps = t.team_warps;
-  a.gather_rows = t.gather_rows < 1 ? 1 : t.gather_rows;
+  a.gather_rows = t.gather_rows;
+  a.gather_cg = t.gather_cg;
   a.stage_epi = stage_epi;
   const int threads = t.threads;
   MELD_REQUIRE(threads % 32 == 0 && threads >= 96 && threads <= 512 && t.gather_warps >= 1 &&

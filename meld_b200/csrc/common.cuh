@@ -61,7 +61,8 @@ struct Tuning {
   int n_stage = 0;        // TMA pipeline depth per CTA (0 = as many as fit in shared memory)
   int threads = 512;      // threads per CTA: 1 producer warp + gather warps + compute warps
   int gather_warps = 3;
-  int gather_rows = 16;   // dictionary rows per warp-level cp.async instruction (1..16)
+  int gather_rows = 0;    // dictionary rows per warp-level cp.async instruction (0 = as many as lanes allow)
+  int gather_cg = 0;      // 1: gathers bypass L1 (cp.async.cg)
   int team_warps = 4;     // compute warps per team; teams take alternate blocks
   int ctas_per_sm = 1;    // persistent CTAs per SM
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)

@@ -282,6 +282,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "gather_warps")) t.gather_warps = value;
   else if (!strcmp(key, "team_warps")) t.team_warps = value;
   else if (!strcmp(key, "gather_rows")) t.gather_rows = value;
+  else if (!strcmp(key, "gather_cg")) t.gather_cg = value;
   else if (!strcmp(key, "p1_segments")) t.p1_segments = value;
   else if (!strcmp(key, "use_dict")) t.use_dict = value;
   else if (!strcmp(key, "x_mode")) t.x_mode = value;

@@ -210,7 +210,7 @@ def test_filter_kernel_variants_agree(mb, tuning):
 
     cheby, _, _ = _oracle()
     defaults = dict(blk_chunk=768, stage_cap=1024, dict_cap=768, row_cap=64, n_stage=0, threads=512, gather_warps=3,
-                    team_warps=4, gather_rows=16, ctas_per_sm=1, group=0, use_dict=1, x_mode=0)
+                    team_warps=4, gather_rows=0, ctas_per_sm=1, group=0, use_dict=1, x_mode=0)
     g = load_golden("blobs2k5_wagner")
     S = np.random.default_rng(9).normal(size=(g["L"].shape[0], 4))
     ref = cheby.cheby_filter(g["L"], g["lmax"], S, "heat", beta=60, chebyshev_order=32)

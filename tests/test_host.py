@@ -114,3 +114,14 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_shard_bounds_are_tile_aligned_and_cover_all_rows():
+    from meld_b200.graph import DeviceGraph
+
+    for n, world in [(500_000, 8), (6000, 3), (1000, 4), (512, 2), (2_000_000, 8), (100, 8)]:
+        b = DeviceGraph.shard_bounds(n, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1
+        assert all(x <= y for x, y in zip(b[:-1], b[1:]))
+        assert all(x % 512 == 0 for x, y in zip(b[:-1], b[1:]) if y > x)  # non-empty ranges start on a 512-row tile
+    assert DeviceGraph.shard_bounds(6000, 3) == [0, 2048, 4096, 6000]
