@@ -258,7 +258,7 @@ def run_b200(args):
     t_e2e = time.perf_counter()
     f0.record()
     for _ in range(args.steps):
-        _, dens = step_e2e()
+        op_e2e, dens = step_e2e()
     f1.record()
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t_e2e))
@@ -288,7 +288,8 @@ def run_b200(args):
                     Xh.nbytes // 2**20, nnz * 12 // 2**20),
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Xh.nbytes + 4 * n),
-                    "d2h_bytes_per_step": int(8 * n * p), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(8 * n * p), "ms_per_step": e2e_ms / args.steps,
+                    "host_timings_ms_last_step": {k: round(1e3 * v, 2) for k, v in op_e2e.timings_.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
@@ -303,10 +304,14 @@ def run_b200(args):
             "roofline_gemm": None if not bt["pass2_ms"] else {
                 "kernel": "tc_search_kernel (bf16-split distance GEMM, fused top-k / emit epilogue)", "bound": "tensor",
                 "achieved": bt["flops_per_pass"] / (bt["pass2_ms"] * 1e-3) / 1e12,
-                "achieved_pass1": bt["flops_per_pass"] / (bt["pass1_ms"] * 1e-3) / 1e12,
+                "achieved_pass1": bt["flops_pass1"] / (bt["pass1_ms"] * 1e-3) / 1e12,
                 "peak": pk.get("bf16_tflops"), "peak_sustained": pk.get("bf16_tflops_sustained"), "unit": "TFLOP/s",
                 "frac": bt["flops_per_pass"] / (bt["pass2_ms"] * 1e-3) / 1e12 / pk.get("bf16_tflops", 1632.2),
                 "ms_pass1": bt["pass1_ms"], "ms_pass2": bt["pass2_ms"], "flops_per_pass": bt["flops_per_pass"],
+                "flops_pass1": bt["flops_pass1"], "flops_unpruned_pass": bt["flops_unpruned_pass"],
+                "tile_pairs_kept": bt["flops_per_pass"] / max(bt["flops_unpruned_pass"], 1.0),
+                "note": "flops = 2 x 128 x 256 x K' per (row tile, column tile) product actually issued; pairs whose "
+                        "bounding balls are farther apart than the emit radius are skipped (ball-tree style pruning)",
                 "share_of_step": (bt["pass1_ms"] + bt["pass2_ms"]) / (ms_total / args.steps),
             },
         }

@@ -53,7 +53,8 @@ int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_
 
 /* Launch-configuration knobs of the Chebyshev kernel, for bench sweeps and tests
  * only (keys: blk_chunk, stage_cap, dict_cap, row_cap, n_stage, threads, gather_warps,
- * ctas_per_sm, group, use_dict, reorder, tc_multicast).  Takes effect for graphs created afterwards.                       */
+ * ctas_per_sm, group, use_dict, reorder, tc_multicast, prune, clusters, kmeans_iters,
+ * reorder_min_n, prune_window, cluster_cells).  Takes effect for graphs created afterwards.                       */
 int meld_b200_set_tuning(const char *key, int value);
 
 /* ---- graph construction ------------------------------------------------------ */
@@ -133,8 +134,10 @@ int meld_b200_graph_export_knn_kernel(const meld_b200_graph_t *g, int64_t *indpt
  * [6] row blocks on the direct path, [7] row blocks.                */
 int meld_b200_graph_build_stats(const meld_b200_graph_t *g, int64_t *stats8_host);
 /* CUDA-event timings of the last build (host): [0] ms of search pass 1, [1] ms of pass 2,
- * [2] flops of ONE pass (2 x rows x padded columns x K'), [3] reserved.               */
-int meld_b200_graph_build_times(const meld_b200_graph_t *g, double *times4_host);
+ * [2] flops issued by pass 2 and [3] by pass 1 (2 x 128 x 256 x K' per (row tile, column tile)
+ * product that survived the bounding-ball pruning), [4] flops of an unpruned pass
+ * (2 x rows x padded columns x K'), [5..7] reserved.                                   */
+int meld_b200_graph_build_times(const meld_b200_graph_t *g, double *times8_host);
 int meld_b200_graph_destroy(meld_b200_graph_t *g);
 
 /* ---- filter ------------------------------------------------------------------- */

@@ -72,6 +72,14 @@ struct Tuning {
   int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast
   int p1_segments = 0;    // candidate search pass 1 scans this many column segments per row (own first; 0 = all)
+  int prune = 1;          // candidate search skips (row tile, column tile) pairs that bounding balls prove too far apart
+  int clusters = 64;      // k-means clusters of the internal cell order (0: Morton order only)
+  int kmeans_iters = 2;   // Lloyd iterations after seeding
+  int reorder_min_n = 4096;  // cells are re-ordered (clusters + Morton curve) from this size on
+  int reg_topk = 1;       // pass 1 keeps its top-k lists in registers (k1 <= 32) instead of shared memory
+  int tl_interleave = 0;  // bit 0 / bit 1: pass 1 / pass 2 chunks of a tile list interleave instead of being contiguous
+  int cluster_cells = 1024;  // fewest cells per k-means cluster (fewer clusters for small inputs)
+  int prune_window = 2;   // the window pass of the pruned search scans own tile +- this many column tiles
 };
 Tuning &tuning();
 
@@ -154,7 +162,8 @@ struct meld_b200_graph {
   meld::DevBuf<double> knn_val;    // knn_nnz
   int64_t knn_nnz = -1;
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  double times[4] = {0, 0, 0, 0};  // ms of search pass 1 / pass 2, flops of one pass, reserved
+  // ms of search pass 1 / pass 2, flops issued by pass 2 / by pass 1, flops of an unpruned pass, reserved
+  double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace meld {

@@ -293,6 +293,14 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "group")) t.group = value;
   else if (!strcmp(key, "use_graph")) t.use_graph = value;
   else if (!strcmp(key, "tc_multicast")) t.tc_multicast = value;
+  else if (!strcmp(key, "prune")) t.prune = value;
+  else if (!strcmp(key, "clusters")) t.clusters = value;
+  else if (!strcmp(key, "kmeans_iters")) t.kmeans_iters = value;
+  else if (!strcmp(key, "reorder_min_n")) t.reorder_min_n = value;
+  else if (!strcmp(key, "prune_window")) t.prune_window = value;
+  else if (!strcmp(key, "cluster_cells")) t.cluster_cells = value;
+  else if (!strcmp(key, "reg_topk")) t.reg_topk = value;
+  else if (!strcmp(key, "tl_interleave")) t.tl_interleave = value;
   else {
     set_error("set_tuning: unknown key '%s'", key);
     return MELD_B200_ERR_INVALID;

@@ -129,14 +129,174 @@ __global__ void gather_rows_kernel(const double *__restrict__ X, const int32_t *
   }
 }
 
+// ---- 0c. k-means clusters of the cells (the top level of the internal order) ---------------------------
+// The pruned candidate search (knn_tc.cu) bounds 256-cell tiles by balls; tiles are only compact when the
+// cells of one tile come from one region of the data, which a Morton curve over four features cannot give
+// in 100 dimensions.  So cells are first assigned to k-means clusters (a few Lloyd iterations over the
+// highest-variance features, float32 -- a heuristic: ANY assignment gives correct graphs), and the Morton
+// curve only orders the cells inside a cluster.  Everything is deterministic (no floating-point atomics):
+// every rank of a sharded build derives the same order from the same data.
+constexpr int kKmDims = 128;   // features used for clustering (highest variance first)
+constexpr int kKmParts = 16;   // partial sums per cluster in the centroid update
+constexpr int kKmMaxC = 128;
+
+// centroids are stored feature-major: cen[k * C + c]
+template <int CPL>  // clusters per lane
+__global__ void __launch_bounds__(256) kmeans_assign_kernel(const double *__restrict__ X, int64_t n, int64_t d,
+                                                            const int32_t *__restrict__ sel, int nd,
+                                                            const double *__restrict__ mu, const float *__restrict__ cen,
+                                                            const float *__restrict__ cn, int C,
+                                                            int32_t *__restrict__ cid) {
+  extern __shared__ float km_sm[];
+  float *scen = km_sm;                 // nd * C
+  float *scn = scen + (size_t)nd * C;  // C
+  float *smu = scn + C;                // kKmDims
+  int *ssel = reinterpret_cast<int *>(smu + kKmDims);
+  for (int t = threadIdx.x; t < nd * C; t += blockDim.x) scen[t] = cen[t];
+  for (int t = threadIdx.x; t < C; t += blockDim.x) scn[t] = cn[t];
+  for (int t = threadIdx.x; t < kKmDims; t += blockDim.x) {
+    ssel[t] = t < nd ? sel[t] : 0;
+    smu[t] = t < nd ? (float)mu[sel[t]] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    float xr[kKmDims / 32];
+#pragma unroll
+    for (int j = 0; j < kKmDims / 32; ++j) {
+      const int k = j * 32 + lane;
+      xr[j] = k < nd ? (float)(X[i * d + ssel[k]] - (double)smu[k]) : 0.f;
+    }
+    float acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kKmDims / 32; ++j) {
+      if (j * 32 < nd) {
+        const int lim = min(32, nd - j * 32);
+        for (int l = 0; l < lim; ++l) {
+          const float xk = __shfl_sync(0xffffffffu, xr[j], l);
+          const float *row = scen + (size_t)(j * 32 + l) * C + lane;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) acc[c] = fmaf(xk, row[32 * c], acc[c]);
+        }
+      }
+    }
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int ci = lane + 32 * c;
+      if (ci < C) {
+        const float dist = scn[ci] - 2.f * acc[c];
+        if (dist < best || (dist == best && ci < bi)) {
+          best = dist;
+          bi = ci;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob < best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (lane == 0) cid[i] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+// seeds: cluster c starts at the cell in position (2c + 1) n / (2C) of the Morton order
+__global__ void kmeans_seed_kernel(const double *__restrict__ X, int64_t n, int64_t d, const int32_t *__restrict__ sel,
+                                   int nd, const double *__restrict__ mu, const int32_t *__restrict__ morton_perm,
+                                   int C, float *__restrict__ cen) {
+  const int c = blockIdx.x, k = threadIdx.x;
+  if (k >= nd) return;
+  const int64_t i = morton_perm[((2 * (int64_t)c + 1) * n) / (2 * (int64_t)C)];
+  cen[(size_t)k * C + c] = (float)(X[i * d + sel[k]] - mu[sel[k]]);
+}
+
+// cn[c] = |centroid c|^2, summed in a fixed order
+__global__ void kmeans_norms_kernel(const float *__restrict__ cen, int nd, int C, float *__restrict__ cn) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < nd; ++k) s = fmaf(cen[(size_t)k * C + c], cen[(size_t)k * C + c], s);
+  cn[c] = s;
+}
+
+// members of cluster c are idx_s[seg[c] .. seg[c + 1]) (cells sorted by cluster id, stable)
+__global__ void kmeans_segments_kernel(const int32_t *__restrict__ cid_sorted, int64_t n, int C, int64_t *__restrict__ seg) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > C) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (cid_sorted[mid] < c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  seg[c] = lo;
+}
+
+__global__ void __launch_bounds__(kKmDims) kmeans_partial_kernel(const double *__restrict__ X, int64_t d,
+                                                                 const int32_t *__restrict__ sel, int nd,
+                                                                 const double *__restrict__ mu,
+                                                                 const int32_t *__restrict__ idx_s,
+                                                                 const int64_t *__restrict__ seg,
+                                                                 float *__restrict__ partial) {
+  const int part = blockIdx.x, c = blockIdx.y, k = threadIdx.x;
+  const int64_t s0 = seg[c], cnt = seg[c + 1] - s0;
+  const int64_t b = s0 + cnt * part / kKmParts, e = s0 + cnt * (part + 1) / kKmParts;
+  float s = 0.f;
+  if (k < nd) {
+    const int64_t col = sel[k];
+    const double m = mu[col];
+    for (int64_t r = b; r < e; ++r) s += (float)(X[(int64_t)idx_s[r] * d + col] - m);
+  }
+  partial[((size_t)c * kKmParts + part) * kKmDims + k] = s;
+}
+
+__global__ void __launch_bounds__(kKmDims) kmeans_update_kernel(const float *__restrict__ partial,
+                                                                const int64_t *__restrict__ seg, int nd, int C,
+                                                                float *__restrict__ cen) {
+  const int c = blockIdx.x, k = threadIdx.x;
+  const int64_t cnt = seg[c + 1] - seg[c];
+  if (k >= nd || cnt <= 0) return;  // an empty cluster keeps its centroid
+  float s = 0.f;
+  for (int part = 0; part < kKmParts; ++part) s += partial[((size_t)c * kKmParts + part) * kKmDims + k];
+  cen[(size_t)k * C + c] = s / (float)cnt;
+}
+
+__global__ void iota_kernel(int32_t *p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+
+// final sort key: cluster id above the Morton key (whose 16 low bits are dropped)
+__global__ void cluster_keys_kernel(unsigned long long *__restrict__ keys, const int32_t *__restrict__ cid, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = ((unsigned long long)(unsigned int)cid[i] << 48) | (keys[i] >> 16);
+}
+
+__global__ void cluster_of_key_kernel(const unsigned long long *__restrict__ keys_sorted, int64_t n,
+                                      int32_t *__restrict__ cid_sorted) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cid_sorted[i] = (int32_t)(keys_sorted[i] >> 48);
+}
+
 // ---- 1b. merge the per-(row, list) top-k1 lists of pass 1 into the emit threshold of pass 2 ----
 // lists: [n][nlists][k1] floats sorted descending in s-space (s = x.y - n_j/2, larger = closer).
-__global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t row_begin, int64_t n, int nlists, int k1,
-                                   const double *__restrict__ norm, const unsigned long long *ymax2_bits,
+__global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t row_begin, int64_t n, int nlists, int stride,
+                                   int k1, const double *__restrict__ norm, const unsigned long long *ymax2_bits,
                                    double margin_c, double radius_factor, float *__restrict__ key2) {
   const int64_t i = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;  // n = end of this call's row range
-  const float *base = lists + (size_t)i * nlists * k1;
+  const float *base = lists + (size_t)i * stride * k1;  // the first nlists of the row's `stride` lists are merged
   int idx[kMaxLists];
   for (int l = 0; l < nlists; ++l) idx[l] = 0;
   float sk = -INFINITY;
@@ -476,9 +636,11 @@ static int warp_grid(int64_t n_rows, int threads) {
 
 using namespace meld;
 
-// perm[a] = original index of the cell placed at position a; Xp = X rows in that order.
-static int morton_order(const double *X, int64_t n, int64_t d, cudaStream_t stream, DevBuf<int32_t> &perm,
-                        DevBuf<double> &Xp) {
+// Internal cell order: k-means cluster first, Morton curve of the four highest-variance features inside a
+// cluster.  perm[a] = original index of the cell placed at position a; Xp = X rows in that order;
+// cid (optional) = cluster id of every position (non-decreasing), empty when clustering is off.
+static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream, DevBuf<int32_t> &perm,
+                      DevBuf<double> &Xp, DevBuf<int32_t> &cid_sorted) {
   DevBuf<double> partial, mu, var;
   MELD_CHECK(partial.alloc((size_t)kMeanBlocks * d));
   MELD_CHECK(mu.alloc((size_t)d));
@@ -498,7 +660,8 @@ static int morton_order(const double *X, int64_t n, int64_t d, cudaStream_t stre
   std::vector<int> order((size_t)d);
   for (int64_t k = 0; k < d; ++k) order[(size_t)k] = (int)k;
   const int ndim = d < 4 ? (int)d : 4;
-  std::partial_sort(order.begin(), order.begin() + ndim, order.end(),
+  const int nd = d < kKmDims ? (int)d : kKmDims;  // features of the k-means step
+  std::partial_sort(order.begin(), order.begin() + nd, order.end(),
                     [&](int a, int b) { return h_var[a] > h_var[b] || (h_var[a] == h_var[b] && a < b); });
   MortonDims md;
   md.ndim = ndim;
@@ -517,13 +680,76 @@ static int morton_order(const double *X, int64_t n, int64_t d, cudaStream_t stre
   MELD_CHECK(perm.alloc((size_t)n));
   morton_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(X, n, d, md, keys.p, idx.p);
   MELD_LAUNCH_CHECK();
-  size_t tmp_bytes = 0;
+  size_t tmp_bytes = 0, tmp_bytes32 = 0;
   MELD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
                                             stream));
+  int C = tuning().clusters;
+  if (C > kKmMaxC) C = kKmMaxC;
+  const int64_t min_cells = tuning().cluster_cells > 0 ? tuning().cluster_cells : 1024;
+  while (C >= 32 && (int64_t)C * min_cells > n) C -= 32;  // at least ~4 tiles per cluster
+  C = C / 32 * 32;
+  DevBuf<int32_t> cid, cid_s, idx_s;
+  if (C >= 32) {
+    MELD_CHECK(cid.alloc((size_t)n));
+    MELD_CHECK(cid_s.alloc((size_t)n));
+    MELD_CHECK(idx_s.alloc((size_t)n));
+    MELD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes32, cid.p, cid_s.p, idx.p, idx_s.p, (int)n, 0, 8, stream));
+    if (tmp_bytes32 > tmp_bytes) tmp_bytes = tmp_bytes32;
+  }
   DevBuf<unsigned char> tmp;
   MELD_CHECK(tmp.alloc(tmp_bytes));
-  MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
-                                            stream));
+  if (C >= 32) {
+    // Morton order first: the seeds are evenly spaced along the curve
+    MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
+                                              stream));
+    DevBuf<int32_t> sel;
+    DevBuf<float> cen, cn, kpart;
+    DevBuf<int64_t> seg;
+    MELD_CHECK(sel.alloc((size_t)kKmDims));
+    MELD_CHECK(cen.alloc((size_t)nd * C));
+    MELD_CHECK(cn.alloc((size_t)C));
+    MELD_CHECK(kpart.alloc((size_t)C * kKmParts * kKmDims));
+    MELD_CHECK(seg.alloc((size_t)C + 1));
+    int32_t h_sel[kKmDims];
+    for (int k = 0; k < kKmDims; ++k) h_sel[k] = k < nd ? order[(size_t)k] : 0;
+    MELD_CUDA(cudaMemcpyAsync(sel.p, h_sel, sizeof(h_sel), cudaMemcpyHostToDevice, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));  // h_sel is a stack array
+    kmeans_seed_kernel<<<C, kKmDims, 0, stream>>>(X, n, d, sel.p, nd, mu.p, perm.p, C, cen.p);
+    MELD_LAUNCH_CHECK();
+    const size_t smem = ((size_t)nd * C + C + kKmDims) * sizeof(float) + kKmDims * sizeof(int);
+    auto assign = C == 32 ? kmeans_assign_kernel<1> : C == 64 ? kmeans_assign_kernel<2>
+                : C == 96 ? kmeans_assign_kernel<3> : kmeans_assign_kernel<4>;
+    MELD_CUDA(cudaFuncSetAttribute(assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int iters = tuning().kmeans_iters;
+    if (iters < 0) iters = 0;
+    if (iters > 16) iters = 16;
+    for (int it = 0; it <= iters; ++it) {
+      kmeans_norms_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, stream>>>(cen.p, nd, C, cn.p);
+      MELD_LAUNCH_CHECK();
+      assign<<<sm_count() * 2, 256, smem, stream>>>(X, n, d, sel.p, nd, mu.p, cen.p, cn.p, C, cid.p);
+      MELD_LAUNCH_CHECK();
+      if (it == iters) break;
+      // centroid update in a fixed summation order: members sorted by cluster (stable), kKmParts partial sums each
+      MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, cid.p, cid_s.p, idx.p, idx_s.p, (int)n, 0, 8, stream));
+      kmeans_segments_kernel<<<(unsigned)ceil_div(C + 1, 128), 128, 0, stream>>>(cid_s.p, n, C, seg.p);
+      MELD_LAUNCH_CHECK();
+      kmeans_partial_kernel<<<dim3(kKmParts, (unsigned)C), kKmDims, 0, stream>>>(X, d, sel.p, nd, mu.p, idx_s.p, seg.p,
+                                                                                kpart.p);
+      MELD_LAUNCH_CHECK();
+      kmeans_update_kernel<<<C, kKmDims, 0, stream>>>(kpart.p, seg.p, nd, C, cen.p);
+      MELD_LAUNCH_CHECK();
+    }
+    cluster_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(keys.p, cid.p, n);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
+                                              stream));
+    MELD_CHECK(cid_sorted.alloc((size_t)n));
+    cluster_of_key_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(keys_sorted.p, n, cid_sorted.p);
+    MELD_LAUNCH_CHECK();
+  } else {
+    MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
+                                              stream));
+  }
   MELD_CHECK(Xp.alloc((size_t)n * d));
   gather_rows_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(X, perm.p, n, d, Xp.p);
   MELD_LAUNCH_CHECK();
@@ -544,10 +770,13 @@ struct Candidates {
   int32_t max_per_row = 0;
   int64_t retries = 0;
   double pass1_ms = 0, pass2_ms = 0, gemm_flops_per_pass = 0;  // CUDA-event times of the two GEMM passes
+  double gemm_flops_pass1 = 0;  // pruned search: pass 1 (window + list pass) and pass 2 multiply different tile sets
+  double tile_frac = 1.0;       // (row tile, column tile) products of pass 2 / all of them
 };
 
 static int candidate_search(const double *X, int64_t n, int64_t d, int k1, double radius_factor, bool simt,
-                            int64_t row_begin, int64_t row_end, cudaStream_t stream, Candidates &out) {
+                            int64_t row_begin, int64_t row_end, const int32_t *cid, cudaStream_t stream,
+                            Candidates &out) {
   const int64_t nloc = row_end - row_begin;
   out.row_begin = row_begin;
   out.row_end = row_end;
@@ -585,16 +814,46 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
       for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]);
     }
   } ev_guard{ev};
+  const bool prune = plan.prune && !plan.simt;
+  TileLists tl;
   MELD_CUDA(cudaEventRecord(ev[0], stream));
-  MELD_CHECK(search_pass1(plan, st, lists.p, stream));
+  if (prune) {
+    // window pass (own tile +- window -> a first bound of eps_i), tile lists from that bound, list pass over
+    // the surviving tiles minus the window: the union of both passes' lists holds the exact k1 nearest
+    MELD_CHECK(tc_tile_balls(plan, X, cid, stream, &st));
+    tm.lap("  tile balls");
+    MELD_CHECK(tc_tile_lists(plan, st, 0, nullptr, nullptr, 0, stream, &tl));
+    tl.chunks = 1;
+    tl.slot0 = 0;
+    MELD_CHECK(tc_pass(plan, st, 1, lists.p, nullptr, nullptr, nullptr, 0, stream, &tl));
+    tm.lap("  window pass");
+    merge_lists_kernel<<<(unsigned)ceil_div(nloc, 128), 128, 0, stream>>>(lists.p, row_begin, row_end, 2, plan.nlists, k1,
+                                                                           norm.p, ymax2.p, plan.margin_c, radius_factor,
+                                                                           out.key2.p);
+    MELD_LAUNCH_CHECK();
+    tm.lap("  window merge");
+    MELD_CHECK(tc_tile_lists(plan, st, 1, out.key2.p, norm.p, 1, stream, &tl));
+    tm.lap("  tile lists");
+    tl.chunks = plan.nchunk;
+    tl.slot0 = 1;
+    MELD_CHECK(tc_pass(plan, st, 1, lists.p, nullptr, nullptr, nullptr, 0, stream, &tl));
+    tm.lap("  list pass");
+  } else {
+    MELD_CHECK(search_pass1(plan, st, lists.p, stream));
+  }
   MELD_CUDA(cudaEventRecord(ev[1], stream));
   tm.lap("search pass 1 (top-k)");
-  merge_lists_kernel<<<(unsigned)ceil_div(nloc, 128), 128, 0, stream>>>(lists.p, row_begin, row_end, plan.nlists, k1,
-                                                                         norm.p, ymax2.p, plan.margin_c, radius_factor,
-                                                                         out.key2.p);
+  merge_lists_kernel<<<(unsigned)ceil_div(nloc, 128), 128, 0, stream>>>(lists.p, row_begin, row_end, plan.nlists,
+                                                                         plan.nlists, k1, norm.p, ymax2.p, plan.margin_c,
+                                                                         radius_factor, out.key2.p);
   MELD_LAUNCH_CHECK();
   lists.release();
   out.passes = 1;
+  if (prune) {
+    MELD_CHECK(tc_tile_lists(plan, st, 2, out.key2.p, norm.p, 2, stream, &tl));
+    tl.chunks = plan.nchunk;
+    tl.slot0 = 0;
+  }
 
   // pass 2 appends (row, col) pairs to one global buffer; sized generously, retried with the exact
   // total if it overflows
@@ -608,11 +867,16 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
     MELD_CUDA(cudaMemsetAsync(gcount.p, 0, sizeof(unsigned long long), stream));
     tm.lap("merge + alloc");
     MELD_CUDA(cudaEventRecord(ev[2], stream));
-    MELD_CHECK(search_pass2(plan, st, out.key2.p, pairs.p, gcount.p, pair_cap, stream));
+    if (prune)
+      MELD_CHECK(tc_pass(plan, st, 2, nullptr, out.key2.p, pairs.p, gcount.p, pair_cap, stream, &tl));
+    else
+      MELD_CHECK(search_pass2(plan, st, out.key2.p, pairs.p, gcount.p, pair_cap, stream));
     MELD_CUDA(cudaEventRecord(ev[3], stream));
     tm.lap("search pass 2 (emit)");
     ++out.passes;
+    unsigned long long h_steps[4] = {0, 0, 0, 0};
     MELD_CUDA(cudaMemcpyAsync(&h_total, gcount.p, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
+    if (prune) MELD_CUDA(cudaMemcpyAsync(h_steps, st.tl_steps.p, sizeof(h_steps), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));
     {
       float ms1 = 0.f, ms2 = 0.f;
@@ -621,6 +885,14 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
       out.pass1_ms = ms1;
       out.pass2_ms = ms2;
       out.gemm_flops_per_pass = 2.0 * (double)nloc * (double)plan.n_pad_cols * (double)plan.kp_used;
+      out.gemm_flops_pass1 = out.gemm_flops_per_pass;
+      if (prune) {  // count the (128-row tile x 256-column tile) products actually issued
+        const double per_step = 2.0 * 128.0 * 256.0 * (double)plan.kp_used;
+        const double full = out.gemm_flops_per_pass;
+        out.gemm_flops_pass1 = per_step * (double)(h_steps[0] + h_steps[1]);
+        out.gemm_flops_per_pass = per_step * (double)h_steps[2];
+        out.tile_frac = full > 0 ? out.gemm_flops_per_pass / full : 1.0;
+      }
     }
     if ((int64_t)h_total <= pair_cap) break;
     if (attempt == 1) {
@@ -702,9 +974,10 @@ static int parse_build_params(const char *who, int64_t n, int64_t d, int knn, do
 // Stage 1 (row-local, shards over query rows with no exchange): candidate search + exact distances + eps
 // for rows [row_begin, row_end) of X (already in internal cell order).
 static int build_stage1(const double *X, int64_t n, int64_t d, const BuildParams &bp, int64_t row_begin,
-                        int64_t row_end, cudaStream_t stream, Candidates &cs, DevBuf<double> &d2, DevBuf<double> &eps) {
+                        int64_t row_end, const int32_t *cid, cudaStream_t stream, Candidates &cs, DevBuf<double> &d2,
+                        DevBuf<double> &eps) {
   StageTimer tm(stream);
-  MELD_CHECK(candidate_search(X, n, d, bp.k1, bp.radius_factor, bp.simt, row_begin, row_end, stream, cs));
+  MELD_CHECK(candidate_search(X, n, d, bp.k1, bp.radius_factor, bp.simt, row_begin, row_end, cid, stream, cs));
   cs.key2.release();
   tm.lap("candidate search total");
   const int64_t nloc = row_end - row_begin;
@@ -875,16 +1148,17 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   StageTimer tm(stream);
   // internal cell order (Morton curve over the highest-variance features)
   DevBuf<double> Xp;
-  DevBuf<int32_t> perm;
-  if (tuning().reorder && n >= 4096) {
-    MELD_CHECK(morton_order(X, n, d, stream, perm, Xp));
+  DevBuf<int32_t> perm, cid;
+  if (tuning().reorder && n >= tuning().reorder_min_n) {
+    MELD_CHECK(cell_order(X, n, d, stream, perm, Xp, cid));
     X = Xp.p;
   }
-  tm.lap("morton order");
+  tm.lap("cell order (k-means + morton)");
   Candidates cs;
   DevBuf<double> d2, eps;
-  MELD_CHECK(build_stage1(X, n, d, bp, 0, n, stream, cs, d2, eps));
+  MELD_CHECK(build_stage1(X, n, d, bp, 0, n, cid.p, stream, cs, d2, eps));
   Xp.release();
+  cid.release();
   meld_b200_graph *g = nullptr;
   MELD_CHECK(build_stage2(n, cs.cptr.p, cs.cand.p, d2.p, cs.total, eps.p, bp, perm, stream, &g));
   g->stats[0] = cs.passes;
@@ -893,6 +1167,8 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   g->times[0] = cs.pass1_ms;
   g->times[1] = cs.pass2_ms;
   g->times[2] = cs.gemm_flops_per_pass;
+  g->times[3] = cs.gemm_flops_pass1;
+  g->times[4] = cs.tile_frac > 0 ? cs.gemm_flops_per_pass / cs.tile_frac : cs.gemm_flops_per_pass;
   *graph_out = g;
   return 0;
 }
@@ -922,12 +1198,13 @@ int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, dou
   c->row_begin = row_begin;
   c->row_end = row_end;
   DevBuf<double> Xp;
-  if (tuning().reorder && n >= 4096) {  // every rank derives the same order from the same data
-    MELD_CHECK(morton_order(X, n, d, stream, c->perm, Xp));
+  DevBuf<int32_t> cid;
+  if (tuning().reorder && n >= tuning().reorder_min_n) {  // every rank derives the same order from the same data
+    MELD_CHECK(cell_order(X, n, d, stream, c->perm, Xp, cid));
     X = Xp.p;
   }
   Candidates cs;
-  MELD_CHECK(build_stage1(X, n, d, bp, row_begin, row_end, stream, cs, c->d2, c->eps));
+  MELD_CHECK(build_stage1(X, n, d, bp, row_begin, row_end, cid.p, stream, cs, c->d2, c->eps));
   c->total = cs.total;
   c->max_per_row = cs.max_per_row;
   c->passes = cs.passes;
@@ -1043,8 +1320,8 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   double radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
   if (radius_factor < 1.0) radius_factor = 1.0;
   Candidates cs;
-  MELD_CHECK(candidate_search(X, n, d, knn + 1, radius_factor, (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0, 0, n, stream,
-                              cs));
+  MELD_CHECK(candidate_search(X, n, d, knn + 1, radius_factor, (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0, 0, n, nullptr,
+                              stream, cs));
   MELD_CUDA(cudaMemcpyAsync(key2_out, cs.key2.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   row_counts_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(cs.cptr.p, n, cnt_out);
   MELD_LAUNCH_CHECK();
@@ -1053,9 +1330,9 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   return 0;
 }
 
-int meld_b200_graph_build_times(const meld_b200_graph_t *g, double *times4_host) {
-  MELD_REQUIRE(g && times4_host, "graph_build_times: NULL argument");
-  for (int i = 0; i < 4; ++i) times4_host[i] = g->times[i];
+int meld_b200_graph_build_times(const meld_b200_graph_t *g, double *times8_host) {
+  MELD_REQUIRE(g && times8_host, "graph_build_times: NULL argument");
+  for (int i = 0; i < 8; ++i) times8_host[i] = g->times[i];
   return 0;
 }
 

@@ -29,6 +29,20 @@ struct SearchPlan {
   int64_t n_pad = 0;  // rows padded to the tile size
   int kp = 0;         // padded K of the bf16 operand (3 d + 3 rounded up to 64)
   int terms = 3;      // bf16 split terms (3: hi*hi + hi*lo + lo*hi)
+  // pruned (ball-tree style) search: column tiles per 256-row group come from lists built with the triangle
+  // inequality on per-tile bounding balls; pass 1 = a window pass (slot 0) + a list pass (slots 1..nchunk)
+  bool prune = false;
+  int nchunk = 1;   // units per row tile in a list-driven pass
+  int window = 2;   // the window pass scans the column tiles within +-window of the row group's own tile
+};
+
+// Which column tiles a list-driven tc_pass visits (device arrays owned by SearchState).
+struct TileLists {
+  const int32_t *list = nullptr;  // [groups][stride], ascending tile indices
+  const int32_t *len = nullptr;   // [groups]
+  int stride = 0, g0 = 0;         // g0: first 256-row group of this call's row range
+  int chunks = 1;                 // units per row tile
+  int slot0 = 0;                  // pass 1: first list slot this launch writes
 };
 
 struct SearchState {
@@ -41,6 +55,13 @@ struct SearchState {
   DevBuf<uint16_t> b_op;  // n_pad x kp bf16, column operand (carries -n_j/2 in its tail columns)
   alignas(64) unsigned char tmap_a[128];
   alignas(64) unsigned char tmap_b[128];
+  // pruned search
+  DevBuf<double> ball_c;     // [tiles][2][d] centres of the (up to) two bounding balls of a 256-cell tile
+  DevBuf<double> ball_rho;   // [tiles][2] radii (-1: empty ball)
+  DevBuf<double> tile_rad;   // [tiles] largest emit radius of a tile's rows
+  DevBuf<int32_t> tl_list, tl_len;
+  DevBuf<unsigned long long> tl_steps;  // [4] (row tile, column tile) products issued by passes 0, 1, 2
+  int64_t n_tiles = 0, g0 = 0, n_groups = 0;
 };
 
 int search_plan(bool simt, int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, SearchPlan *plan);
@@ -56,6 +77,14 @@ int tc_plan(int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, Se
 int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const double *norm, cudaStream_t stream,
                SearchState *st);
 int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2,
-            unsigned long long *pairs, unsigned long long *count, int64_t cap, cudaStream_t stream);
+            unsigned long long *pairs, unsigned long long *count, int64_t cap, cudaStream_t stream,
+            const TileLists *tl = nullptr);
+// pruned search helpers (knn_tc.cu).  X is in internal cell order; cid (optional) is the non-decreasing cluster id
+// of every cell in that order -- a tile that straddles a cluster boundary gets one ball per side.
+int tc_tile_balls(const SearchPlan &plan, const double *X, const int32_t *cid, cudaStream_t stream, SearchState *st);
+// kind 0: window lists; 1: radius test from key2 without the window tiles; 2: radius test, all tiles.
+// counter: which tl_steps slot accumulates the (row tile x column tile) products of the pass that will use the lists.
+int tc_tile_lists(const SearchPlan &plan, SearchState &st, int kind, const float *key2, const double *norm, int counter,
+                  cudaStream_t stream, TileLists *out);
 
 }  // namespace meld

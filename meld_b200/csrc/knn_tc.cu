@@ -191,6 +191,15 @@ struct TcArgs {
   unsigned long long *pairs;   // pass 2: global append buffer of (row << 32 | col)
   unsigned long long *count;   // its fill count (keeps growing past cap)
   long long cap;
+  // Pruned search (ball-tree style): when tl_list is set, the column tiles a 256-row group must visit come
+  // from a per-group list (tl_list[(g - tl_g0) * tl_stride ..], tl_len[g - tl_g0] entries, ascending) instead
+  // of "all of them"; a unit is (row tile, chunk of its group's list), n_passes chunks per row tile.
+  const int32_t *tl_list;
+  const int32_t *tl_len;
+  int tl_stride, tl_g0;
+  int slot0;      // pass 1: first list slot of this launch (the window pass writes slot 0, the list pass 1..)
+  int n_slots;    // pass 1: list slots per (row, half) pair in `lists`
+  int interleave; // 1: chunk c = list entries c, c + n_passes, ... ; 0: contiguous chunks
 };
 
 // Work unit u -> (row tile, segment, column-tile order).  Units are issued segment-major so concurrent CTAs
@@ -200,12 +209,40 @@ struct TcArgs {
 // top-k threshold tight after the first tile instead of after a slow monotone approach.
 struct UnitPlan {
   int rt, seg, pass, ct0, len, start;
+  const int32_t *lp;  // listed column tiles of this unit (pruned search), or nullptr
+  int lstep;          // stride through the list (chunks interleave)
+  __device__ __forceinline__ int tile(int j) const { return lp ? __ldg(lp + (size_t)j * lstep) : ct0 + (start + j) % len; }
 };
 __device__ __forceinline__ UnitPlan unit_plan(const TcArgs &a, int u) {
   UnitPlan p;
   const int pass = u / a.n_row_tiles;  // 0: own segment, then the following ones cyclically
   p.rt = a.rt_begin + u % a.n_row_tiles;
   p.pass = pass;
+  p.lp = nullptr;
+  p.lstep = 1;
+  if (a.tl_list != nullptr) {
+    // chunk `pass` of the list of the 256-row group this row tile belongs to; the CTAs of a 2-cluster hold the
+    // two row tiles of one group, so they walk identical sequences in lockstep
+    // Chunks interleave (chunk c = list entries c, c + n_passes, ...): every chunk is a uniform sample of the
+    // group's tiles, so in pass 1 the bound published by chunk c (units are issued chunk-major) is already
+    // within a few percent of the final one and later chunks rarely take the insertion path.
+    const int gl = (p.rt * BM) / BN - a.tl_g0;
+    const int n = __ldg(a.tl_len + gl);
+    if (a.interleave) {
+      p.lp = a.tl_list + (size_t)gl * a.tl_stride + pass;
+      p.lstep = a.n_passes;
+      p.len = n > pass ? (n - pass + a.n_passes - 1) / a.n_passes : 0;
+    } else {
+      const int b = (int)(((long long)n * pass) / a.n_passes), e = (int)(((long long)n * (pass + 1)) / a.n_passes);
+      p.lp = a.tl_list + (size_t)gl * a.tl_stride + b;
+      p.lstep = 1;
+      p.len = e - b;
+    }
+    p.seg = pass;
+    p.ct0 = 0;
+    p.start = 0;
+    return p;
+  }
   const int own_ct = ((p.rt - p.rt % a.mc) * BM) / BN;  // identical for every CTA of a cluster (lockstep)
   int own_seg = (int)(((int64_t)own_ct * a.nseg) / a.n_col_tiles);
   while (own_seg + 1 < a.nseg && (int)((int64_t)a.n_col_tiles * (own_seg + 1) / a.nseg) <= own_ct) ++own_seg;
@@ -229,6 +266,22 @@ struct Bars {
   uint32_t tmem_base;
 };
 
+// KR > 0 (pass 1, k1 <= KR): every epilogue thread keeps its row's k1 largest s in KR registers, sorted, and
+// inserts with a branch-free max/min network (2 KR instructions, no memory).  The KR - k1 leading slots are
+// preset to +inf, so the k1-th largest value always sits in the LAST register (a runtime-indexed slot would
+// push the whole list to local memory).  The shared-memory lists of the
+// KR = 0 variant cost a dependent load per shifted slot -- ~30x slower on the tiles that hold a row's true
+// neighbours, which is most of what the pruned search still visits.
+template <int KR>
+__device__ __forceinline__ void topk_insert(float (&l)[KR > 0 ? KR : 1], float s) {
+#pragma unroll
+  for (int i = 0; i < KR; ++i) {
+    const float hi = fmaxf(l[i], s);
+    s = fminf(l[i], s);
+    l[i] = hi;
+  }
+}
+template <int KR>
 __global__ void __launch_bounds__(kTcThreads, 1)
     tc_search_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const TcArgs a) {
@@ -286,13 +339,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (int u = u_first; u < n_units; u += u_step) {
         const UnitPlan up = unit_plan(a, u);
         const int rt = up.rt;
+        if (up.len <= 0) continue;  // empty chunk of a pruned list: no role touches a barrier for it
         if (a.a_resident) {
           bar_wait(&bars->a_empty, uphase ^ 1u);
           bar_expect_tx(&bars->a_full, (uint32_t)a.nkb * kABytes);
           for (int kb = 0; kb < a.nkb; ++kb) tma_load_2d(&tmap_a, &bars->a_full, smA + kb * kABytes, kb * BK, rt * BM);
         }
         for (int j = 0; j < up.len; ++j) {
-          const int ct = up.ct0 + (up.start + j) % up.len;
+          const int ct = up.tile(j);
           for (int kb = 0; kb < a.nkb; ++kb) {
             bar_wait(&bars->empty[stage], phase ^ 1u);
             bar_expect_tx(&bars->full[stage], a.a_resident ? kBBytes : kBBytes + kABytes);
@@ -321,6 +375,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       uint32_t phase = 0, bphase = 0, uphase = 0;
       for (int u = u_first; u < n_units; u += u_step) {
         const UnitPlan up = unit_plan(a, u);
+        if (up.len <= 0) continue;
         if (a.a_resident) {
           bar_wait(&bars->a_full, uphase);
           tc_fence_after();
@@ -368,9 +423,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const UnitPlan up = unit_plan(a, u);
       const int rt = up.rt;
       const int64_t row = (int64_t)rt * BM + rin;
+      if (up.len <= 0) {  // empty chunk: its pass-1 list is all -inf
+        if (a.mode == 1 && row < a.row_end) {
+          float *out = a.lists + ((size_t)row * a.n_slots * 2 + (size_t)(a.slot0 + up.pass) * 2 + half) * a.k1;
+          for (int s = 0; s < a.k1; ++s) out[s] = -INFINITY;
+        }
+        continue;
+      }
       float thr;
+      float rl[KR > 0 ? KR : 1];
+#pragma unroll
+      for (int i = 0; i < (KR > 0 ? KR : 1); ++i) rl[i] = (i < KR - a.k1) ? INFINITY : -INFINITY;
       if (a.mode == 1) {
-        for (int s = 0; s < a.k1; ++s) lst[s * 2 * BM + lcol] = -INFINITY;
+        if (KR == 0)
+          for (int s = 0; s < a.k1; ++s) lst[s * 2 * BM + lcol] = -INFINITY;
         // start from the bound earlier segments of this row have published: values below it cannot be
         // among the k1 largest of the union, so this list only needs what beats it
         thr = row < a.row_end ? __ldcg(a.thr_g + row) : INFINITY;
@@ -399,14 +465,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         __syncwarp();
       };
       for (int j = 0; j < up.len; ++j) {
-        const int ct = up.ct0 + (up.start + j) % up.len;
+        const int ct = up.tile(j);
         bar_wait(&bars->tmem_full[buf], bphase);
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * BN;
         // Branch-free fast path: one max over the 32 columns of a chunk and a single compare; only a
         // chunk that holds a hit is scanned element by element.  Two chunks are kept in flight so the
         // TMEM load of the next one overlaps the scan of the current one.
-        auto scan = [&](const uint32_t (&v)[32], int chunk) {
+        auto scan = [&](const uint32_t (&v)[32], int chunk, float (&rl)[KR > 0 ? KR : 1]) {
           float t16[16];  // log-depth max (a serial chain of 31 dependent FMNMX would cost ~130 cycles per chunk)
 #pragma unroll
           for (int c = 0; c < 16; ++c) t16[c] = fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 16]));
@@ -422,7 +488,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll  // static register indices (a dynamic index would spill v to local memory)
               for (int c = 0; c < 32; ++c) {
                 const float s = __uint_as_float(v[c]);
-                if (s > thr) {
+                if (KR > 0) {
+                  if (s > thr) {
+                    topk_insert<KR>(rl, s);
+                    thr = fmaxf(thr, rl[KR > 0 ? KR - 1 : 0]);
+                  }
+                } else if (s > thr) {
                   int pos = a.k1 - 1;
                   while (pos > 0 && lst[(pos - 1) * 2 * BM + lcol] < s) {
                     lst[pos * 2 * BM + lcol] = lst[(pos - 1) * 2 * BM + lcol];
@@ -463,10 +534,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int chunk = 0; chunk < kChunks; chunk += 2) {
           tmem_ld_wait();
           tmem_ld32(tbase + (c0 + chunk + 1) * 32, vb);
-          scan(va, c0 + chunk);
+          scan(va, c0 + chunk, rl);
           tmem_ld_wait();
           if (chunk + 2 < kChunks) tmem_ld32(tbase + (c0 + chunk + 2) * 32, va);
-          scan(vb, c0 + chunk + 1);
+          scan(vb, c0 + chunk + 1, rl);
         }
         tc_fence_before();
         __syncwarp();
@@ -476,10 +547,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       if (a.mode == 2) flush_queue();
       if (a.mode == 1 && row < a.row_end) {
-        float *out = a.lists + ((size_t)row * a.n_passes * 2 + up.pass * 2 + half) * a.k1;  // list per (segment, half)
-        for (int s = 0; s < a.k1; ++s) out[s] = lst[s * 2 * BM + lcol];
+        float *out = a.lists + ((size_t)row * a.n_slots * 2 + (size_t)(a.slot0 + up.pass) * 2 + half) * a.k1;  // list per (slot, half)
+        float mine;
+        if (KR > 0) {
+#pragma unroll
+          for (int s = 0; s < KR; ++s)
+            if (s >= KR - a.k1) out[s - (KR - a.k1)] = rl[s];
+          mine = rl[KR > 0 ? KR - 1 : 0];
+        } else {
+          for (int s = 0; s < a.k1; ++s) out[s] = lst[s * 2 * BM + lcol];
+          mine = lst[(a.k1 - 1) * 2 * BM + lcol];
+        }
         // publish (monotone max; floats >= 0 and < 0 both ordered through the signed/unsigned trick)
-        const float mine = lst[(a.k1 - 1) * 2 * BM + lcol];
         if (mine > -INFINITY) {
           if (mine >= 0.f)
             atomicMax(reinterpret_cast<int *>(a.thr_g + row), __float_as_int(mine));
@@ -496,6 +575,153 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
+// ---- pruned search: bounding balls of 256-cell tiles and the column-tile lists --------------------
+// The reference's sklearn ball tree prunes by the triangle inequality; here the tree is one level of
+// 256-cell tiles of the internal cell order (k-means clusters, Morton curve inside a cluster).  A tile that
+// straddles a cluster boundary keeps one ball per side, so the ~n_clusters straddlers cost two ordinary
+// tiles instead of being near everything.  Any centre gives a valid bound as long as the radius is the
+// maximum distance to that same centre.
+constexpr int kTile = BN;  // cells per tile = one column tile = the two row tiles of a 2-CTA cluster
+
+__global__ void __launch_bounds__(kTile) tile_balls_kernel(const double *__restrict__ X, int64_t n, int64_t d,
+                                                           const int32_t *__restrict__ cid, double *__restrict__ ball_c,
+                                                           double *__restrict__ ball_rho) {
+  __shared__ int s_split;
+  __shared__ unsigned long long s_rho[2];
+  const int64_t t = blockIdx.x, t0 = t * kTile;
+  const int tid = threadIdx.x;
+  int64_t rem = n - t0;
+  const int cnt = rem <= 0 ? 0 : (rem < kTile ? (int)rem : kTile);
+  if (tid == 0) {
+    s_split = cnt;
+    s_rho[0] = s_rho[1] = 0ull;
+  }
+  __syncthreads();
+  if (cid != nullptr && tid < cnt && cid[t0 + tid] != cid[t0]) atomicMin(&s_split, tid);
+  __syncthreads();
+  const int split = s_split;
+  double *c0 = ball_c + (size_t)t * 2 * d, *c1 = c0 + d;
+  for (int64_t k = tid; k < d; k += kTile) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int r = 0; r < split; ++r) s0 += X[(t0 + r) * d + k];
+    for (int r = split; r < cnt; ++r) s1 += X[(t0 + r) * d + k];
+    c0[k] = split > 0 ? s0 / split : 0.0;
+    c1[k] = cnt > split ? s1 / (cnt - split) : 0.0;
+  }
+  __syncthreads();  // the block's own global writes are visible to it after the barrier
+  if (tid < cnt) {
+    const int b = tid < split ? 0 : 1;
+    const double *c = b ? c1 : c0;
+    const double *x = X + (t0 + tid) * d;
+    double acc = 0.0;
+    for (int64_t k = 0; k < d; ++k) {
+      const double diff = x[k] - c[k];
+      acc = fma(diff, diff, acc);
+    }
+    atomicMax(&s_rho[b], (unsigned long long)__double_as_longlong(acc));  // acc >= 0: bit order = value order
+  }
+  __syncthreads();
+  if (tid < 2) {
+    const bool has = tid == 0 ? split > 0 : cnt > split;
+    const double r2 = __longlong_as_double((long long)s_rho[tid]);
+    ball_rho[t * 2 + tid] = has ? sqrt(r2) * (1.0 + 1e-12) + 1e-300 : -1.0;
+  }
+}
+
+// Largest emit radius of the rows of a tile that belong to this call: r_i^2 = n_i - 2 key2_i is the squared
+// distance below which pass 2 emits (error margins included), and an upper bound of every distance the
+// search still needs for row i.
+__global__ void __launch_bounds__(kTile) tile_radius_kernel(const float *__restrict__ key2, const double *__restrict__ norm,
+                                                            int64_t n, int64_t row_begin, int64_t row_end,
+                                                            double *__restrict__ tile_rad) {
+  __shared__ double sh[kTile / 32];
+  const int64_t row = (int64_t)blockIdx.x * kTile + threadIdx.x;
+  double t2 = -1.0;  // no local row in this tile
+  if (row >= row_begin && row < row_end && row < n) {
+    const float k = key2[row];
+    t2 = isfinite(k) ? norm[row] - 2.0 * (double)k : INFINITY;
+    if (!(t2 >= 0.0)) t2 = (t2 != t2) ? INFINITY : 0.0;
+  }
+  for (int o = 16; o > 0; o >>= 1) t2 = fmax(t2, __shfl_xor_sync(0xffffffffu, t2, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kTile / 32; ++w) t2 = fmax(t2, sh[w]);
+    tile_rad[blockIdx.x] = t2 < 0.0 ? -1.0 : sqrt(t2) * (1.0 + 1e-9);
+  }
+}
+
+// One block per 256-row group: test every column tile, keep the survivors in ascending order.
+// kind 0: tiles within +-window (no test); 1: radius test without the window tiles; 2: radius test.
+__global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restrict__ ball_c,
+                                                           const double *__restrict__ ball_rho,
+                                                           const double *__restrict__ tile_rad, int64_t d, int n_tiles,
+                                                           int g0, int kind, int window, int rt_begin, int rt_end,
+                                                           int32_t *__restrict__ list, int32_t *__restrict__ len,
+                                                           unsigned long long *__restrict__ steps) {
+  __shared__ int s_warp[kTile / 32];
+  __shared__ int s_base;
+  const int gl = blockIdx.x, g = g0 + gl;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t *out = list + (size_t)gl * n_tiles;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  const double rad = kind == 0 ? 0.0 : tile_rad[g];
+  const double rr0 = ball_rho[(size_t)g * 2], rr1 = ball_rho[(size_t)g * 2 + 1];
+  const double *cr = ball_c + (size_t)g * 2 * d;
+  for (int base = 0; base < n_tiles; base += kTile) {
+    const int c = base + tid;
+    bool keep = false;
+    if (c < n_tiles) {
+      const bool in_window = c >= g - window && c <= g + window;
+      if (kind == 0) {
+        keep = in_window;
+      } else if (rad >= 0.0 && !(kind == 1 && in_window)) {
+        const double *cc = ball_c + (size_t)c * 2 * d;
+        const double rc0 = ball_rho[(size_t)c * 2], rc1 = ball_rho[(size_t)c * 2 + 1];
+        for (int a = 0; a < 2 && !keep; ++a) {
+          const double ra = a ? rr1 : rr0;
+          if (ra < 0.0) continue;
+          for (int b = 0; b < 2 && !keep; ++b) {
+            const double rb = b ? rc1 : rc0;
+            if (rb < 0.0) continue;
+            const double *pa = cr + (size_t)a * d, *pb = cc + (size_t)b * d;
+            double acc = 0.0;
+            for (int64_t k = 0; k < d; ++k) {
+              const double diff = pa[k] - pb[k];
+              acc = fma(diff, diff, acc);
+            }
+            // rows x of ball a, columns y of ball b: |x - y| >= |ca - cb| - ra - rb
+            const double lb = sqrt(acc) * (1.0 - 1e-12) - ra - rb;
+            keep = !(lb > rad);  // rad = inf keeps everything
+          }
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (keep) out[off + __popc(m & ((1u << lane) - 1u))] = c;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < kTile / 32; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    len[gl] = s_base;
+    // row tiles of this group inside the call's range (flop accounting)
+    int nrt = 0;
+    for (int rt = g * (BN / BM); rt < (g + 1) * (BN / BM); ++rt) nrt += (rt >= rt_begin && rt < rt_end) ? 1 : 0;
+    atomicAdd(steps, (unsigned long long)s_base * (unsigned long long)nrt);
   }
 }
 
@@ -565,6 +791,15 @@ int tc_plan(int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, Se
   plan->nlists = (int)nseg;
   if (tuning().p1_segments > 0 && tuning().p1_segments < plan->nlists) plan->nlists = tuning().p1_segments;
   plan->nlists *= 2;  // two epilogue threads (column halves) per row keep separate lists
+  plan->prune = tuning().prune != 0;
+  if (plan->prune) {
+    // list-driven passes: the window pass writes list slot 0, the list pass slots 1 .. nchunk
+    int64_t nchunk = nseg;
+    if (nchunk > kMaxLists / 2 - 1) nchunk = kMaxLists / 2 - 1;
+    plan->nchunk = (int)nchunk;
+    plan->nlists = 2 * (1 + (int)nchunk);
+    plan->window = tuning().prune_window > 0 ? tuning().prune_window : 0;
+  }
   // bf16 split error of x.y (~2^-15.8 |x||y|) plus fp32 accumulation, x2 for d^2, 4x safety
   plan->margin_c = ldexp(1.0, -11);
   return 0;
@@ -589,8 +824,54 @@ int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const 
   return 0;
 }
 
+
+int tc_tile_balls(const SearchPlan &plan, const double *X, const int32_t *cid, cudaStream_t stream, SearchState *st) {
+  const int64_t T = plan.n_pad / kTile;
+  st->n_tiles = T;
+  st->g0 = plan.row_begin / kTile;
+  const int64_t row_hi = plan.row_end == plan.n ? plan.n_pad : plan.row_end;
+  st->n_groups = ceil_div(row_hi, kTile) - st->g0;
+  MELD_REQUIRE(T < (int64_t)1 << 30 && st->n_groups >= 1, "tc_search: bad tile counts");
+  MELD_CHECK(st->ball_c.alloc((size_t)T * 2 * plan.d));
+  MELD_CHECK(st->ball_rho.alloc((size_t)T * 2));
+  MELD_CHECK(st->tile_rad.alloc((size_t)T));
+  MELD_CHECK(st->tl_list.alloc((size_t)st->n_groups * T));
+  MELD_CHECK(st->tl_len.alloc((size_t)st->n_groups));
+  MELD_CHECK(st->tl_steps.alloc(4));
+  MELD_CUDA(cudaMemsetAsync(st->tl_steps.p, 0, 4 * sizeof(unsigned long long), stream));
+  tile_balls_kernel<<<(unsigned)T, kTile, 0, stream>>>(X, plan.n, plan.d, cid, st->ball_c.p, st->ball_rho.p);
+  MELD_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_tile_lists(const SearchPlan &plan, SearchState &st, int kind, const float *key2, const double *norm, int counter,
+                  cudaStream_t stream, TileLists *out) {
+  MELD_REQUIRE(st.n_tiles > 0 && counter >= 0 && counter < 4, "tc_search: tile balls missing");
+  if (kind != 0) {
+    MELD_REQUIRE(key2 && norm, "tc_search: tile lists need the emit keys");
+    tile_radius_kernel<<<(unsigned)st.n_tiles, kTile, 0, stream>>>(key2, norm, plan.n, plan.row_begin, plan.row_end,
+                                                                   st.tile_rad.p);
+    MELD_LAUNCH_CHECK();
+  }
+  const int rt_begin = (int)(plan.row_begin / BM);
+  const int rt_end =
+      rt_begin + (int)((plan.row_end == plan.n ? plan.n_pad - plan.row_begin : plan.row_end - plan.row_begin) / BM);
+  MELD_CUDA(cudaMemsetAsync(st.tl_steps.p + counter, 0, sizeof(unsigned long long), stream));
+  tile_lists_kernel<<<(unsigned)st.n_groups, kTile, 0, stream>>>(st.ball_c.p, st.ball_rho.p, st.tile_rad.p, plan.d,
+                                                                 (int)st.n_tiles, (int)st.g0, kind, plan.window, rt_begin,
+                                                                 rt_end, st.tl_list.p, st.tl_len.p,
+                                                                 st.tl_steps.p + counter);
+  MELD_LAUNCH_CHECK();
+  out->list = st.tl_list.p;
+  out->len = st.tl_len.p;
+  out->stride = (int)st.n_tiles;
+  out->g0 = (int)st.g0;
+  return 0;
+}
+
 int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2,
-            unsigned long long *pairs, unsigned long long *count, int64_t cap, cudaStream_t stream) {
+            unsigned long long *pairs, unsigned long long *count, int64_t cap, cudaStream_t stream,
+            const TileLists *tl) {
   TcArgs a{};
   a.mode = mode;
   a.n = plan.n;
@@ -622,13 +903,34 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
   if (a.n_stages > kMaxStages) a.n_stages = kMaxStages;
   MELD_REQUIRE(a.n_stages >= 2, "tc_search: shared memory too small for a pipeline (knn too large)");
   const size_t smem = fixed + a.a_region + (size_t)a.n_stages * kBBytes;
-  MELD_CUDA(cudaFuncSetAttribute(tc_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcArgs);
+  TcKernel kern = tc_search_kernel<0>;
+  if (mode == 1 && tuning().reg_topk) {
+    if (plan.k1 <= 8) kern = tc_search_kernel<8>;
+    else if (plan.k1 <= 16) kern = tc_search_kernel<16>;
+    else if (plan.k1 <= 32) kern = tc_search_kernel<32>;
+  }
+  MELD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.n_passes = mode == 1 ? plan.nlists / 2 : a.nseg;  // pass 1 visits nlists/2 segments per row (own first)
+  a.n_slots = plan.nlists / 2;
+  a.slot0 = 0;
+  if (tl) {
+    MELD_REQUIRE(tl->list && tl->len && tl->chunks >= 1 && tl->slot0 + (mode == 1 ? tl->chunks : 0) <= a.n_slots,
+                 "tc_search: bad tile lists");
+    a.tl_list = tl->list;
+    a.tl_len = tl->len;
+    a.tl_stride = tl->stride;
+    a.tl_g0 = tl->g0;
+    a.n_passes = tl->chunks;
+    a.slot0 = tl->slot0;
+    a.interleave = mode == 1 ? (tuning().tl_interleave & 1) : ((tuning().tl_interleave >> 1) & 1);
+  }
   const int units = a.n_row_tiles * a.n_passes;
   // cluster size: B tiles are loaded once per cluster (TMA multicast), which divides the L2 -> SM traffic of
   // the streamed operand -- the kernel's real bound at K' = 320 -- by the cluster size
   int cs = tuning().tc_multicast;
   if (cs != 2 && cs != 4) cs = 1;
+  if (tl && cs > 2) cs = 2;  // lists are per 256-row group = the two row tiles of a 2-CTA cluster
   while (cs > 1 && (a.n_row_tiles % cs != 0 || a.rt_begin % cs != 0 || units < cs)) cs >>= 1;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kTcThreads);
@@ -647,7 +949,7 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
     // strand SMs for cluster size 4)
     cfg.gridDim = dim3((unsigned)(sm_count() / cs * cs));
     int max_clusters = 0;
-    MELD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, tc_search_kernel, &cfg));
+    MELD_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
     if (max_clusters < 1) {
       cs = 1;
       cfg.numAttrs = 0;
@@ -667,7 +969,7 @@ int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, con
     MELD_CHECK(encode_operand_map(st.b_op.p, plan.n_pad, plan.kp, BN / cs, tm));  // one slice of a B tile per CTA
     memcpy(&mb, tm, sizeof(mb));
   }
-  MELD_CUDA(cudaLaunchKernelEx(&cfg, tc_search_kernel, ma, mb, a));
+  MELD_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, a));
   MELD_LAUNCH_CHECK();
   return 0;
 }

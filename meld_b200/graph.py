@@ -298,9 +298,10 @@ class DeviceGraph:
         return {k: int(arr[i]) for i, k in enumerate(keys)}
 
     def build_times(self):
-        arr = (C.c_double * 4)()
+        arr = (C.c_double * 8)()
         nv.check(nv.lib().meld_b200_graph_build_times(self._h, arr), "graph_build_times")
-        return {"pass1_ms": arr[0], "pass2_ms": arr[1], "flops_per_pass": arr[2]}
+        return {"pass1_ms": arr[0], "pass2_ms": arr[1], "flops_per_pass": arr[2], "flops_pass1": arr[3] or arr[2],
+                "flops_unpruned_pass": arr[4] or arr[2]}
 
     # ---- lifetime ------------------------------------------------------------------------
     def close(self):

@@ -283,7 +283,7 @@ class MELD(object):
                 labels = labels.reshape(-1)
             else:
                 raise ValueError("sample_labels must be a single column. Got" "shape={}".format(labels.shape))
-        codes, uniques = pd.factorize(labels)  # hash pass; np.unique would sort N strings
+        codes, uniques = _factorize(labels)  # hash pass; np.unique would sort N strings
         uniques = np.asarray(uniques)
         order = np.argsort(uniques, kind="stable")
         rank = np.empty(len(order), dtype=np.int32)
@@ -416,6 +416,33 @@ class MELD(object):
         """Build the graph on ``X`` and estimate the density of each sample in ``sample_labels``."""
         self.fit(X, **kwargs)
         return self.transform(sample_labels)
+
+
+_HASH_MULT = np.random.default_rng(0x5EED).integers(1, 2**63 - 1, size=64, dtype=np.int64).astype(np.uint64) | np.uint64(1)
+
+
+def _factorize(labels):
+    """``pd.factorize`` (codes in order of first appearance, uniques), with a fast exact path for fixed-width
+    numpy string labels: hashing 64-bit words of the raw bytes avoids creating one Python string per cell."""
+    if labels.dtype.kind in "US" and labels.ndim == 1 and 0 < labels.dtype.itemsize <= 512 and len(labels) > 4096:
+        n, w = len(labels), labels.dtype.itemsize
+        raw = np.ascontiguousarray(labels).view(np.uint8).reshape(n, w)
+        w8 = (w + 7) // 8
+        if w8 * 8 != w:
+            pad = np.zeros((n, w8 * 8), dtype=np.uint8)
+            pad[:, :w] = raw
+            raw = pad
+        words = raw.view(np.uint64).reshape(n, w8)
+        h = words @ _HASH_MULT[:w8]  # wraps modulo 2^64
+        codes, _ = pd.factorize(h)
+        k = int(codes.max()) + 1
+        first = np.empty(k, dtype=np.int64)
+        first[codes[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)  # last write wins = first occurrence
+        rep = words[first]
+        # exact check that no two different labels shared a hash (else fall through to the generic path)
+        if k <= 4096 and all(np.array_equal(words[:, j], rep[:, j][codes]) for j in range(w8)):
+            return codes, labels[first]
+    return pd.factorize(labels)
 
 
 def _same_data(torch, a, b):

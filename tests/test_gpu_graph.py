@@ -169,3 +169,30 @@ def test_search_kernel_variants_build_the_same_graph(mb, tuning):
         assert np.abs(L.data - g["L"].data).max() <= 1e-10 * np.abs(g["L"].data).max()
     finally:
         nv.set_tuning(tc_multicast=2)
+
+
+def test_pruned_search_matches_oracle_and_unpruned(mb):
+    """k-means cell order + bounding-ball tile pruning (forced on at a test-sized n): the graph equals the
+    oracle's and the unpruned search's bit for bit, and tile pairs really were skipped."""
+    from meld_b200 import _native as nv
+    from oracle import graph as og
+
+    X, _ = mb.synthetic.make_blobs(20000, 30, 6, 3, 8.0, seed=9)
+    kw = dict(knn=9, decay=40.0, thresh=1e-4)
+    ref = og.build_graph(X, n_pca=None, **kw)["L"]
+    try:
+        nv.set_tuning(cluster_cells=512, clusters=32)  # 20000 cells -> 32 clusters of ~2.4 tiles
+        g1 = mb.DeviceGraph.from_data(X, anisotropy=1.0, **kw)
+        bt = g1.build_times()
+        L1 = g1.to_scipy_L()
+        nv.set_tuning(prune=0)
+        L0 = mb.DeviceGraph.from_data(X, anisotropy=1.0, **kw).to_scipy_L()
+        nv.set_tuning(prune=1, tc_multicast=1)
+        L2 = mb.DeviceGraph.from_data(X, anisotropy=1.0, **kw).to_scipy_L()
+    finally:
+        nv.set_tuning(cluster_cells=1024, clusters=64, prune=1, tc_multicast=2)
+    assert bt["flops_per_pass"] < 0.8 * bt["flops_unpruned_pass"], bt
+    for L in (L1, L2):
+        assert _same_pattern(L, ref)
+        assert np.abs(L.data - ref.data).max() <= 1e-10 * np.abs(ref.data).max()
+        assert _same_pattern(L, L0) and np.array_equal(L.data, L0.data)

@@ -125,3 +125,23 @@ def test_shard_bounds_are_tile_aligned_and_cover_all_rows():
         assert all(x <= y for x, y in zip(b[:-1], b[1:]))
         assert all(x % 512 == 0 for x, y in zip(b[:-1], b[1:]) if y > x)  # non-empty ranges start on a 512-row tile
     assert DeviceGraph.shard_bounds(6000, 3) == [0, 2048, 4096, 6000]
+
+
+def test_fast_label_factorize_equals_pandas():
+    """The raw-bytes hashing path of MELD._label_codes returns exactly pd.factorize's codes and uniques."""
+    import pandas as pd
+
+    from meld_b200.meld import _factorize
+
+    rng = np.random.default_rng(3)
+    for names, dtype in ((["sample_%d" % i for i in range(5)], None), (["a", "bb", "ccc"], "S3"),
+                         (["treatment", "control"], None)):
+        lab = np.array(names)[rng.integers(0, len(names), 20000)]
+        if dtype:
+            lab = lab.astype(dtype)
+        c0, u0 = pd.factorize(lab)
+        c1, u1 = _factorize(lab)
+        assert np.array_equal(c0, c1) and list(u0) == list(u1)
+    few = np.array(["x", "y", "x"])
+    c1, u1 = _factorize(few)  # short inputs take the generic path
+    assert list(c1) == [0, 1, 0] and list(u1) == ["x", "y"]
