@@ -76,6 +76,7 @@ struct Tuning {
   int clusters = 64;      // k-means clusters of the internal cell order (0: Morton order only)
   int kmeans_iters = 2;   // Lloyd iterations after seeding
   int reorder_min_n = 4096;  // cells are re-ordered (clusters + Morton curve) from this size on
+  int prune_proj = 1;     // tile pruning also uses the projection bound between k-means clusters
   int reg_topk = 1;       // pass 1 keeps its top-k lists in registers (k1 <= 32) instead of shared memory
   int tl_interleave = 0;  // bit 0 / bit 1: pass 1 / pass 2 chunks of a tile list interleave instead of being contiguous
   int cluster_cells = 1024;  // fewest cells per k-means cluster (fewer clusters for small inputs)

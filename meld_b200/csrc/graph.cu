@@ -300,6 +300,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "prune_window")) t.prune_window = value;
   else if (!strcmp(key, "cluster_cells")) t.cluster_cells = value;
   else if (!strcmp(key, "reg_topk")) t.reg_topk = value;
+  else if (!strcmp(key, "prune_proj")) t.prune_proj = value;
   else if (!strcmp(key, "tl_interleave")) t.tl_interleave = value;
   else {
     set_error("set_tuning: unknown key '%s'", key);

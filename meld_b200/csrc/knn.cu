@@ -136,9 +136,7 @@ __global__ void gather_rows_kernel(const double *__restrict__ X, const int32_t *
 // highest-variance features, float32 -- a heuristic: ANY assignment gives correct graphs), and the Morton
 // curve only orders the cells inside a cluster.  Everything is deterministic (no floating-point atomics):
 // every rank of a sharded build derives the same order from the same data.
-constexpr int kKmDims = 128;   // features used for clustering (highest variance first)
 constexpr int kKmParts = 16;   // partial sums per cluster in the centroid update
-constexpr int kKmMaxC = 128;
 
 // centroids are stored feature-major: cen[k * C + c]
 template <int CPL>  // clusters per lane
@@ -638,10 +636,12 @@ using namespace meld;
 
 // Internal cell order: k-means cluster first, Morton curve of the four highest-variance features inside a
 // cluster.  perm[a] = original index of the cell placed at position a; Xp = X rows in that order;
-// cid (optional) = cluster id of every position (non-decreasing), empty when clustering is off.
+// cl = the clusters (cluster id of every position, centroids), left empty when clustering is off.
 static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream, DevBuf<int32_t> &perm,
-                      DevBuf<double> &Xp, DevBuf<int32_t> &cid_sorted) {
-  DevBuf<double> partial, mu, var;
+                      DevBuf<double> &Xp, CellClusters &cl) {
+  DevBuf<double> partial, var;
+  DevBuf<double> &mu = cl.mu;
+  DevBuf<int32_t> &cid_sorted = cl.cid;
   MELD_CHECK(partial.alloc((size_t)kMeanBlocks * d));
   MELD_CHECK(mu.alloc((size_t)d));
   MELD_CHECK(var.alloc((size_t)d));
@@ -702,9 +702,12 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
     // Morton order first: the seeds are evenly spaced along the curve
     MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
                                               stream));
-    DevBuf<int32_t> sel;
-    DevBuf<float> cen, cn, kpart;
+    DevBuf<int32_t> &sel = cl.sel;
+    DevBuf<float> &cen = cl.cen;
+    DevBuf<float> cn, kpart;
     DevBuf<int64_t> seg;
+    cl.nd = nd;
+    cl.C = C;
     MELD_CHECK(sel.alloc((size_t)kKmDims));
     MELD_CHECK(cen.alloc((size_t)nd * C));
     MELD_CHECK(cn.alloc((size_t)C));
@@ -775,7 +778,7 @@ struct Candidates {
 };
 
 static int candidate_search(const double *X, int64_t n, int64_t d, int k1, double radius_factor, bool simt,
-                            int64_t row_begin, int64_t row_end, const int32_t *cid, cudaStream_t stream,
+                            int64_t row_begin, int64_t row_end, const CellClusters *cl, cudaStream_t stream,
                             Candidates &out) {
   const int64_t nloc = row_end - row_begin;
   out.row_begin = row_begin;
@@ -820,7 +823,7 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
   if (prune) {
     // window pass (own tile +- window -> a first bound of eps_i), tile lists from that bound, list pass over
     // the surviving tiles minus the window: the union of both passes' lists holds the exact k1 nearest
-    MELD_CHECK(tc_tile_balls(plan, X, cid, stream, &st));
+    MELD_CHECK(tc_tile_balls(plan, X, cl, stream, &st));
     tm.lap("  tile balls");
     MELD_CHECK(tc_tile_lists(plan, st, 0, nullptr, nullptr, 0, stream, &tl));
     tl.chunks = 1;
@@ -974,10 +977,10 @@ static int parse_build_params(const char *who, int64_t n, int64_t d, int knn, do
 // Stage 1 (row-local, shards over query rows with no exchange): candidate search + exact distances + eps
 // for rows [row_begin, row_end) of X (already in internal cell order).
 static int build_stage1(const double *X, int64_t n, int64_t d, const BuildParams &bp, int64_t row_begin,
-                        int64_t row_end, const int32_t *cid, cudaStream_t stream, Candidates &cs, DevBuf<double> &d2,
+                        int64_t row_end, const CellClusters *cl, cudaStream_t stream, Candidates &cs, DevBuf<double> &d2,
                         DevBuf<double> &eps) {
   StageTimer tm(stream);
-  MELD_CHECK(candidate_search(X, n, d, bp.k1, bp.radius_factor, bp.simt, row_begin, row_end, cid, stream, cs));
+  MELD_CHECK(candidate_search(X, n, d, bp.k1, bp.radius_factor, bp.simt, row_begin, row_end, cl, stream, cs));
   cs.key2.release();
   tm.lap("candidate search total");
   const int64_t nloc = row_end - row_begin;
@@ -1148,17 +1151,17 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   StageTimer tm(stream);
   // internal cell order (Morton curve over the highest-variance features)
   DevBuf<double> Xp;
-  DevBuf<int32_t> perm, cid;
+  DevBuf<int32_t> perm;
+  CellClusters cl;
   if (tuning().reorder && n >= tuning().reorder_min_n) {
-    MELD_CHECK(cell_order(X, n, d, stream, perm, Xp, cid));
+    MELD_CHECK(cell_order(X, n, d, stream, perm, Xp, cl));
     X = Xp.p;
   }
   tm.lap("cell order (k-means + morton)");
   Candidates cs;
   DevBuf<double> d2, eps;
-  MELD_CHECK(build_stage1(X, n, d, bp, 0, n, cid.p, stream, cs, d2, eps));
+  MELD_CHECK(build_stage1(X, n, d, bp, 0, n, &cl, stream, cs, d2, eps));
   Xp.release();
-  cid.release();
   meld_b200_graph *g = nullptr;
   MELD_CHECK(build_stage2(n, cs.cptr.p, cs.cand.p, d2.p, cs.total, eps.p, bp, perm, stream, &g));
   g->stats[0] = cs.passes;
@@ -1198,13 +1201,13 @@ int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, dou
   c->row_begin = row_begin;
   c->row_end = row_end;
   DevBuf<double> Xp;
-  DevBuf<int32_t> cid;
+  CellClusters cl;
   if (tuning().reorder && n >= tuning().reorder_min_n) {  // every rank derives the same order from the same data
-    MELD_CHECK(cell_order(X, n, d, stream, c->perm, Xp, cid));
+    MELD_CHECK(cell_order(X, n, d, stream, c->perm, Xp, cl));
     X = Xp.p;
   }
   Candidates cs;
-  MELD_CHECK(build_stage1(X, n, d, bp, row_begin, row_end, cid.p, stream, cs, c->d2, c->eps));
+  MELD_CHECK(build_stage1(X, n, d, bp, row_begin, row_end, &cl, stream, cs, c->d2, c->eps));
   c->total = cs.total;
   c->max_per_row = cs.max_per_row;
   c->passes = cs.passes;

@@ -36,6 +36,17 @@ struct SearchPlan {
   int window = 2;   // the window pass scans the column tiles within +-window of the row group's own tile
 };
 
+// k-means clusters of the internal cell order (filled by cell_order in knn.cu; empty when clustering is off)
+constexpr int kKmDims = 128;   // features used for clustering (highest variance first)
+constexpr int kKmMaxC = 128;
+struct CellClusters {
+  DevBuf<int32_t> cid;  // [n] cluster of every position of the internal order, non-decreasing
+  DevBuf<float> cen;    // [nd][C] centroids of the centred data on the selected features
+  DevBuf<int32_t> sel;  // [kKmDims] the selected features
+  DevBuf<double> mu;    // [d] column means used for centring
+  int nd = 0, C = 0;
+};
+
 // Which column tiles a list-driven tc_pass visits (device arrays owned by SearchState).
 struct TileLists {
   const int32_t *list = nullptr;  // [groups][stride], ascending tile indices
@@ -59,6 +70,13 @@ struct SearchState {
   DevBuf<double> ball_c;     // [tiles][2][d] centres of the (up to) two bounding balls of a 256-cell tile
   DevBuf<double> ball_rho;   // [tiles][2] radii (-1: empty ball)
   DevBuf<double> tile_rad;   // [tiles] largest emit radius of a tile's rows
+  // projection bound between cells of different clusters A != B: with w = (c_B - c_A)/|c_B - c_A| and m the
+  // midpoint, |x - y| >= w.(y - x) = -p_AB(x) - p_BA(y), p_AB(x) = w.(x - m); tile_hi holds max p per segment
+  DevBuf<int32_t> tile_cl;   // [tiles][2] cluster of a tile's segment (-1: empty or mixed)
+  DevBuf<double> tile_hi;    // [tiles][2][C]
+  DevBuf<double> cl_norm;    // [C] |c_A|^2
+  DevBuf<double> cl_dist;    // [C][C] |c_A - c_B|
+  int n_clusters = 0;
   DevBuf<int32_t> tl_list, tl_len;
   DevBuf<unsigned long long> tl_steps;  // [4] (row tile, column tile) products issued by passes 0, 1, 2
   int64_t n_tiles = 0, g0 = 0, n_groups = 0;
@@ -79,9 +97,9 @@ int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const 
 int tc_pass(const SearchPlan &plan, SearchState &st, int mode, float *lists, const float *key2,
             unsigned long long *pairs, unsigned long long *count, int64_t cap, cudaStream_t stream,
             const TileLists *tl = nullptr);
-// pruned search helpers (knn_tc.cu).  X is in internal cell order; cid (optional) is the non-decreasing cluster id
-// of every cell in that order -- a tile that straddles a cluster boundary gets one ball per side.
-int tc_tile_balls(const SearchPlan &plan, const double *X, const int32_t *cid, cudaStream_t stream, SearchState *st);
+// pruned search helpers (knn_tc.cu).  X is in internal cell order; cl (optional) describes the k-means clusters of
+// that order -- a tile that straddles a cluster boundary gets one ball per side.
+int tc_tile_balls(const SearchPlan &plan, const double *X, const CellClusters *cl, cudaStream_t stream, SearchState *st);
 // kind 0: window lists; 1: radius test from key2 without the window tiles; 2: radius test, all tiles.
 // counter: which tl_steps slot accumulates the (row tile x column tile) products of the pass that will use the lists.
 int tc_tile_lists(const SearchPlan &plan, SearchState &st, int kind, const float *key2, const double *norm, int counter,

@@ -632,6 +632,124 @@ __global__ void __launch_bounds__(kTile) tile_balls_kernel(const double *__restr
   }
 }
 
+// |c_A|^2 and |c_A - c_B| of the k-means centroids, in double from the float centroids (cen[k * C + c])
+__global__ void cluster_tables_kernel(const float *__restrict__ cen, int nd, int C, double *__restrict__ cl_norm,
+                                      double *__restrict__ cl_dist) {
+  const int a = blockIdx.x;
+  for (int b = threadIdx.x; b < C; b += blockDim.x) {
+    double acc = 0.0, na = 0.0;
+    for (int k = 0; k < nd; ++k) {
+      const double ca = (double)cen[(size_t)k * C + a], cb = (double)cen[(size_t)k * C + b];
+      const double diff = ca - cb;
+      acc = fma(diff, diff, acc);
+      na = fma(ca, ca, na);
+    }
+    cl_dist[(size_t)a * C + b] = sqrt(acc);
+    if (b == 0) cl_norm[a] = na;
+  }
+}
+
+// Projection bound (see SearchState::tile_hi).  With z = (x - mu) on the selected features and g_B(z) = c_B . z,
+//   p_AB(x) = w_AB . (z - m_AB) = (g_B - g_A - (|c_B|^2 - |c_A|^2)/2) / |c_B - c_A|,
+// so one pass of "all centroids times the cell" (the k-means assignment's contraction, here in float64) gives a
+// cell's projection towards every other cluster.  One block per tile; per segment the maximum over its cells.
+template <int CPL>
+__global__ void __launch_bounds__(kTile) tile_proj_kernel(const double *__restrict__ X, int64_t n, int64_t d,
+                                                          const int32_t *__restrict__ cid, const int32_t *__restrict__ sel,
+                                                          int nd, const double *__restrict__ mu,
+                                                          const float *__restrict__ cen, int C,
+                                                          const double *__restrict__ cl_norm,
+                                                          const double *__restrict__ cl_dist,
+                                                          int32_t *__restrict__ tile_cl, double *__restrict__ tile_hi) {
+  extern __shared__ double pj_sm[];
+  double *scen = pj_sm;                          // nd * C
+  double *shi = scen + (size_t)nd * C;           // [warps][2][C]
+  double *smu = shi + (size_t)(kTile / 32) * 2 * C;  // kKmDims
+  int *ssel = reinterpret_cast<int *>(smu + kKmDims);
+  __shared__ int s_split;
+  const int64_t t = blockIdx.x, t0 = t * kTile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int64_t rem = n - t0;
+  const int cnt = rem <= 0 ? 0 : (rem < kTile ? (int)rem : kTile);
+  for (int i = tid; i < nd * C; i += kTile) scen[i] = (double)cen[i];
+  for (int i = tid; i < kKmDims; i += kTile) {
+    ssel[i] = i < nd ? sel[i] : 0;
+    smu[i] = i < nd ? mu[sel[i]] : 0.0;
+  }
+  if (tid == 0) s_split = cnt;
+  __syncthreads();
+  if (tid < cnt && cid[t0 + tid] != cid[t0]) atomicMin(&s_split, tid);
+  __syncthreads();
+  const int split = s_split;
+  // segment clusters: cid is sorted, so a segment is pure iff its first and last cells agree
+  const int cl0 = split > 0 ? cid[t0] : -1;
+  const int cl1 = (cnt > split && cid[t0 + split] == cid[t0 + cnt - 1]) ? cid[t0 + split] : -1;
+  double hm[2][CPL];
+#pragma unroll
+  for (int sgm = 0; sgm < 2; ++sgm)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) hm[sgm][c] = -INFINITY;
+  for (int r = warp; r < cnt; r += kTile / 32) {
+    const int sgm = r < split ? 0 : 1;
+    const int A = sgm ? cl1 : cl0;
+    if (A < 0) continue;  // warp-uniform
+    double z[kKmDims / 32];
+#pragma unroll
+    for (int j = 0; j < kKmDims / 32; ++j) {
+      const int k = j * 32 + lane;
+      z[j] = k < nd ? X[(t0 + r) * d + ssel[k]] - smu[k] : 0.0;
+    }
+    double acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+#pragma unroll
+    for (int j = 0; j < kKmDims / 32; ++j) {
+      if (j * 32 < nd) {
+        const int lim = min(32, nd - j * 32);
+        for (int l = 0; l < lim; ++l) {
+          const double zk = __shfl_sync(0xffffffffu, z[j], l);
+          const double *row = scen + (size_t)(j * 32 + l) * C + lane;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) acc[c] = fma(zk, row[32 * c], acc[c]);
+        }
+      }
+    }
+    double gA = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const double v = __shfl_sync(0xffffffffu, acc[c], A & 31);
+      if (c == (A >> 5)) gA = v;
+    }
+    const double nA = cl_norm[A];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int B = lane + 32 * c;
+      const double D = cl_dist[(size_t)A * C + B];
+      double pr = (acc[c] - gA - 0.5 * (cl_norm[B] - nA)) / D;
+      // (nearly) coincident centroids: the quotient amplifies rounding -> no bound for this pair
+      if (B == A || !(D > 1e-6 * (sqrt(nA) + sqrt(cl_norm[B]) + 1.0)) || !(pr == pr)) pr = INFINITY;
+      if (sgm == 0)
+        hm[0][c] = fmax(hm[0][c], pr);
+      else
+        hm[1][c] = fmax(hm[1][c], pr);
+    }
+  }
+#pragma unroll
+  for (int sgm = 0; sgm < 2; ++sgm)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) shi[((size_t)warp * 2 + sgm) * C + lane + 32 * c] = hm[sgm][c];
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += kTile) {
+    double m = -INFINITY;
+    for (int w = 0; w < kTile / 32; ++w) m = fmax(m, shi[(size_t)w * 2 * C + i]);
+    tile_hi[(size_t)t * 2 * C + i] = m;
+  }
+  if (tid == 0) {
+    tile_cl[t * 2] = cl0;
+    tile_cl[t * 2 + 1] = cl1;
+  }
+}
+
 // Largest emit radius of the rows of a tile that belong to this call: r_i^2 = n_i - 2 key2_i is the squared
 // distance below which pass 2 emits (error margins included), and an upper bound of every distance the
 // search still needs for row i.
@@ -659,8 +777,11 @@ __global__ void __launch_bounds__(kTile) tile_radius_kernel(const float *__restr
 // kind 0: tiles within +-window (no test); 1: radius test without the window tiles; 2: radius test.
 __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restrict__ ball_c,
                                                            const double *__restrict__ ball_rho,
-                                                           const double *__restrict__ tile_rad, int64_t d, int n_tiles,
-                                                           int g0, int kind, int window, int rt_begin, int rt_end,
+                                                           const double *__restrict__ tile_rad,
+                                                           const int32_t *__restrict__ tile_cl,
+                                                           const double *__restrict__ tile_hi, int C, int64_t d,
+                                                           int n_tiles, int g0, int kind, int window, int rt_begin,
+                                                           int rt_end,
                                                            int32_t *__restrict__ list, int32_t *__restrict__ len,
                                                            unsigned long long *__restrict__ steps) {
   __shared__ int s_warp[kTile / 32];
@@ -673,6 +794,7 @@ __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restr
   const double rad = kind == 0 ? 0.0 : tile_rad[g];
   const double rr0 = ball_rho[(size_t)g * 2], rr1 = ball_rho[(size_t)g * 2 + 1];
   const double *cr = ball_c + (size_t)g * 2 * d;
+  const int rA0 = tile_cl ? tile_cl[(size_t)g * 2] : -1, rA1 = tile_cl ? tile_cl[(size_t)g * 2 + 1] : -1;
   for (int base = 0; base < n_tiles; base += kTile) {
     const int c = base + tid;
     bool keep = false;
@@ -689,6 +811,15 @@ __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restr
           for (int b = 0; b < 2 && !keep; ++b) {
             const double rb = b ? rc1 : rc0;
             if (rb < 0.0) continue;
+            // cells of different clusters A != B: |x - y| >= -p_AB(x) - p_BA(y) (projection on the centroid axis)
+            const int A = a ? rA1 : rA0;
+            const int B = tile_cl ? tile_cl[(size_t)c * 2 + b] : -1;
+            if (A >= 0 && B >= 0 && A != B) {
+              const double h1 = tile_hi[((size_t)g * 2 + a) * C + B], h2 = tile_hi[((size_t)c * 2 + b) * C + A];
+              const double lbp = -h1 - h2;
+              // proven too far for this pair of segments (slack: float64 rounding of the projections)
+              if (lbp - 1e-9 * (fabs(h1) + fabs(h2) + 1.0) > rad) continue;
+            }
             const double *pa = cr + (size_t)a * d, *pb = cc + (size_t)b * d;
             double acc = 0.0;
             for (int64_t k = 0; k < d; ++k) {
@@ -825,7 +956,8 @@ int tc_prepare(const SearchPlan &plan, const double *X, const double *mu, const 
 }
 
 
-int tc_tile_balls(const SearchPlan &plan, const double *X, const int32_t *cid, cudaStream_t stream, SearchState *st) {
+int tc_tile_balls(const SearchPlan &plan, const double *X, const CellClusters *cl, cudaStream_t stream, SearchState *st) {
+  const int32_t *cid = (cl && cl->cid.p) ? cl->cid.p : nullptr;
   const int64_t T = plan.n_pad / kTile;
   st->n_tiles = T;
   st->g0 = plan.row_begin / kTile;
@@ -841,6 +973,24 @@ int tc_tile_balls(const SearchPlan &plan, const double *X, const int32_t *cid, c
   MELD_CUDA(cudaMemsetAsync(st->tl_steps.p, 0, 4 * sizeof(unsigned long long), stream));
   tile_balls_kernel<<<(unsigned)T, kTile, 0, stream>>>(X, plan.n, plan.d, cid, st->ball_c.p, st->ball_rho.p);
   MELD_LAUNCH_CHECK();
+  st->n_clusters = 0;
+  if (cid && cl->C >= 32 && cl->C % 32 == 0 && cl->C <= kKmMaxC && tuning().prune_proj) {
+    const int C = cl->C, nd = cl->nd;
+    MELD_CHECK(st->cl_norm.alloc((size_t)C));
+    MELD_CHECK(st->cl_dist.alloc((size_t)C * C));
+    MELD_CHECK(st->tile_cl.alloc((size_t)T * 2));
+    MELD_CHECK(st->tile_hi.alloc((size_t)T * 2 * C));
+    cluster_tables_kernel<<<C, 128, 0, stream>>>(cl->cen.p, nd, C, st->cl_norm.p, st->cl_dist.p);
+    MELD_LAUNCH_CHECK();
+    const size_t smem = ((size_t)nd * C + (size_t)(kTile / 32) * 2 * C + kKmDims) * sizeof(double) + kKmDims * sizeof(int);
+    auto proj = C == 32 ? tile_proj_kernel<1> : C == 64 ? tile_proj_kernel<2> : C == 96 ? tile_proj_kernel<3>
+                                                                                       : tile_proj_kernel<4>;
+    MELD_CUDA(cudaFuncSetAttribute(proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proj<<<(unsigned)T, kTile, smem, stream>>>(X, plan.n, plan.d, cid, cl->sel.p, nd, cl->mu.p, cl->cen.p, C,
+                                               st->cl_norm.p, st->cl_dist.p, st->tile_cl.p, st->tile_hi.p);
+    MELD_LAUNCH_CHECK();
+    st->n_clusters = C;
+  }
   return 0;
 }
 
@@ -857,10 +1007,10 @@ int tc_tile_lists(const SearchPlan &plan, SearchState &st, int kind, const float
   const int rt_end =
       rt_begin + (int)((plan.row_end == plan.n ? plan.n_pad - plan.row_begin : plan.row_end - plan.row_begin) / BM);
   MELD_CUDA(cudaMemsetAsync(st.tl_steps.p + counter, 0, sizeof(unsigned long long), stream));
-  tile_lists_kernel<<<(unsigned)st.n_groups, kTile, 0, stream>>>(st.ball_c.p, st.ball_rho.p, st.tile_rad.p, plan.d,
-                                                                 (int)st.n_tiles, (int)st.g0, kind, plan.window, rt_begin,
-                                                                 rt_end, st.tl_list.p, st.tl_len.p,
-                                                                 st.tl_steps.p + counter);
+  tile_lists_kernel<<<(unsigned)st.n_groups, kTile, 0, stream>>>(
+      st.ball_c.p, st.ball_rho.p, st.tile_rad.p, st.n_clusters ? st.tile_cl.p : nullptr,
+      st.n_clusters ? st.tile_hi.p : nullptr, st.n_clusters, plan.d, (int)st.n_tiles, (int)st.g0, kind, plan.window,
+      rt_begin, rt_end, st.tl_list.p, st.tl_len.p, st.tl_steps.p + counter);
   MELD_LAUNCH_CHECK();
   out->list = st.tl_list.p;
   out->len = st.tl_len.p;
