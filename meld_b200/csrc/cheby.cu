@@ -447,6 +447,162 @@ __global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
   }
 }
 
+// ---- x_mode 2: the flat kernel ---------------------------------------------------------------------------
+// Measured on B200 (tools/microbench/gather_bench.cu): random 32-byte rows out of an L2-resident table arrive
+// at 0.55 / 0.70 / 0.79 rows per cycle per SM with 1024 / 2048 / 4096 LDG.256 in flight per SM, LDGSTS and
+// 32-byte TMA bulk copies are far slower (0.2 and 0.16 at best) -- the gather is bound by memory-level
+// parallelism, not by L1 wavefronts.  So this kernel spends nothing on staging: no shared memory, no
+// producer / gather / compute roles, no barriers; every one of the (up to) 32 warps per SM walks its own rows
+// (G lanes per row, U independent gathers per lane in flight) and streams values and columns straight from
+// global memory with evict-first loads.  Row groups are dealt to warps round-robin, so the warps of the grid
+// stream one contiguous window of the matrix at any time.
+__device__ __forceinline__ int ld_stream_s32(const int32_t *p) {
+  int v;
+  asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void ld_stream_v4(const double *p, double (&v)[4]) {
+  asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld_stream_c4(const int32_t *p, int (&c)[4]) {
+  asm volatile("ld.global.cs.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "l"(p));
+}
+
+template <int P>
+struct FlatUnroll {
+  static constexpr int value = P <= 4 ? 4 : 2;  // gathers in flight per lane
+};
+
+template <int P, int G, int TB>
+__global__ void __launch_bounds__(TB, 1) cheby_flat_kernel(const StepArgs a, const int64_t n_rows) {
+  constexpr int U = FlatUnroll<P>::value;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gid = lane / G, gl = lane % G;
+  const int64_t gw = (int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5);
+  const int64_t nW = (int64_t)gridDim.x * (TB / 32);
+  for (int64_t rb = gw * RPW; rb < n_rows; rb += nW * RPW) {  // warp-uniform
+    const int64_t r = rb + gid;
+    const bool act = r < n_rows;
+    int eb = 0, ee = 0;
+    if (act) {
+      eb = __ldg(a.row_ptr + r);
+      ee = __ldg(a.row_ptr + r + 1);
+    }
+    const bool epi = act && gl < P;
+    const size_t li = (size_t)r * P + gl;
+    double tc = 0.0, told = 0.0, rold = 0.0;
+    if (epi) {  // requested first so their latency overlaps the row product
+      tc = __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
+      if (a.gamma != 0.0) told = ld_stream(a.Told + li);
+      if (a.R != nullptr && a.r_acc) rold = ld_stream(a.R + li);
+    }
+    double acc[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) acc[k] = 0.0;
+    // Each lane takes U consecutive entries per iteration, starting at a multiple of 4 entries: values and
+    // columns arrive as one aligned 256-bit / 128-bit load per lane (entries before the row's first or past
+    // its last are masked; the arrays are padded by kCsrPad entries).
+    for (int a0 = (eb & ~3) + gl * 4; a0 < ee; a0 += 4 * G) {
+      double v[4];
+      int c[4];
+      ld_stream_v4(a.val + a0, v);
+      ld_stream_c4(a.col + a0, c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int eu = a0 + u;
+        if (eu < eb || eu >= ee) {
+          v[u] = 0.0;
+          c[u] = -1;
+        }
+      }
+      if constexpr (U >= 4) {
+        double x[4][P];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c[u] >= 0) {
+            gather_row<P>(a.Tcur, c[u], x[u]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < P; ++k) x[u][k] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) acc[k] = fma(v[u], x[u][k], acc[k]);
+        }
+      } else {  // wide signals: two gathers in flight at a time
+#pragma unroll
+        for (int h = 0; h < 4; h += 2) {
+          double x[2][P];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (c[h + u] >= 0) {
+              gather_row<P>(a.Tcur, c[h + u], x[u]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < P; ++k) x[u][k] = 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) acc[k] = fma(v[h + u], x[u][k], acc[k]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < P; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (epi) {
+      double y = acc[0];
+#pragma unroll
+      for (int k = 1; k < P; ++k)
+        if (gl == k) y = acc[k];
+      double tn = a.alpha * (y - a.shift * tc);
+      if (a.gamma != 0.0) tn -= a.gamma * told;
+      if (a.Tnew) a.Tnew[li] = tn;  // gathered by the next step: keep cacheable
+      if (a.R) {
+        double rv = a.c * tn + a.c_cur * tc;
+        if (a.r_acc) rv += rold;
+        st_stream(a.R + li, rv);
+      }
+    }
+  }
+}
+
+typedef void (*FlatKernel)(const StepArgs, const int64_t);
+
+template <int P, int TB>
+static FlatKernel pick_flat_group(int G) {
+  if constexpr (P <= 4) {
+    if (G == 4) return cheby_flat_kernel<P, 4, TB>;
+  }
+  if (G <= 8) return cheby_flat_kernel<P, 8, TB>;
+  return cheby_flat_kernel<P, 16, TB>;
+}
+
+template <int TB>
+static FlatKernel pick_flat(int P, int G) {
+  switch (P) {
+    case 1: return pick_flat_group<1, TB>(G);
+    case 2: return pick_flat_group<2, TB>(G);
+    case 3: return pick_flat_group<3, TB>(G);
+    case 4: return pick_flat_group<4, TB>(G);
+    case 5: return pick_flat_group<5, TB>(G);
+    case 6: return pick_flat_group<6, TB>(G);
+    case 7: return pick_flat_group<7, TB>(G);
+    case 8: return pick_flat_group<8, TB>(G);
+    default: return nullptr;
+  }
+}
+
 typedef void (*StepKernel)(const StepArgs);
 
 template <int P>
@@ -491,6 +647,25 @@ static int choose_group(const meld_b200_graph *g, int P) {
 static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_epi, cudaStream_t stream) {
   const Tuning &t = tuning();
   const int G = choose_group(g, P);
+  if (g->x_mode == 2 && G <= 16) {  // flat kernel (very long rows keep the 32-lane staged kernel)
+    int Gf = t.flat_group > 0 ? t.flat_group : G;
+    if (Gf < P) Gf = 8;
+    const bool wide = t.flat_threads != 768;
+    FlatKernel fk = wide ? pick_flat<1024>(P, Gf) : pick_flat<768>(P, Gf);
+    MELD_REQUIRE(fk != nullptr, "cheby_step: p=%d outside 1..8", P);
+    a.row_ptr = g->row_ptr.p;
+    a.col = g->col.p;
+    a.val = g->val.p;
+    a.row0 = g->row0;
+    int grid = sm_count() * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
+    const int threads = wide ? 1024 : 768;
+    const int64_t groups = ceil_div(g->n_rows, 32 / (Gf <= 4 ? 4 : (Gf <= 8 ? 8 : 16)));
+    if ((int64_t)grid * (threads / 32) > groups) grid = (int)ceil_div(groups, threads / 32);
+    if (grid < 1) grid = 1;
+    fk<<<grid, threads, 0, stream>>>(a, g->n_rows);
+    MELD_LAUNCH_CHECK();
+    return 0;
+  }
   StepKernel k = pick_kernel(P, G);
   MELD_REQUIRE(k != nullptr, "cheby_step: p=%d outside 1..8", P);
   a.row_ptr = g->row_ptr.p;

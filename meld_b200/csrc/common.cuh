@@ -67,7 +67,10 @@ struct Tuning {
   int ctas_per_sm = 1;    // persistent CTAs per SM
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)
   int use_dict = 1;       // 0: every block takes the direct (global-memory) path
-  int x_mode = 0;         // 0: dictionary + cp.async gathers into the stage; 1: staged matrix, direct register gathers
+  int x_mode = 2;         // 0: dictionary + cp.async gathers into the stage; 1: staged matrix, direct register gathers;
+                          // 2: flat kernel (no staging: every warp streams its rows and gathers into registers)
+  int flat_threads = 1024;  // threads per CTA of the flat kernel (1024: <= 64 registers, 768: <= 80)
+  int flat_group = 0;     // lanes per row of the flat kernel (0 = like the staged kernel)
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast

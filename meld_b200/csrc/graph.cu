@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kDictThreads) build_dict_kernel(const int32_t 
     if (tid == 0) dcnt[b] = n == 0 ? 0 : -1;
     return;
   }
-  if (x_mode == 1) {  // staged matrix with direct gathers: no dictionary, the stage holds the int32 columns
+  if (x_mode >= 1) {  // direct gathers (staged matrix or flat kernel): no dictionary
     if (tid == 0) dcnt[b] = 0;
     return;
   }
@@ -301,6 +301,8 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "cluster_cells")) t.cluster_cells = value;
   else if (!strcmp(key, "reg_topk")) t.reg_topk = value;
   else if (!strcmp(key, "prune_proj")) t.prune_proj = value;
+  else if (!strcmp(key, "flat_threads")) t.flat_threads = value;
+  else if (!strcmp(key, "flat_group")) t.flat_group = value;
   else if (!strcmp(key, "tl_interleave")) t.tl_interleave = value;
   else {
     set_error("set_tuning: unknown key '%s'", key);
