@@ -480,11 +480,20 @@ __global__ void __launch_bounds__(TB, 1) cheby_flat_kernel(const StepArgs a, con
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int gid = lane / G, gl = lane % G;
-  const int64_t gw = (int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5);
-  const int64_t nW = (int64_t)gridDim.x * (TB / 32);
-  for (int64_t rb = gw * RPW; rb < n_rows; rb += nW * RPW) {  // warp-uniform
+  // Row groups go to warps round-robin over the whole grid (a.blk == nullptr), or every CTA owns one contiguous
+  // row range holding 1/gridDim of the nonzeros (cut at the row blocks of graph_finalize) and deals its
+  // groups to its own warps: balanced by nonzeros, and a CTA's L1 keeps seeing the same neighbourhood.
+  int64_t rb0 = ((int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5)) * RPW, r_end = n_rows;
+  int64_t rstep = (int64_t)gridDim.x * (TB / 32) * RPW;
+  if (a.blk != nullptr) {
+    const int64_t b0 = ((int64_t)blockIdx.x * a.n_blk) / gridDim.x, b1 = ((int64_t)(blockIdx.x + 1) * a.n_blk) / gridDim.x;
+    rb0 = __ldg(a.blk + b0) + (int64_t)(threadIdx.x >> 5) * RPW;
+    r_end = __ldg(a.blk + b1);
+    rstep = (int64_t)(TB / 32) * RPW;
+  }
+  for (int64_t rb = rb0; rb < r_end; rb += rstep) {  // warp-uniform
     const int64_t r = rb + gid;
-    const bool act = r < n_rows;
+    const bool act = r < r_end;
     int eb = 0, ee = 0;
     if (act) {
       eb = __ldg(a.row_ptr + r);
@@ -657,6 +666,8 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
     a.col = g->col.p;
     a.val = g->val.p;
     a.row0 = g->row0;
+    a.blk = (t.flat_sched == 1 && g->blk.p != nullptr && g->n_blk >= 4 * sm_count()) ? g->blk.p : nullptr;
+    a.n_blk = g->n_blk;
     int grid = sm_count() * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
     const int threads = wide ? 1024 : 768;
     const int64_t groups = ceil_div(g->n_rows, 32 / (Gf <= 4 ? 4 : (Gf <= 8 ? 8 : 16)));

@@ -70,6 +70,7 @@ struct Tuning {
   int x_mode = 2;         // 0: dictionary + cp.async gathers into the stage; 1: staged matrix, direct register gathers;
                           // 2: flat kernel (no staging: every warp streams its rows and gathers into registers)
   int flat_threads = 1024;  // threads per CTA of the flat kernel (1024: <= 64 registers, 768: <= 80)
+  int flat_sched = 1;     // flat kernel: 1 = every CTA owns a contiguous, nonzero-balanced row range; 0 = round-robin
   int flat_group = 0;     // lanes per row of the flat kernel (0 = like the staged kernel)
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
