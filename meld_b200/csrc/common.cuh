@@ -78,10 +78,12 @@ struct Tuning {
   int p1_segments = 0;    // candidate search pass 1 scans this many column segments per row (own first; 0 = all)
   int prune = 1;          // candidate search skips (row tile, column tile) pairs that bounding balls prove too far apart
   int clusters = 64;      // k-means clusters of the internal cell order (0: Morton order only)
-  int kmeans_iters = 2;   // Lloyd iterations after seeding
+  int kmeans_iters = 1;   // Lloyd iterations after seeding
   int reorder_min_n = 4096;  // cells are re-ordered (clusters + Morton curve) from this size on
+  int merge_rows = 1;     // graph assembly places mirrored entries by rank instead of a segmented sort of every row
   int prune_proj = 1;     // tile pruning also uses the projection bound between k-means clusters
   int reg_topk = 1;       // pass 1 keeps its top-k lists in registers (k1 <= 32) instead of shared memory
+  int tl_sort = 0;        // 1: pass-1 tile lists are ordered closest tile first (measured: no gain once insertion is cheap)
   int tl_interleave = 0;  // bit 0 / bit 1: pass 1 / pass 2 chunks of a tile list interleave instead of being contiguous
   int cluster_cells = 1024;  // fewest cells per k-means cluster (fewer clusters for small inputs)
   int prune_window = 2;   // the window pass of the pruned search scans own tile +- this many column tiles

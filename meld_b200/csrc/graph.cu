@@ -301,6 +301,8 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "cluster_cells")) t.cluster_cells = value;
   else if (!strcmp(key, "reg_topk")) t.reg_topk = value;
   else if (!strcmp(key, "prune_proj")) t.prune_proj = value;
+  else if (!strcmp(key, "merge_rows")) t.merge_rows = value;
+  else if (!strcmp(key, "tl_sort")) t.tl_sort = value;
   else if (!strcmp(key, "flat_threads")) t.flat_threads = value;
   else if (!strcmp(key, "flat_group")) t.flat_group = value;
   else if (!strcmp(key, "flat_sched")) t.flat_sched = value;

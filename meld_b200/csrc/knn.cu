@@ -34,7 +34,7 @@
 namespace meld {
 
 // ---- 0. preparation: column means, centred norms -------------------------------------------
-constexpr int kMeanBlocks = 128;
+constexpr int kMeanBlocks = 592;  // 4 per SM; fixed, so the column sums do not depend on the device
 
 __global__ void col_partial_sums_kernel(const double *__restrict__ X, int64_t n, int64_t d, double *partial) {
   // block b sums rows b, b + gridDim.x, ... ; thread t handles columns t, t + blockDim.x, ...
@@ -335,20 +335,44 @@ __global__ void refine_dist_kernel(const double *__restrict__ X, int64_t row_beg
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 31) == 0);
   for (int64_t i = warp; i < n; i += nwarps) {
     // i is a LOCAL row (n = number of local rows); the query point is global row row_begin + i
     const int c = (int)(cptr[i + 1] - cptr[i]);
     const int32_t *ci = cand + cptr[i];
     double *di = d2buf + cptr[i];
     const double *xi = X + (row_begin + i) * d;
-    for (int t = lane; t < c; t += 32) {
-      const double *xj = X + (int64_t)ci[t] * d;
-      double acc = 0.0;
-      for (int64_t k = 0; k < d; ++k) {  // sequential, unfused: the ball tree's rdist order
-        const double diff = __dsub_rn(xi[k], xj[k]);
-        acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+    if (vec4) {
+      // rows are 32-byte aligned (d % 4 == 0): one 256-bit load per four features and lane instead of four
+      // 8-byte ones -- the scalar loop is bound by L1 tag lookups (32 distinct lines per warp instruction)
+      for (int t = lane; t < c; t += 32) {
+        const double *xj = X + (int64_t)ci[t] * d;
+        double acc = 0.0;
+        for (int64_t k = 0; k < d; k += 4) {  // same sequential, unfused order as below
+          double a0, a1, a2, a3, b0, b1, b2, b3;
+          asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(xi + k));
+          asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3) : "l"(xj + k));
+          double diff = __dsub_rn(a0, b0);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          diff = __dsub_rn(a1, b1);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          diff = __dsub_rn(a2, b2);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          diff = __dsub_rn(a3, b3);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+        }
+        di[t] = acc;
       }
-      di[t] = acc;
+    } else {
+      for (int t = lane; t < c; t += 32) {
+        const double *xj = X + (int64_t)ci[t] * d;
+        double acc = 0.0;
+        for (int64_t k = 0; k < d; ++k) {  // sequential, unfused: the ball tree's rdist order
+          const double diff = __dsub_rn(xi[k], xj[k]);
+          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+        }
+        di[t] = acc;
+      }
     }
     __syncwarp();
     if (c < k1) {
@@ -480,6 +504,52 @@ __global__ void fill_sym_kernel(int64_t n, const int32_t *__restrict__ cand, con
       base += __popc(m);
     }
   }
+}
+
+// Rows come out of fill_sym_kernel as [own entries, ascending by column | mirrored entries, any order], all
+// columns of a row distinct.  The final position of an entry is the number of entries of its row with a smaller
+// column: its index among the own entries (a binary search for a mirrored one) plus a count over the few
+// mirrored ones -- one pass over the matrix instead of a segmented sort of all of it.
+__global__ void merge_rows_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ kept,
+                                  const int32_t *__restrict__ ucol, const double *__restrict__ uval,
+                                  int32_t *__restrict__ col, double *__restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int base = row_ptr[i], k = kept[i], x = row_ptr[i + 1] - base - k;
+    const int32_t *own = ucol + base, *ext = ucol + base + k;
+    for (int t = lane; t < k; t += 32) {
+      const int32_t c = own[t];
+      int cnt = 0;
+      for (int e = 0; e < x; ++e) cnt += ext[e] < c ? 1 : 0;
+      col[base + t + cnt] = c;
+      val[base + t + cnt] = uval[base + t];
+    }
+    for (int e = lane; e < x; e += 32) {
+      const int32_t c = ext[e];
+      int cnt = 0;
+      for (int f = 0; f < x; ++f) cnt += ext[f] < c ? 1 : 0;
+      int lo = 0, hi = k;  // own entries below c
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (own[mid] < c)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      col[base + lo + cnt] = c;
+      val[base + lo + cnt] = uval[base + k + e];
+    }
+  }
+}
+
+__global__ void max_int_kernel(const int32_t *__restrict__ a, int64_t n, int32_t *out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t m = 0;
+  for (; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, a[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
 // Compact the un-symmetrised kernel (slot order -> sorted later on the host side of the test).
@@ -639,6 +709,7 @@ using namespace meld;
 // cl = the clusters (cluster id of every position, centroids), left empty when clustering is off.
 static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream, DevBuf<int32_t> &perm,
                       DevBuf<double> &Xp, CellClusters &cl) {
+  StageTimer tm(stream);
   DevBuf<double> partial, var;
   DevBuf<double> &mu = cl.mu;
   DevBuf<int32_t> &cid_sorted = cl.cid;
@@ -657,6 +728,7 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
   MELD_CUDA(cudaMemcpyAsync(h_mu.data(), mu.p, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, stream));
   MELD_CUDA(cudaMemcpyAsync(h_var.data(), var.p, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, stream));
   MELD_CUDA(cudaStreamSynchronize(stream));
+  tm.lap("  order: means + variances");
   std::vector<int> order((size_t)d);
   for (int64_t k = 0; k < d; ++k) order[(size_t)k] = (int)k;
   const int ndim = d < 4 ? (int)d : 4;
@@ -717,6 +789,7 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
     for (int k = 0; k < kKmDims; ++k) h_sel[k] = k < nd ? order[(size_t)k] : 0;
     MELD_CUDA(cudaMemcpyAsync(sel.p, h_sel, sizeof(h_sel), cudaMemcpyHostToDevice, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));  // h_sel is a stack array
+    tm.lap("  order: morton sort");
     kmeans_seed_kernel<<<C, kKmDims, 0, stream>>>(X, n, d, sel.p, nd, mu.p, perm.p, C, cen.p);
     MELD_LAUNCH_CHECK();
     const size_t smem = ((size_t)nd * C + C + kKmDims) * sizeof(float) + kKmDims * sizeof(int);
@@ -742,6 +815,7 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
       kmeans_update_kernel<<<C, kKmDims, 0, stream>>>(kpart.p, seg.p, nd, C, cen.p);
       MELD_LAUNCH_CHECK();
     }
+    tm.lap("  order: k-means");
     cluster_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(keys.p, cid.p, n);
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
@@ -753,10 +827,12 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
     MELD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, idx.p, perm.p, (int)n, 0, 64,
                                               stream));
   }
+  tm.lap("  order: final sort");
   MELD_CHECK(Xp.alloc((size_t)n * d));
   gather_rows_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(X, perm.p, n, d, Xp.p);
   MELD_LAUNCH_CHECK();
   MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
+  tm.lap("  order: gather rows");
   return 0;
 }
 
@@ -1009,7 +1085,8 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
                         const BuildParams &bp, DevBuf<int32_t> &perm, cudaStream_t stream, meld_b200_graph **graph_out) {
   StageTimer tm(stream);
   DevBuf<double> kraw;
-  DevBuf<int32_t> kept, extra, tot;
+  DevBuf<int32_t> kept, extra, tot, max_extra;
+  int32_t h_max_extra = 0;
   MELD_CHECK(kept.alloc((size_t)n));
   MELD_CHECK(extra.alloc((size_t)n));
   MELD_CHECK(tot.alloc((size_t)n + 1));
@@ -1041,6 +1118,11 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
     MELD_CHECK(tmp.alloc(tmp_bytes));
     MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, tot.p, g->row_ptr.p, (int)(n + 1), stream));
     int32_t h_nnz = 0;
+    MELD_CHECK(max_extra.alloc(1));
+    MELD_CUDA(cudaMemsetAsync(max_extra.p, 0, sizeof(int32_t), stream));
+    max_int_kernel<<<296, 256, 0, stream>>>(extra.p, n, max_extra.p);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaMemcpyAsync(&h_max_extra, max_extra.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(&h_nnz, g->row_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));
     if (h_nnz < 0) {
@@ -1063,13 +1145,20 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
     MELD_CHECK(g->val.alloc((size_t)g->nnz + kCsrPad));
     MELD_CUDA(cudaMemsetAsync(g->col.p + g->nnz, 0, kCsrPad * sizeof(int32_t), stream));
     MELD_CUDA(cudaMemsetAsync(g->val.p + g->nnz, 0, kCsrPad * sizeof(double), stream));
-    size_t tmp_bytes = 0;
-    MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p, (int)g->nnz,
-                                                  (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
-    DevBuf<unsigned char> tmp;
-    MELD_CHECK(tmp.alloc(tmp_bytes));
-    MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp.p, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p, (int)g->nnz,
-                                                  (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
+    if (h_max_extra <= 2048 && tuning().merge_rows) {
+      // few mirrored entries per row (the usual case): place every entry by rank
+      merge_rows_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(n, g->row_ptr.p, kept.p, ucol.p, uval.p, g->col.p,
+                                                                g->val.p);
+      MELD_LAUNCH_CHECK();
+    } else {  // a hub row collected thousands of mirrored entries: sort the rows (library plumbing)
+      size_t tmp_bytes = 0;
+      MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p, (int)g->nnz,
+                                                    (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
+      DevBuf<unsigned char> tmp;
+      MELD_CHECK(tmp.alloc(tmp_bytes));
+      MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp.p, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p,
+                                                    (int)g->nnz, (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
+    }
     MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
   }
   tm.lap("kernel values, fill, sort");

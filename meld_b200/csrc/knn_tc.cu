@@ -485,22 +485,45 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const int col0 = ct * BN + chunk * 32;
           if (a.mode == 1) {
             if (mx > thr) {
-#pragma unroll  // static register indices (a dynamic index would spill v to local memory)
-              for (int c = 0; c < 32; ++c) {
-                const float s = __uint_as_float(v[c]);
-                if (KR > 0) {
-                  if (s > thr) {
+              if (KR > 0) {
+                // hit mask first (branch-free), then ONE copy of the insertion code in a loop over the set bits:
+                // the element is picked out of the 32 registers by a 5-level select tree (static indices only).
+                // Fully unrolling 32 insertion networks costs ~1100 instructions per call site and stalls the
+                // epilogue warps on instruction fetch.
+                unsigned m = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[c]) > thr) ? (1u << c) : 0u;
+                while (m) {
+                  const int c = __ffs(m) - 1;
+                  m &= m - 1;
+                  uint32_t t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) t16[i] = (c & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) t8[i] = (c & 2) ? t16[2 * i + 1] : t16[2 * i];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) t4[i] = (c & 4) ? t8[2 * i + 1] : t8[2 * i];
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) t2[i] = (c & 8) ? t4[2 * i + 1] : t4[2 * i];
+                  const float s = __uint_as_float((c & 16) ? t2[1] : t2[0]);
+                  if (s > thr) {  // thr may have risen since the mask was taken
                     topk_insert<KR>(rl, s);
                     thr = fmaxf(thr, rl[KR > 0 ? KR - 1 : 0]);
                   }
-                } else if (s > thr) {
-                  int pos = a.k1 - 1;
-                  while (pos > 0 && lst[(pos - 1) * 2 * BM + lcol] < s) {
-                    lst[pos * 2 * BM + lcol] = lst[(pos - 1) * 2 * BM + lcol];
-                    --pos;
+                }
+              } else {
+#pragma unroll  // static register indices (a dynamic index would spill v to local memory)
+                for (int c = 0; c < 32; ++c) {
+                  const float s = __uint_as_float(v[c]);
+                  if (s > thr) {
+                    int pos = a.k1 - 1;
+                    while (pos > 0 && lst[(pos - 1) * 2 * BM + lcol] < s) {
+                      lst[pos * 2 * BM + lcol] = lst[(pos - 1) * 2 * BM + lcol];
+                      --pos;
+                    }
+                    lst[pos * 2 * BM + lcol] = s;
+                    thr = fmaxf(thr, lst[(a.k1 - 1) * 2 * BM + lcol]);
                   }
-                  lst[pos * 2 * BM + lcol] = s;
-                  thr = fmaxf(thr, lst[(a.k1 - 1) * 2 * BM + lcol]);
                 }
               }
             }
@@ -781,9 +804,15 @@ __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restr
                                                            const int32_t *__restrict__ tile_cl,
                                                            const double *__restrict__ tile_hi, int C, int64_t d,
                                                            int n_tiles, int g0, int kind, int window, int rt_begin,
-                                                           int rt_end,
+                                                           int rt_end, int sort_pow2,
                                                            int32_t *__restrict__ list, int32_t *__restrict__ len,
                                                            unsigned long long *__restrict__ steps) {
+  // sort_pow2 > 0: the kept tiles are re-ordered by their lower bound, closest first (dynamic shared memory:
+  // sort_pow2 float keys + sort_pow2 int tiles).  Pass 1 then meets a row's true neighbours in its first chunk
+  // and the bound it publishes keeps the later chunks off the insertion path.
+  extern __shared__ unsigned char tl_sm[];
+  float *skey = reinterpret_cast<float *>(tl_sm);
+  int *sval = reinterpret_cast<int *>(tl_sm + (size_t)sort_pow2 * sizeof(float));
   __shared__ int s_warp[kTile / 32];
   __shared__ int s_base;
   const int gl = blockIdx.x, g = g0 + gl;
@@ -798,6 +827,7 @@ __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restr
   for (int base = 0; base < n_tiles; base += kTile) {
     const int c = base + tid;
     bool keep = false;
+    float lbf = 0.f;
     if (c < n_tiles) {
       const bool in_window = c >= g - window && c <= g + window;
       if (kind == 0) {
@@ -829,6 +859,7 @@ __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restr
             // rows x of ball a, columns y of ball b: |x - y| >= |ca - cb| - ra - rb
             const double lb = sqrt(acc) * (1.0 - 1e-12) - ra - rb;
             keep = !(lb > rad);  // rad = inf keeps everything
+            lbf = (float)lb;
           }
         }
       }
@@ -838,7 +869,14 @@ __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restr
     __syncthreads();
     int off = s_base;
     for (int w = 0; w < warp; ++w) off += s_warp[w];
-    if (keep) out[off + __popc(m & ((1u << lane) - 1u))] = c;
+    if (keep) {
+      const int pos = off + __popc(m & ((1u << lane) - 1u));
+      out[pos] = c;
+      if (sort_pow2 > 0) {
+        skey[pos] = lbf;
+        sval[pos] = c;
+      }
+    }
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
@@ -846,6 +884,37 @@ __global__ void __launch_bounds__(kTile) tile_lists_kernel(const double *__restr
       s_base += tot;
     }
     __syncthreads();
+  }
+  if (sort_pow2 > 0 && s_base > 1) {  // block-uniform
+    const int nk = s_base;
+    int size = 1;
+    while (size < nk) size <<= 1;
+    for (int i = nk + tid; i < size; i += kTile) {
+      skey[i] = INFINITY;
+      sval[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int k = 2; k <= size; k <<= 1) {  // bitonic sort, ascending by (bound, tile)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < size; i += kTile) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const float ka = skey[i], kb = skey[ixj];
+            const int va = sval[i], vb = sval[ixj];
+            const bool gt = ka > kb || (ka == kb && va > vb);
+            const bool up = (i & k) == 0;
+            if (gt == up) {
+              skey[i] = kb;
+              skey[ixj] = ka;
+              sval[i] = vb;
+              sval[ixj] = va;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < nk; i += kTile) out[i] = sval[i];
   }
   if (tid == 0) {
     len[gl] = s_base;
@@ -1007,10 +1076,19 @@ int tc_tile_lists(const SearchPlan &plan, SearchState &st, int kind, const float
   const int rt_end =
       rt_begin + (int)((plan.row_end == plan.n ? plan.n_pad - plan.row_begin : plan.row_end - plan.row_begin) / BM);
   MELD_CUDA(cudaMemsetAsync(st.tl_steps.p + counter, 0, sizeof(unsigned long long), stream));
-  tile_lists_kernel<<<(unsigned)st.n_groups, kTile, 0, stream>>>(
+  int sort_pow2 = 0;
+  if (kind == 1 && tuning().tl_sort) {
+    sort_pow2 = 1;
+    while (sort_pow2 < st.n_tiles) sort_pow2 <<= 1;
+    if ((size_t)sort_pow2 * 8 > 200 * 1024) sort_pow2 = 0;  // does not fit shared memory: keep the index order
+  }
+  const size_t smem = (size_t)sort_pow2 * 8;
+  if (smem > 48 * 1024)
+    MELD_CUDA(cudaFuncSetAttribute(tile_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tile_lists_kernel<<<(unsigned)st.n_groups, kTile, smem, stream>>>(
       st.ball_c.p, st.ball_rho.p, st.tile_rad.p, st.n_clusters ? st.tile_cl.p : nullptr,
       st.n_clusters ? st.tile_hi.p : nullptr, st.n_clusters, plan.d, (int)st.n_tiles, (int)st.g0, kind, plan.window,
-      rt_begin, rt_end, st.tl_list.p, st.tl_len.p, st.tl_steps.p + counter);
+      rt_begin, rt_end, sort_pow2, st.tl_list.p, st.tl_len.p, st.tl_steps.p + counter);
   MELD_LAUNCH_CHECK();
   out->list = st.tl_list.p;
   out->len = st.tl_len.p;

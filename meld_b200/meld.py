@@ -12,6 +12,8 @@ Chebyshev filter run in libmeld_b200 on the GPU.  There is no CPU path.
 from __future__ import annotations
 
 import numbers
+import os
+import threading
 import time
 
 import numpy as np
@@ -323,7 +325,7 @@ class MELD(object):
         self._indicators = value
 
     # ---- transform --------------------------------------------------------------------------
-    def transform(self, sample_labels):
+    def transform(self, sample_labels, _codes=None):
         """Filter the sample indicators of ``sample_labels`` over the graph.
 
         Returns a DataFrame (N, p) of sample densities, columns = sorted unique labels,
@@ -340,7 +342,8 @@ class MELD(object):
             )
         flat_check = getattr(sample_labels, "values", sample_labels)
         if np.asarray(flat_check).ndim == 1 or np.asarray(flat_check).shape[1] == 1:
-            samples, codes = self._label_codes(sample_labels)
+            # fit_transform factorises the labels on a host thread while the GPU builds the graph
+            samples, codes = _codes if _codes is not None else self._label_codes(sample_labels)
             n_unique = len(samples)
         else:
             samples, codes = None, None
@@ -414,8 +417,34 @@ class MELD(object):
 
     def fit_transform(self, X, sample_labels, **kwargs):
         """Build the graph on ``X`` and estimate the density of each sample in ``sample_labels``."""
-        self.fit(X, **kwargs)
-        return self.transform(sample_labels)
+        # The label codes do not depend on the graph: factorise them on a host thread while the build runs
+        # (the C call releases the GIL).  Any error is left for transform to raise in the reference's order.
+        pre = {}
+
+        def _prefetch():
+            t_thr = time.perf_counter()
+            try:
+                flat = np.asarray(getattr(sample_labels, "values", sample_labels))
+                if flat.ndim == 1 or (flat.ndim == 2 and flat.shape[1] == 1):
+                    pre["codes"] = self._label_codes(sample_labels)
+            except Exception:  # noqa: BLE001 - recomputed (and raised) by transform
+                pre.clear()
+            self.timings_["labels_thread"] = time.perf_counter() - t_thr
+
+        worker = threading.Thread(target=_prefetch, name="meld_b200-labels", daemon=True)
+        if os.environ.get("MELD_B200_NO_LABEL_THREAD"):
+            _prefetch()
+        else:
+            worker.start()
+        t_fit = time.perf_counter()
+        try:
+            self.fit(X, **kwargs)
+        finally:
+            self.timings_["fit_call"] = time.perf_counter() - t_fit
+            if worker.ident is not None:
+                worker.join()
+        self.timings_["fit_and_join"] = time.perf_counter() - t_fit
+        return self.transform(sample_labels, _codes=pre.get("codes"))
 
 
 _HASH_MULT = np.random.default_rng(0x5EED).integers(1, 2**63 - 1, size=64, dtype=np.int64).astype(np.uint64) | np.uint64(1)

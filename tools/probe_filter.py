@@ -41,7 +41,11 @@ def main():
         op.fit(X)
         torch.cuda.synchronize()
         t_fit = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         op.graph.estimate_lmax()
+        torch.cuda.synchronize()
+        t_lmax = time.perf_counter() - t0
         st = op.graph.build_stats()
         nnz = op.graph.nnz
         best = 1e9
@@ -56,7 +60,7 @@ def main():
         print(json.dumps(dict(cfg=c, fit_s=round(t_fit, 3), filter_ms=round(best, 3), us_step=round(best * 1e3 / m, 1),
                               GBs=round(gbs, 1), frac=round(gbs / 6538.6, 3), nnz=nnz, direct=st["direct_blocks"],
                               blocks=st["row_blocks"], dict_per_nnz=round(st["dict_total"] / nnz, 3),
-                              lmax_iters=op.graph.lmax_iters)), flush=True)
+                              lmax_iters=op.graph.lmax_iters, lmax_ms=round(1e3 * t_lmax, 2))), flush=True)
         del op
 
 
