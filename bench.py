@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=None, help="override the number of cells")
     ap.add_argument("--cpu-cells", type=int, default=20000, help="cells in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="replicas", choices=["replicas", "sharded"],
+                    help="N > 1: 'replicas' = every rank runs its own dataset of the config (weak scaling, no data-path "
+                         "collective); 'sharded' = ONE dataset, candidate search sharded by query rows + NCCL all-gather "
+                         "(strong scaling)")
     return ap.parse_args()
 
 
@@ -166,7 +170,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg, n_full), "sample_cells": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,10 +197,13 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = nv.lib()
 
-    # N > 1: ONE job of n cells; the candidate search (the dominant stage) is sharded over the ranks by
-    # query rows, one NCCL all-gather of the candidate lists follows, the rest is replicated: strong scaling
-    Xh, labels, kw, cfg = make_inputs(args, seed_offset=0)
-    if world > 1:
+    # N > 1, default: every rank runs the whole path on ITS OWN dataset of the config (weak scaling; a 500k-cell
+    # job takes ~55 ms on one GPU and does not outgrow it, so there is nothing to exchange -- DESIGN.md section 6).
+    # --multi sharded: ONE dataset, the candidate search sharded over the ranks by query rows, one NCCL
+    # all-gather of the candidate lists, the rest replicated (strong scaling).
+    sharded = world > 1 and args.multi == "sharded"
+    Xh, labels, kw, cfg = make_inputs(args, seed_offset=0 if (sharded or world == 1) else 100 * rank)
+    if sharded:
         kw = dict(kw, distributed=True)
     n, d = Xh.shape
     p = cfg["n_samples"]
@@ -233,14 +240,18 @@ def run_b200(args):
     sampler.start()
     launches0 = lib.meld_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
-    for _ in range(args.steps):
+    marks[0].record()
+    for i in range(args.steps):
         op, out = step_device(events)
+        marks[i + 1].record()  # per-step times for the record (no extra synchronisation)
     e1.record()
     barrier()
     launches = lib.meld_b200_launch_count() - launches0
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
+    step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     nnz = op.graph.nnz
     lmax = op.graph.lmax
     stats = op.graph.build_stats()
@@ -267,19 +278,24 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0]), float(t[1])
-    value = n * args.steps / (ms_total * 1e-3)
-    e2e_value = n * args.steps / (e2e_ms * 1e-3)
+    jobs = 1 if (sharded or world == 1) else world  # replicas: every rank pushed n cells through per step
+    value = jobs * n * args.steps / (ms_total * 1e-3)
+    e2e_value = jobs * n * args.steps / (e2e_ms * 1e-3)
 
     if rank == 0:
         pk, pk_kind = peaks()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "step_ms": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
             "config": {
                 "workload": workload_name(args, cfg, n),
-                "parallelism": "1 GPU" if world == 1 else "query rows of the candidate search sharded x{} + NCCL "
-                               "all-gather of candidate lists; Laplacian assembly and filter replicated".format(world),
+                "parallelism": "1 GPU" if world == 1 else (
+                    "query rows of the candidate search sharded x{} + NCCL all-gather of candidate lists; Laplacian "
+                    "assembly and filter replicated".format(world) if sharded else
+                    "{} independent replicas (one {}-cell dataset per GPU, different seeds), no data-path "
+                    "collective; value = cells of all ranks / max-over-ranks time".format(world, n)),
                 "nnz_L": int(nnz), "nnz_per_row": nnz / n, "lmax": lmax, "candidate_cap": stats["candidate_cap"],
                 "max_candidates": stats["max_candidates"], "search_passes": stats["search_passes"],
                 "row_blocks": stats["row_blocks"], "direct_blocks": stats["direct_blocks"],
@@ -287,8 +303,8 @@ def run_b200(args):
                 "l2_note": "inputs (X {} MB, L {} MB) exceed the 126 MB L2; no explicit flush".format(
                     Xh.nbytes // 2**20, nnz * 12 // 2**20),
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Xh.nbytes + 4 * n),
-                    "d2h_bytes_per_step": int(8 * n * p), "ms_per_step": e2e_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(jobs * (Xh.nbytes + 4 * n)),
+                    "d2h_bytes_per_step": int(jobs * 8 * n * p), "ms_per_step": e2e_ms / args.steps,
                     "host_timings_ms_last_step": {k: round(1e3 * v, 2) for k, v in op_e2e.timings_.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
