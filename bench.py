@@ -57,7 +57,13 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every 200 ms while the timed region runs.
+
+    In-process NVML (one already-open device handle, two cheap queries per sample).  Spawning ``nvidia-smi -lms``
+    beside the timed region -- the first version -- initialises NVML for every GPU of the box and takes driver
+    locks that stalled this process's own cudaMallocAsync / synchronise calls by 30-700 ms at random; a step is
+    ~55 ms, so that distorted the measurement it was meant to vouch for.  ``MELD_BENCH_CLOCKS=smi`` restores the
+    subprocess sampler, ``MELD_BENCH_NO_CLOCKS=1`` disables sampling."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -67,9 +73,44 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.samples = []
+        self.nvml = None
+        self.handle = None
+        if os.environ.get("MELD_BENCH_NO_CLOCKS") or os.environ.get("MELD_BENCH_CLOCKS") == "smi":
+            return
+        try:  # open NVML and the handle BEFORE the timed region
+            import pynvml
+
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.samples.append((sm, reasons))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
 
     def start(self):
         if os.environ.get("MELD_BENCH_NO_CLOCKS"):
+            return
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, name="clock-sampler", daemon=True)
+            self.thread.start()
             return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
@@ -83,6 +124,28 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                     ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                     ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+            fallback = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            reasons = set()
+            for sm, bits in self.samples:
+                for name, attr in names:
+                    mask = int(getattr(nv, attr, fallback[name]))
+                    if bits & mask:
+                        reasons.add(name)
+            if self.samples:
+                out["sm_mhz"] = float(np.median([x[0] for x in self.samples]))
+                out["sm_max_mhz"] = self.max_sm
+                out["samples"] = len(self.samples)
+            out["reasons"] = sorted(reasons)
+            out["sampler"] = "nvml"
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -113,6 +176,7 @@ class ClockSampler:
             out["sm_max_mhz"] = float(max(smax))
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
+        out["sampler"] = "nvidia-smi"
         return out
 
 

@@ -99,13 +99,37 @@ cudaStream_t &current_stream();
 void use_stream(cudaStream_t s);  // also configures the pool on first use
 bool use_pool();                  // MELD_B200_NO_POOL=1 falls back to cudaMalloc / cudaFree (diagnosis)
 
+// Build-scoped temporaries come from ONE library-owned arena instead of the pool: a build allocates ~60 device
+// buffers (4-5 GB at 500k cells), and although the pool keeps its memory, cudaMallocAsync / cudaFreeAsync of
+// such blocks were seen to stall the calling thread by 30-700 ms at random on busy hosts -- an order of magnitude
+// more than the ~45 ms the build's kernels take.  arena_begin() at the top of a build makes DevBuf::alloc a
+// pointer bump; arena_end() resets it (a build ends synchronised, so nothing is still in use).  The first build
+// of a process runs on the pool and records the high-water mark; the arena is sized from it once.  Buffers
+// that outlive the build (everything inside a graph / candidates handle) are `persistent` and stay on the pool.
+void *arena_alloc(size_t bytes);   // nullptr: arena not active or full (caller falls back to the pool)
+bool arena_owns(const void *p);
+void arena_begin(cudaStream_t s);
+void arena_end();
+struct ArenaScope {
+  explicit ArenaScope(cudaStream_t s) { arena_begin(s); }
+  ~ArenaScope() { arena_end(); }
+};
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool persistent = false;
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
+    if (!persistent) {
+      p = static_cast<T *>(arena_alloc(count * sizeof(T)));
+      if (p) {
+        n = count;
+        return 0;
+      }
+    }
     cudaError_t e = use_pool() ? cudaMallocAsync((void **)&p, count * sizeof(T), current_stream())
                                : cudaMalloc((void **)&p, count * sizeof(T));
     if (e != cudaSuccess) {
@@ -118,7 +142,7 @@ struct DevBuf {
     return 0;
   }
   void release() {
-    if (p) {
+    if (p && !arena_owns(p)) {
       if (use_pool())
         cudaFreeAsync(p, current_stream());  // ordered after the kernels already queued on that stream
       else
@@ -129,6 +153,7 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   DevBuf() = default;
+  explicit DevBuf(bool persistent_) : persistent(persistent_) {}
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
 };
@@ -143,30 +168,30 @@ constexpr int kCsrPad = 16;
 struct meld_b200_graph {
   int64_t n_rows = 0, n_cols = 0, row0 = 0, nnz = 0;
   // CSR of L (values f64, columns int32, row pointers int32: nnz < 2^31 per GPU).
-  meld::DevBuf<int32_t> row_ptr;  // n_rows + 1
-  meld::DevBuf<int32_t> col;      // nnz + kCsrPad
-  meld::DevBuf<double> val;       // nnz + kCsrPad
+  meld::DevBuf<int32_t> row_ptr{true};  // n_rows + 1
+  meld::DevBuf<int32_t> col{true};      // nnz + kCsrPad
+  meld::DevBuf<double> val{true};       // nnz + kCsrPad
   // Row-block partition for the TMA-staged SpMM: block b = rows [blk[b], blk[b+1]).
-  meld::DevBuf<int32_t> blk;  // n_blk + 1
+  meld::DevBuf<int32_t> blk{true};  // n_blk + 1
   int32_t n_blk = 0;
   int32_t blk_chunk = 0;  // target nnz per block (C)
   int32_t max_row_nnz = 0;
   // Per-block column dictionaries: dict[b * dict_cap + t] = t-th distinct column of block b,
   // dcnt[b] = their number (-1: block takes the direct path), lidx[e] = position of col[e].
-  meld::DevBuf<int32_t> dict;
-  meld::DevBuf<int32_t> dcnt;
-  meld::DevBuf<uint16_t> lidx;  // nnz + kCsrPad
+  meld::DevBuf<int32_t> dict{true};
+  meld::DevBuf<int32_t> dcnt{true};
+  meld::DevBuf<uint16_t> lidx{true};  // nnz + kCsrPad
   int32_t stage_cap = 0, dict_cap = 0, row_cap = 0, x_mode = 0;
   int64_t dict_total = 0, direct_blocks = 0;  // statistics
   // Cell order used internally (graph row a = caller's cell perm[a]); null = identity.
-  meld::DevBuf<int32_t> perm;
+  meld::DevBuf<int32_t> perm{true};
   // Chebyshev / Lanczos workspace, grown on demand.
-  meld::DevBuf<double> work;
+  meld::DevBuf<double> work{true};
   // Un-symmetrised kNN kernel kept for export (compact CSR, slot order), optional.
-  meld::DevBuf<int64_t> knn_ptr;   // n + 1
-  meld::DevBuf<int32_t> knn_cnt;   // n + 1
-  meld::DevBuf<int32_t> knn_col;   // knn_nnz
-  meld::DevBuf<double> knn_val;    // knn_nnz
+  meld::DevBuf<int64_t> knn_ptr{true};   // n + 1
+  meld::DevBuf<int32_t> knn_cnt{true};   // n + 1
+  meld::DevBuf<int32_t> knn_col{true};   // knn_nnz
+  meld::DevBuf<double> knn_val{true};    // knn_nnz
   int64_t knn_nnz = -1;
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // ms of search pass 1 / pass 2, flops issued by pass 2 / by pass 1, flops of an unpruned pass, reserved

@@ -40,6 +40,70 @@ void use_stream(cudaStream_t s) {
   cudaGetLastError();
 }
 
+// ---- build-scoped arena (see common.cuh) ------------------------------------------------------------------
+namespace {
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, off = 0, need = 0, high = 0;
+  bool active = false;
+  int dev = -1;
+} g_arena;
+constexpr size_t kArenaAlign = 256;
+}  // namespace
+
+void arena_begin(cudaStream_t s) {
+  Arena &a = g_arena;
+  if (a.active || getenv("MELD_B200_NO_ARENA")) return;  // nested / concurrent build: stays on the pool
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (a.base && dev != a.dev) {  // the process switched devices: start over
+    cudaSetDevice(a.dev);
+    cudaFree(a.base);
+    cudaSetDevice(dev);
+    a.base = nullptr;
+    a.cap = a.high = 0;
+  }
+  a.dev = dev;
+  if (a.high > a.cap) {  // grow to the high-water mark of earlier builds (+6 %), outside any timed kernel work
+    cudaStreamSynchronize(s);
+    if (a.base) cudaFree(a.base);
+    a.base = nullptr;
+    const size_t want = a.high + a.high / 16 + (64u << 20);
+    if (cudaMalloc((void **)&a.base, want) == cudaSuccess) {
+      a.cap = want;
+    } else {
+      cudaGetLastError();
+      a.cap = 0;
+    }
+  }
+  a.off = a.need = 0;
+  a.active = true;
+}
+
+void arena_end() {
+  Arena &a = g_arena;
+  if (!a.active) return;
+  if (a.need > a.high) a.high = a.need;
+  a.off = 0;
+  a.active = false;
+}
+
+void *arena_alloc(size_t bytes) {
+  Arena &a = g_arena;
+  if (!a.active) return nullptr;
+  const size_t sz = (bytes + kArenaAlign - 1) / kArenaAlign * kArenaAlign;
+  a.need += sz;
+  if (!a.base || a.off + sz > a.cap) return nullptr;
+  void *p = a.base + a.off;
+  a.off += sz;
+  return p;
+}
+
+bool arena_owns(const void *p) {
+  const Arena &a = g_arena;
+  return a.base && (const char *)p >= a.base && (const char *)p < a.base + a.cap;
+}
+
 int sm_count() {
   static int cached = 0;
   if (cached) return cached;

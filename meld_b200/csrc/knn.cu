@@ -1200,11 +1200,11 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
   tm.lap("anisotropy + laplacian");
   MELD_CHECK(graph_finalize(g, stream));
   tm.lap("finalize (block dictionaries)");
-  if (perm.p) {
-    g->perm.p = perm.p;  // hand the buffer over to the graph
-    g->perm.n = perm.n;
-    perm.p = nullptr;
-    perm.n = 0;
+  if (perm.p) {  // the graph keeps its own copy (perm may live in the build arena)
+    MELD_CHECK(g->perm.alloc(perm.n));
+    MELD_CUDA(cudaMemcpyAsync(g->perm.p, perm.p, perm.n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));
+    perm.release();
   }
   g->stats[2] = total;
   g->stats[4] = bp.simt ? 1 : 0;
@@ -1216,11 +1216,12 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
 // Opaque result of stage 1 for a row range (include/meld_b200.h: meld_b200_cands_t).
 struct meld_b200_cands {
   int64_t n = 0, d = 0, row_begin = 0, row_end = 0, total = 0;
-  meld::DevBuf<int64_t> cptr;  // local rows + 1
-  meld::DevBuf<int32_t> cand;  // total
-  meld::DevBuf<double> d2;     // total
-  meld::DevBuf<double> eps;    // local rows
-  meld::DevBuf<int32_t> perm;  // n, or empty (identity)
+  // persistent: these outlive the call that built them (temporaries of a build live in the arena)
+  meld::DevBuf<int64_t> cptr{true};  // local rows + 1
+  meld::DevBuf<int32_t> cand{true};  // total
+  meld::DevBuf<double> d2{true};     // total
+  meld::DevBuf<double> eps{true};    // local rows
+  meld::DevBuf<int32_t> perm{true};  // n, or empty (identity)
   int32_t max_per_row = 0;
   int passes = 0;
 };
@@ -1232,6 +1233,7 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
                               meld_b200_graph_t **graph_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
   meld::use_stream(stream);
+  meld::ArenaScope arena_scope(stream);
   MELD_REQUIRE(graph_out != nullptr, "knn_graph_build: graph_out is NULL");
   *graph_out = nullptr;
   MELD_REQUIRE(X != nullptr, "knn_graph_build: X is NULL");
@@ -1270,6 +1272,7 @@ int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, dou
                              meld_b200_cands_t **cands_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
   meld::use_stream(stream);
+  meld::ArenaScope arena_scope(stream);
   MELD_REQUIRE(cands_out != nullptr && X != nullptr, "knn_candidates: NULL argument");
   *cands_out = nullptr;
   BuildParams bp;
@@ -1300,14 +1303,12 @@ int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, dou
   c->total = cs.total;
   c->max_per_row = cs.max_per_row;
   c->passes = cs.passes;
-  c->cptr.p = cs.cptr.p;
-  c->cptr.n = cs.cptr.n;
-  cs.cptr.p = nullptr;
-  cs.cptr.n = 0;
-  c->cand.p = cs.cand.p;
-  c->cand.n = cs.cand.n;
-  cs.cand.p = nullptr;
-  cs.cand.n = 0;
+  // the handle keeps its own copies (the search's buffers live in the build arena)
+  MELD_CHECK(c->cptr.alloc(cs.cptr.n));
+  MELD_CHECK(c->cand.alloc(cs.cand.n));
+  MELD_CUDA(cudaMemcpyAsync(c->cptr.p, cs.cptr.p, cs.cptr.n * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+  MELD_CUDA(cudaMemcpyAsync(c->cand.p, cs.cand.p, cs.cand.n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+  MELD_CUDA(cudaStreamSynchronize(stream));
   guard.c = nullptr;
   *cands_out = c;
   return 0;
@@ -1358,6 +1359,7 @@ int meld_b200_graph_from_candidates(int64_t n, const int64_t *counts, const int3
                                     meld_b200_graph_t **graph_out) {
   cudaStream_t stream = (cudaStream_t)stream_;
   meld::use_stream(stream);
+  meld::ArenaScope arena_scope(stream);
   MELD_REQUIRE(graph_out && counts && cand && d2 && eps, "graph_from_candidates: NULL argument");
   *graph_out = nullptr;
   BuildParams bp;
@@ -1405,6 +1407,7 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
                                      int32_t *cnt_out, int64_t *cap_host) {
   cudaStream_t stream = (cudaStream_t)stream_;
   meld::use_stream(stream);
+  meld::ArenaScope arena_scope(stream);
   MELD_REQUIRE(X && key2_out && cnt_out && n >= 2 && d >= 1 && knn >= 1 && knn + 1 <= n && knn + 1 <= kMaxK1,
                "debug_candidate_search: bad argument");
   const double thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
