@@ -703,7 +703,7 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
                    (t.gather_warps * 32) % 8 == 0,
                "cheby_step: bad tuning (threads=%d gather_warps=%d)", threads, t.gather_warps);
   const size_t epi_len = (size_t)a.rows_cap * P + 2;
-  a.x_mode = g->x_mode;
+  a.x_mode = g->x_mode >= 1 ? 1 : 0;  // a flat-kernel graph whose rows are too long for it runs staged + direct gathers
   if (a.x_mode == 1) a.ucap = 0;  // no dictionary / gathered-row area in the stage
   size_t stage = (size_t)a.cap * (a.x_mode == 1 ? 12 : 10) + (size_t)a.rcap * 4 + (size_t)a.ucap * 4 +
                  (size_t)a.ucap * P * 8 + 3 * epi_len * 8;

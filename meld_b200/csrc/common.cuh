@@ -83,6 +83,7 @@ struct Tuning {
   int merge_rows = 1;     // graph assembly places mirrored entries by rank instead of a segmented sort of every row
   int prune_proj = 1;     // tile pruning also uses the projection bound between k-means clusters
   int reg_topk = 1;       // pass 1 keeps its top-k lists in registers (k1 <= 32) instead of shared memory
+  int tl_chunks = 4;      // most units per row tile in a list-driven search pass
   int tl_sort = 0;        // 1: pass-1 tile lists are ordered closest tile first (measured: no gain once insertion is cheap)
   int tl_interleave = 0;  // bit 0 / bit 1: pass 1 / pass 2 chunks of a tile list interleave instead of being contiguous
   int cluster_cells = 1024;  // fewest cells per k-means cluster (fewer clusters for small inputs)

@@ -279,10 +279,12 @@ int graph_finalize(meld_b200_graph *g, cudaStream_t stream) {
   }
   MELD_CUDA(cudaMemcpyAsync(&g->max_row_nnz, mx.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   // block dictionaries
-  MELD_CHECK(g->dict.alloc((size_t)g->n_blk * g->dict_cap));
   MELD_CHECK(g->dcnt.alloc((size_t)g->n_blk));
-  MELD_CHECK(g->lidx.alloc((size_t)g->nnz + kCsrPad));
-  MELD_CUDA(cudaMemsetAsync(g->lidx.p, 0, ((size_t)g->nnz + kCsrPad) * sizeof(uint16_t), stream));
+  if (t.x_mode == 0) {  // only the dictionary-staged kernel reads these
+    MELD_CHECK(g->dict.alloc((size_t)g->n_blk * g->dict_cap));
+    MELD_CHECK(g->lidx.alloc((size_t)g->nnz + kCsrPad));
+    MELD_CUDA(cudaMemsetAsync(g->lidx.p, 0, ((size_t)g->nnz + kCsrPad) * sizeof(uint16_t), stream));
+  }
   build_dict_kernel<<<g->n_blk, kDictThreads, 0, stream>>>(g->row_ptr.p, g->col.p, g->blk.p, g->stage_cap, g->dict_cap,
                                                           g->row_cap + 8, t.use_dict, t.x_mode, g->dict.p, g->dcnt.p, g->lidx.p);
   MELD_LAUNCH_CHECK();
@@ -367,6 +369,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "prune_proj")) t.prune_proj = value;
   else if (!strcmp(key, "merge_rows")) t.merge_rows = value;
   else if (!strcmp(key, "tl_sort")) t.tl_sort = value;
+  else if (!strcmp(key, "tl_chunks")) t.tl_chunks = value;
   else if (!strcmp(key, "flat_threads")) t.flat_threads = value;
   else if (!strcmp(key, "flat_group")) t.flat_group = value;
   else if (!strcmp(key, "flat_sched")) t.flat_sched = value;
