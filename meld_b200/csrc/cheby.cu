@@ -586,6 +586,125 @@ __global__ void __launch_bounds__(TB, 1) cheby_flat_kernel(const StepArgs a, con
   }
 }
 
+// Software-pipelined flat kernel (P <= 4).  In cheby_flat_kernel a warp's work is a serial chain per row group:
+// row pointers -> (values, columns) -> gathers -> next 4 entries ..., three dependent memory latencies during
+// which that warp has no gathers in flight.  Here the row pointers of the NEXT group are requested at the top
+// of the current one, and the columns of the next step (next 4 entries of the row, or the first 4 of the next
+// group) are requested BEFORE the current step's gathers, so a warp goes from gathers to gathers; the values
+// of a step are requested together with its gathers (only the FMAs need them).
+template <int P, int G, int TB>
+__global__ void __launch_bounds__(TB, 1) cheby_flat_pipe_kernel(const StepArgs a, const int64_t n_rows) {
+  static_assert(P <= 4, "pipelined flat kernel: P <= 4");
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gid = lane / G, gl = lane % G;
+  int64_t rb0 = ((int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5)) * RPW, r_end = n_rows;
+  int64_t rstep = (int64_t)gridDim.x * (TB / 32) * RPW;
+  if (a.blk != nullptr) {
+    const int64_t b0 = ((int64_t)blockIdx.x * a.n_blk) / gridDim.x, b1 = ((int64_t)(blockIdx.x + 1) * a.n_blk) / gridDim.x;
+    rb0 = __ldg(a.blk + b0) + (int64_t)(threadIdx.x >> 5) * RPW;
+    r_end = __ldg(a.blk + b1);
+    rstep = (int64_t)(TB / 32) * RPW;
+  }
+  if (rb0 >= r_end) return;  // warp-uniform
+  // prologue: row pointers and first columns of the first group
+  int eb_n = 0, ee_n = 0;
+  if (rb0 + gid < r_end) {
+    eb_n = __ldg(a.row_ptr + rb0 + gid);
+    ee_n = __ldg(a.row_ptr + rb0 + gid + 1);
+  }
+  int cn[4] = {-1, -1, -1, -1};
+  {
+    const int a0 = (eb_n & ~3) + gl * 4;
+    if (a0 < ee_n) ld_stream_c4(a.col + a0, cn);
+  }
+  for (int64_t rb = rb0; rb < r_end; rb += rstep) {  // warp-uniform
+    const int64_t r = rb + gid;
+    const bool act = r < r_end;
+    const int eb = eb_n, ee = ee_n;
+    {  // row pointers of the next group
+      const int64_t rn = r + rstep;
+      eb_n = ee_n = 0;
+      if (rn < r_end) {
+        eb_n = __ldg(a.row_ptr + rn);
+        ee_n = __ldg(a.row_ptr + rn + 1);
+      }
+    }
+    const bool epi = act && gl < P;
+    const size_t li = (size_t)r * P + gl;
+    double tc = 0.0, told = 0.0, rold = 0.0;
+    if (epi) {
+      tc = __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
+      if (a.gamma != 0.0) told = ld_stream(a.Told + li);
+      if (a.R != nullptr && a.r_acc) rold = ld_stream(a.R + li);
+    }
+    double acc[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) acc[k] = 0.0;
+    int a0 = (eb & ~3) + gl * 4;
+    while (true) {  // warp-uniform trip count: the longest row of the group
+      int c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int eu = a0 + u;
+        c[u] = (eu >= eb && eu < ee) ? cn[u] : -1;
+      }
+      // 1. the columns of the next step
+      const int a1 = a0 + 4 * G;
+      const bool more = a1 < ee;
+      const bool any_more = __any_sync(0xffffffffu, more);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cn[u] = -1;
+      if (any_more) {
+        if (more) ld_stream_c4(a.col + a1, cn);
+      } else {
+        const int an = (eb_n & ~3) + gl * 4;  // first step of the next group (its row pointers were requested above)
+        if (an < ee_n) ld_stream_c4(a.col + an, cn);
+      }
+      // 2. this step's gathers and values
+      double x[4][P];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c[u] >= 0) {
+          gather_row<P>(a.Tcur, c[u], x[u]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < P; ++k) x[u][k] = 0.0;
+        }
+      }
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      if (a0 < ee) ld_stream_v4(a.val + a0, v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (c[u] < 0) v[u] = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc[k] = fma(v[u], x[u][k], acc[k]);
+      }
+      if (!any_more) break;
+      a0 = a1;
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < P; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (epi) {
+      double y = acc[0];
+#pragma unroll
+      for (int k = 1; k < P; ++k)
+        if (gl == k) y = acc[k];
+      double tn = a.alpha * (y - a.shift * tc);
+      if (a.gamma != 0.0) tn -= a.gamma * told;
+      if (a.Tnew) a.Tnew[li] = tn;
+      if (a.R) {
+        double rv = a.c * tn + a.c_cur * tc;
+        if (a.r_acc) rv += rold;
+        st_stream(a.R + li, rv);
+      }
+    }
+  }
+}
+
 typedef void (*FlatKernel)(const StepArgs, const int64_t);
 
 template <int P, int TB>
@@ -661,6 +780,14 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
     if (Gf < P) Gf = 8;
     const bool wide = t.flat_threads != 768;
     FlatKernel fk = wide ? pick_flat<1024>(P, Gf) : pick_flat<768>(P, Gf);
+    if ((t.flat_pipe == 1 || (t.flat_pipe == 2 && P == 1)) && P <= 4 && Gf == 8) {
+      switch (P) {
+        case 1: fk = wide ? cheby_flat_pipe_kernel<1, 8, 1024> : cheby_flat_pipe_kernel<1, 8, 768>; break;
+        case 2: fk = wide ? cheby_flat_pipe_kernel<2, 8, 1024> : cheby_flat_pipe_kernel<2, 8, 768>; break;
+        case 3: fk = wide ? cheby_flat_pipe_kernel<3, 8, 1024> : cheby_flat_pipe_kernel<3, 8, 768>; break;
+        default: fk = wide ? cheby_flat_pipe_kernel<4, 8, 1024> : cheby_flat_pipe_kernel<4, 8, 768>; break;
+      }
+    }
     MELD_REQUIRE(fk != nullptr, "cheby_step: p=%d outside 1..8", P);
     a.row_ptr = g->row_ptr.p;
     a.col = g->col.p;

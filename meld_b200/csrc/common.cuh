@@ -70,6 +70,8 @@ struct Tuning {
   int x_mode = 2;         // 0: dictionary + cp.async gathers into the stage; 1: staged matrix, direct register gathers;
                           // 2: flat kernel (no staging: every warp streams its rows and gathers into registers)
   int flat_threads = 1024;  // threads per CTA of the flat kernel (1024: <= 64 registers, 768: <= 80)
+  int flat_pipe = 2;      // software-pipelined flat kernel (8 lanes per row): 0 never, 1 for P <= 4, 2 for P = 1 only
+                          // (measured: 154 us either way at p = 4 -- L1-tag bound; Lanczos p = 1 gains 15 %)
   int flat_sched = 1;     // flat kernel: 1 = every CTA owns a contiguous, nonzero-balanced row range; 0 = round-robin
   int flat_group = 0;     // lanes per row of the flat kernel (0 = like the staged kernel)
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
@@ -83,7 +85,7 @@ struct Tuning {
   int merge_rows = 1;     // graph assembly places mirrored entries by rank instead of a segmented sort of every row
   int prune_proj = 1;     // tile pruning also uses the projection bound between k-means clusters
   int reg_topk = 1;       // pass 1 keeps its top-k lists in registers (k1 <= 32) instead of shared memory
-  int tl_chunks = 4;      // most units per row tile in a list-driven search pass
+  int tl_chunks = 2;      // most units per row tile in a list-driven search pass
   int tl_sort = 0;        // 1: pass-1 tile lists are ordered closest tile first (measured: no gain once insertion is cheap)
   int tl_interleave = 0;  // bit 0 / bit 1: pass 1 / pass 2 chunks of a tile list interleave instead of being contiguous
   int cluster_cells = 1024;  // fewest cells per k-means cluster (fewer clusters for small inputs)

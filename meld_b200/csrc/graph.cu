@@ -373,6 +373,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "flat_threads")) t.flat_threads = value;
   else if (!strcmp(key, "flat_group")) t.flat_group = value;
   else if (!strcmp(key, "flat_sched")) t.flat_sched = value;
+  else if (!strcmp(key, "flat_pipe")) t.flat_pipe = value;
   else if (!strcmp(key, "tl_interleave")) t.tl_interleave = value;
   else {
     set_error("set_tuning: unknown key '%s'", key);

@@ -997,7 +997,7 @@ int tc_plan(int64_t n, int64_t d, int k1, int64_t row_begin, int64_t row_end, Se
     // units per row tile: pruned lists are short (~100 tiles at 500k cells), and every unit pays an A-tile
     // reload and a pipeline refill, so fewer, longer units than the unpruned segment count
     int64_t nchunk = nseg;
-    const int64_t cap = tuning().tl_chunks > 0 ? tuning().tl_chunks : 4;
+    const int64_t cap = tuning().tl_chunks > 0 ? tuning().tl_chunks : 2;
     if (nchunk > cap) nchunk = cap;
     if (nchunk > kMaxLists / 2 - 1) nchunk = kMaxLists / 2 - 1;
     plan->nchunk = (int)nchunk;

@@ -371,7 +371,11 @@ class MELD(object):
         dev = self.graph.device
         d_codes = torch.from_numpy(codes).to(dev, non_blocking=True)
         densities = self.transform_device(d_codes, len(samples))
-        host = densities.cpu().numpy()
+        # pinned staging (torch's caching host allocator): a pageable 16 MB read-back costs ~3x as long
+        staged = torch.empty(densities.shape, dtype=densities.dtype, device="cpu", pin_memory=True)
+        staged.copy_(densities, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        host = staged.numpy()
         self.timings_["transform"] = time.perf_counter() - t0
         self.sample_densities = pd.DataFrame(host, index=self._labels_index, columns=self.samples)
         return self.sample_densities

@@ -12,6 +12,7 @@ from conftest import GOLDEN_CASES, density_parity, load_golden
 pytestmark = pytest.mark.gpu
 
 DEFAULT_X_MODE = 2  # the shipped kernel variant (common.cuh Tuning::x_mode)
+DEFAULT_FLAT_PIPE = 2
 
 RTOL = 1e-5  # north_star tolerance
 TIGHT = 1e-9  # what the fp64 kernel should actually deliver
@@ -207,6 +208,7 @@ def test_api_contract_on_device(mb):
     dict(group=16), dict(group=4), dict(team_warps=6), dict(gather_rows=4, gather_warps=4),
     dict(x_mode=2), dict(x_mode=2, flat_threads=768, flat_group=4), dict(x_mode=2, flat_group=16),  # flat kernel
     dict(x_mode=0),                                        # the dictionary-staged kernel
+    dict(flat_pipe=1), dict(flat_pipe=1, flat_threads=768), dict(flat_pipe=0),  # software-pipelined flat kernel
 ])
 def test_filter_kernel_variants_agree(mb, tuning):
     """Every launch configuration of the Chebyshev kernel computes the same filter (1e-12)."""
@@ -215,7 +217,7 @@ def test_filter_kernel_variants_agree(mb, tuning):
     cheby, _, _ = _oracle()
     defaults = dict(blk_chunk=768, stage_cap=1024, dict_cap=768, row_cap=64, n_stage=0, threads=512, gather_warps=3,
                     team_warps=4, gather_rows=0, ctas_per_sm=1, group=0, use_dict=1, x_mode=DEFAULT_X_MODE, flat_threads=1024,
-                    flat_group=0)
+                    flat_group=0, flat_pipe=DEFAULT_FLAT_PIPE)
     g = load_golden("blobs2k5_wagner")
     S = np.random.default_rng(9).normal(size=(g["L"].shape[0], 4))
     ref = cheby.cheby_filter(g["L"], g["lmax"], S, "heat", beta=60, chebyshev_order=32)
