@@ -802,7 +802,7 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
     for (int it = 0; it <= iters; ++it) {
       kmeans_norms_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, stream>>>(cen.p, nd, C, cn.p);
       MELD_LAUNCH_CHECK();
-      assign<<<sm_count() * 2, 256, smem, stream>>>(X, n, d, sel.p, nd, mu.p, cen.p, cn.p, C, cid.p);
+      assign<<<sm_count() * 8, 256, smem, stream>>>(X, n, d, sel.p, nd, mu.p, cen.p, cn.p, C, cid.p);
       MELD_LAUNCH_CHECK();
       if (it == iters) break;
       // centroid update in a fixed summation order: members sorted by cluster (stable), kKmParts partial sums each

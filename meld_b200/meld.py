@@ -217,19 +217,20 @@ class MELD(object):
             raise NotImplementedError("graph keyword(s) {} are not available in the B200 engine".format(unsupported))
 
     def _reduce_data(self, X):
-        """graphtools ``Data._reduce_data``: randomised PCA when n_pca < min(X.shape) (host sklearn
-        call, shared with the oracle; SURVEY 8a row B')."""
+        """graphtools ``Data._reduce_data``: randomised PCA when n_pca < min(X.shape) (SURVEY 8a row B').
+        Runs on the device (``meld_b200/pca.py``: scikit-learn's randomized-SVD algorithm with the same
+        RandomState draw, so ``data_nu`` equals the reference's to rounding)."""
         n_pca = self.n_pca
         if n_pca is None or n_pca >= min(X.shape):
             return X
         torch = nv.require_cuda()
-        from sklearn.decomposition import PCA
+        from . import pca as _pca
 
         t0 = time.perf_counter()
         self._log("Calculating PCA...")
-        Xh = X.cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(getattr(X, "values", X), dtype=np.float64)
-        self.data_pca = PCA(n_pca, svd_solver="randomized", random_state=self.random_state)
-        out = self.data_pca.fit_transform(Xh)
+        Xd = _as_device_f64(torch, X)
+        out, self.data_pca = _pca.randomized_pca(Xd, n_pca, random_state=self.random_state)
+        torch.cuda.current_stream(out.device).synchronize()
         self.timings_["pca"] = time.perf_counter() - t0
         self._log("Calculated PCA in {:.2f} seconds.".format(self.timings_["pca"]))
         return out

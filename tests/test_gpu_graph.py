@@ -196,3 +196,30 @@ def test_pruned_search_matches_oracle_and_unpruned(mb):
         assert _same_pattern(L, ref)
         assert np.abs(L.data - ref.data).max() <= 1e-10 * np.abs(ref.data).max()
         assert _same_pattern(L, L0) and np.array_equal(L.data, L0.data)
+
+
+def test_device_pca_matches_sklearn(mb):
+    """Row B' on the device: same algorithm and RandomState draw as sklearn's randomized PCA -> same data_nu
+    (1e-9 relative), for N > D and N < D (transposed branch), and fit_transform through it matches the oracle."""
+    import torch
+    from sklearn.decomposition import PCA
+
+    from meld_b200 import pca
+    from oracle import meld as omeld
+
+    for n, D, k, seed in ((3000, 300, 50, 0), (400, 1000, 60, 3)):
+        X, _ = mb.synthetic.make_blobs(n, D, 6, 3, tau=D / 10.0, seed=5)
+        ref = PCA(k, svd_solver="randomized", random_state=seed).fit_transform(X)
+        out, obj = pca.randomized_pca(torch.from_numpy(X).cuda(), k, random_state=seed)
+        assert np.abs(out.cpu().numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
+        assert obj.components_.shape == (k, D)
+    X, labels = mb.synthetic.make_blobs(2500, 400, 5, 3, tau=40.0, seed=11)
+    ref, g, lmax = omeld.fit_transform(X, labels, n_pca=50, random_state=0, knn=7)
+    op = mb.MELD(verbose=0, n_pca=50, random_state=0, knn=7)
+    op.fit(X)
+    L = op.graph.to_scipy_L()
+    assert _same_pattern(L, g["L"])
+    op.graph.lmax = lmax
+    dens = op.transform(labels)
+    normwise, ok = density_parity(dens.values, ref.values, 1e-5)
+    assert ok and normwise < 1e-7, normwise
