@@ -111,11 +111,16 @@ bool use_pool();                  // MELD_B200_NO_POOL=1 falls back to cudaMallo
 // that outlive the build (everything inside a graph / candidates handle) are `persistent` and stay on the pool.
 void *arena_alloc(size_t bytes);   // nullptr: arena not active or full (caller falls back to the pool)
 bool arena_owns(const void *p);
-void arena_begin(cudaStream_t s);
+bool arena_begin(cudaStream_t s);  // false: another build holds the arena (this one stays on the pool)
 void arena_end();
 struct ArenaScope {
-  explicit ArenaScope(cudaStream_t s) { arena_begin(s); }
-  ~ArenaScope() { arena_end(); }
+  bool mine;
+  explicit ArenaScope(cudaStream_t s) : mine(arena_begin(s)) {}
+  ~ArenaScope() {
+    if (mine) arena_end();
+  }
+  ArenaScope(const ArenaScope &) = delete;
+  ArenaScope &operator=(const ArenaScope &) = delete;
 };
 
 template <typename T>

@@ -1,6 +1,8 @@
 // Graph handle management: adopt / export CSR Laplacians, row-block partition.
 #include "common.cuh"
 
+#include <thread>
+
 #include <string.h>
 #include <stdlib.h>
 
@@ -47,13 +49,14 @@ struct Arena {
   size_t cap = 0, off = 0, need = 0, high = 0;
   bool active = false;
   int dev = -1;
+  std::thread::id owner;  // only the thread whose build opened the arena allocates from it
 } g_arena;
 constexpr size_t kArenaAlign = 256;
 }  // namespace
 
-void arena_begin(cudaStream_t s) {
+bool arena_begin(cudaStream_t s) {
   Arena &a = g_arena;
-  if (a.active || getenv("MELD_B200_NO_ARENA")) return;  // nested / concurrent build: stays on the pool
+  if (a.active || getenv("MELD_B200_NO_ARENA")) return false;  // nested / concurrent build: stays on the pool
   int dev = -1;
   cudaGetDevice(&dev);
   if (a.base && dev != a.dev) {  // the process switched devices: start over
@@ -77,7 +80,9 @@ void arena_begin(cudaStream_t s) {
     }
   }
   a.off = a.need = 0;
+  a.owner = std::this_thread::get_id();
   a.active = true;
+  return true;
 }
 
 void arena_end() {
@@ -90,7 +95,7 @@ void arena_end() {
 
 void *arena_alloc(size_t bytes) {
   Arena &a = g_arena;
-  if (!a.active) return nullptr;
+  if (!a.active || a.owner != std::this_thread::get_id()) return nullptr;
   const size_t sz = (bytes + kArenaAlign - 1) / kArenaAlign * kArenaAlign;
   a.need += sz;
   if (!a.base || a.off + sz > a.cap) return nullptr;
