@@ -713,7 +713,8 @@ static FlatKernel pick_flat_group(int G) {
     if (G == 4) return cheby_flat_kernel<P, 4, TB>;
   }
   if (G <= 8) return cheby_flat_kernel<P, 8, TB>;
-  return cheby_flat_kernel<P, 16, TB>;
+  if (G <= 16) return cheby_flat_kernel<P, 16, TB>;
+  return cheby_flat_kernel<P, 32, TB>;
 }
 
 template <int TB>
@@ -775,7 +776,7 @@ static int choose_group(const meld_b200_graph *g, int P) {
 static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_epi, cudaStream_t stream) {
   const Tuning &t = tuning();
   const int G = choose_group(g, P);
-  if (g->x_mode == 2 && G <= 16) {  // flat kernel (very long rows keep the 32-lane staged kernel)
+  if (g->x_mode == 2) {  // flat kernel
     int Gf = t.flat_group > 0 ? t.flat_group : G;
     if (Gf < P) Gf = 8;
     const bool wide = t.flat_threads != 768;
@@ -797,7 +798,7 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
     a.n_blk = g->n_blk;
     int grid = sm_count() * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 1);
     const int threads = wide ? 1024 : 768;
-    const int64_t groups = ceil_div(g->n_rows, 32 / (Gf <= 4 ? 4 : (Gf <= 8 ? 8 : 16)));
+    const int64_t groups = ceil_div(g->n_rows, 32 / (Gf <= 4 ? 4 : (Gf <= 8 ? 8 : (Gf <= 16 ? 16 : 32))));
     if ((int64_t)grid * (threads / 32) > groups) grid = (int)ceil_div(groups, threads / 32);
     if (grid < 1) grid = 1;
     fk<<<grid, threads, 0, stream>>>(a, g->n_rows);

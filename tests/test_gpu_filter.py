@@ -206,7 +206,7 @@ def test_api_contract_on_device(mb):
     dict(use_dict=0),                                      # every block on the direct global-memory path
     dict(blk_chunk=256, stage_cap=512, dict_cap=256, row_cap=16),  # tiny stages: oversize / direct blocks mix in
     dict(group=16), dict(group=4), dict(team_warps=6), dict(gather_rows=4, gather_warps=4),
-    dict(x_mode=2), dict(x_mode=2, flat_threads=768, flat_group=4), dict(x_mode=2, flat_group=16),  # flat kernel
+    dict(x_mode=2), dict(x_mode=2, flat_threads=768, flat_group=4), dict(x_mode=2, flat_group=16), dict(x_mode=2, flat_group=32),  # flat kernel
     dict(x_mode=0),                                        # the dictionary-staged kernel
     dict(flat_pipe=1), dict(flat_pipe=1, flat_threads=768), dict(flat_pipe=0),  # software-pipelined flat kernel
 ])

@@ -21,10 +21,13 @@ def main():
     ap.add_argument("--cells", type=int, default=None)
     ap.add_argument("--configs", default="[{}]")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-pca", action="store_true", help="n_pca=None: build the graph on the raw features")
     args = ap.parse_args()
     cfg = synthetic.CONFIGS[args.config]
     n = args.cells or cfg["N"]
     Xh, labels, kw = synthetic.make_config(args.config, N=n)
+    if args.no_pca:
+        kw = dict(kw, n_pca=None)
     X = torch.from_numpy(Xh).cuda()
     samples, codes = np.unique(labels, return_inverse=True)
     codes = torch.from_numpy(codes.astype(np.int32)).cuda()
