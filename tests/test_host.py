@@ -145,3 +145,23 @@ def test_fast_label_factorize_equals_pandas():
     few = np.array(["x", "y", "x"])
     c1, u1 = _factorize(few)  # short inputs take the generic path
     assert list(c1) == [0, 1, 0] and list(u1) == ["x", "y"]
+
+
+def test_device_pca_algorithm_equals_sklearn_on_cpu_tensors(monkeypatch):
+    """meld_b200/pca.py restates scikit-learn's randomized PCA (same RandomState draw): run on CPU tensors here
+    (the product path only ever hands it CUDA tensors), data_nu must equal sklearn's to rounding."""
+    import torch
+    from sklearn.decomposition import PCA
+
+    from meld_b200 import _native as nv
+    from meld_b200 import pca, synthetic
+
+    monkeypatch.setattr(nv, "require_cuda", lambda: torch)
+    for n, D, k, seed in ((1500, 200, 40, 0), (300, 700, 50, 3), (900, 120, 100, 1)):
+        X, _ = synthetic.make_blobs(n, D, 5, 3, tau=D / 10.0, seed=7)
+        ref = PCA(k, svd_solver="randomized", random_state=seed).fit_transform(X)
+        out, obj = pca.randomized_pca(torch.from_numpy(X), k, random_state=seed)
+        assert np.abs(out.numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
+        assert tuple(obj.components_.shape) == (k, D) and obj.n_components_ == k
+    with pytest.raises(ValueError):
+        pca.randomized_pca(torch.zeros(10, 5, dtype=torch.float64), 6)
