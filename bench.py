@@ -14,6 +14,7 @@ the configuration the metric's roofline target is quoted on; it fits one GPU.  P
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -196,17 +197,26 @@ def workload_name(args, cfg, n):
 
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_leg(args, n_cells, n_jobs):
-    """The reference's CPU path (oracle port: same sklearn / scipy calls) on a bounded sample."""
-    from oracle import meld as omeld  # test infrastructure; allowed here as the timed CPU baseline only
+    """The reference's CPU path (oracle port: same sklearn / scipy calls) on a bounded sample.
+    Returns (cells/s, seconds, nnz(L), per-stage seconds) -- the stages are oracle.meld.fit_transform unrolled."""
+    from oracle import graph as ograph  # test infrastructure; allowed here as the timed CPU baseline only
+    from oracle import meld as omeld
     from meld_b200 import synthetic
 
     cfg = synthetic.CONFIGS[args.config]
     X, labels, kw = synthetic.make_config(args.config, N=n_cells)
+    graph_kw = {k: kw[k] for k in ("knn", "decay", "thresh", "anisotropy") if k in kw}
+    filter_kw = {k: v for k, v in kw.items() if k not in graph_kw}
     t0 = time.perf_counter()
-    dens, g, lmax = omeld.fit_transform(X, labels, n_pca=None if cfg["D"] <= 100 else 100, random_state=0,
-                                        n_jobs=n_jobs, **kw)
-    dt = time.perf_counter() - t0
-    return n_cells / dt, dt, int(g["L"].nnz)
+    g = ograph.build_graph(X, n_pca=None if cfg["D"] <= 100 else 100, random_state=0, n_jobs=n_jobs, **graph_kw)
+    t1 = time.perf_counter()
+    lmax = ograph.estimate_lmax(g["L"], g["dw"])
+    t2 = time.perf_counter()
+    omeld.transform(g["L"], lmax, labels, **filter_kw)
+    t3 = time.perf_counter()
+    dt = t3 - t0
+    stages = {"graph_s": round(t1 - t0, 3), "lmax_s": round(t2 - t1, 3), "filter_s": round(t3 - t2, 3)}
+    return n_cells / dt, dt, int(g["L"].nnz), stages
 
 
 def run_reference(args):
@@ -224,7 +234,7 @@ def run_reference(args):
         cpu_reference_leg(args, n, cores)
     t_all = time.perf_counter()
     for _ in range(args.steps):
-        v, dt, nnz = cpu_reference_leg(args, n, cores)
+        v, dt, nnz, stages = cpu_reference_leg(args, n, cores)
         vals.append((v, dt))
     total = time.perf_counter() - t_all
     value = n * args.steps / total
@@ -236,7 +246,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg, n_full), "sample_cells": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "stages_last_step": stages},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -283,10 +294,18 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    fit_marks = []
+
     def step_device(events=None):
         op = meld_b200.MELD(verbose=0, **kw)
         op.profile_events = events
+        m0 = torch.cuda.Event(enable_timing=True)
+        m1 = torch.cuda.Event(enable_timing=True)
+        m0.record()
         op.fit(X_dev)
+        m1.record()
+        if events is not None:
+            fit_marks.append((m0, m1))
         out = op.transform_device(codes_dev, p)
         return op, out
 
@@ -305,6 +324,8 @@ def run_b200(args):
     launches0 = lib.meld_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    gc.collect()
+    gc.disable()
     e0.record()
     marks[0].record()
     for i in range(args.steps):
@@ -312,6 +333,7 @@ def run_b200(args):
         marks[i + 1].record()  # per-step times for the record (no extra synchronisation)
     e1.record()
     barrier()
+    gc.enable()
     launches = lib.meld_b200_launch_count() - launches0
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
@@ -330,13 +352,19 @@ def run_b200(args):
         step_e2e()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = []
+    gc.collect()
+    gc.disable()  # a generation-2 collection in the middle of a 60 ms step is measurement noise, not the engine
     t_e2e = time.perf_counter()
     f0.record()
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         op_e2e, dens = step_e2e()
+        e2e_steps.append(1e3 * (time.perf_counter() - t_s))  # the DataFrame is on the host when the call returns
     f1.record()
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t_e2e))
+    gc.enable()
 
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -352,7 +380,9 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "step_ms": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
+            "step_ms": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms),
+                        "fit_median": float(np.median([a.elapsed_time(b) for a, b in fit_marks])) if fit_marks else None,
+                        "filter_median": float(np.median(filt_ms)) if filt_ms else None},
             "config": {
                 "workload": workload_name(args, cfg, n),
                 "parallelism": "1 GPU" if world == 1 else (
@@ -369,6 +399,7 @@ def run_b200(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(jobs * (Xh.nbytes + 4 * n)),
                     "d2h_bytes_per_step": int(jobs * 8 * n * p), "ms_per_step": e2e_ms / args.steps,
+                    "step_ms": {"min": min(e2e_steps), "median": float(np.median(e2e_steps)), "max": max(e2e_steps)},
                     "host_timings_ms_last_step": {k: round(1e3 * v, 2) for k, v in op_e2e.timings_.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -398,11 +429,12 @@ def run_b200(args):
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             ncpu = min(args.cpu_cells, n)
-            v, dt, _ = cpu_reference_leg(args, ncpu, cores)
+            v, dt, _, cpu_stages = cpu_reference_leg(args, ncpu, cores)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "oracle port (sklearn ball-tree kNN n_jobs={}, scipy matvecs) fit_transform on a {}-cell "
                           "sample of the same generator, {:.1f} s".format(cores, ncpu, dt),
+                "stages": cpu_stages,
             }
         print(json.dumps(line), flush=True)
     if world > 1:
