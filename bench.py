@@ -404,9 +404,14 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "kernel": "cheby_step_kernel (CSR SpMM + fused three-term update)", "bound": "hbm",
+                "kernel": "cheby_flat_kernel<4,8,1024> (CSR SpMM + fused three-term update; meld_b200_cheby_step)",
+                "bound": "hbm",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "bytes_per_launch": int(bytes_step),
+                "frac": achieved / pk["hbm_gbs"],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+                # kernel on this workload (profiles/r01b_ncu_cheby_flat_c4.txt); other workloads: not captured
+                "traffic": 443832576 if (args.config == "c4" and n == 500000) else None,
+                "bytes_per_launch": int(bytes_step),
                 "us_per_launch": launch_us, "launches_per_step": m,
                 "filter_share_of_step": float(np.mean(filt_ms)) / (ms_total / args.steps),
             },

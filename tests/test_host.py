@@ -165,3 +165,34 @@ def test_device_pca_algorithm_equals_sklearn_on_cpu_tensors(monkeypatch):
         assert tuple(obj.components_.shape) == (k, D) and obj.n_components_ == k
     with pytest.raises(ValueError):
         pca.randomized_pca(torch.zeros(10, 5, dtype=torch.float64), 6)
+
+
+def test_fit_transform_prefetches_label_codes_on_a_thread(monkeypatch):
+    """fit_transform factorises the labels while fit runs and hands the codes to transform; labels it cannot
+    factorise (multi-column) are left for transform to reject with the reference's own error."""
+    import meld_b200
+
+    op = meld_b200.MELD(verbose=0)
+    seen = {}
+    monkeypatch.setattr(op, "fit", lambda X, **kw: op)
+
+    def fake_transform(labels, _codes=None):
+        seen["codes"] = _codes
+        return "ok"
+
+    monkeypatch.setattr(op, "transform", fake_transform)
+    labels = np.array(["b", "a", "b", "c"] * 2000)
+    assert op.fit_transform(np.zeros((8000, 3)), labels) == "ok"
+    samples, codes = seen["codes"]
+    ref_samples, ref_codes = np.unique(labels, return_inverse=True)
+    assert list(samples) == list(ref_samples) and np.array_equal(codes, ref_codes)
+    assert op.timings_["labels_thread"] >= 0
+    op.fit_transform(np.zeros((4, 3)), np.zeros((4, 2)))
+    assert seen["codes"] is None
+
+    def boom(X, **kw):
+        raise RuntimeError("build failed")
+
+    monkeypatch.setattr(op, "fit", boom)
+    with pytest.raises(RuntimeError, match="build failed"):
+        op.fit_transform(np.zeros((8000, 3)), labels)
