@@ -6,22 +6,20 @@
 //             T_k = (2/a1)(L - a2 I) T_{k-1} - T_{k-2}; R += c_k T_k      (a1 = a2 = lmax/2)
 //   estimate_lmax: 1.01 * largest eigenvalue of L.
 //
-// Kernel design (one launch per recurrence term, one persistent 512-thread CTA per SM):
-//   * the matrix is cut into row blocks of ~blk_chunk CSR entries.  graph_finalize gives every
-//     block a dictionary of its distinct columns and rewrites its column indices as 16-bit
-//     positions in that dictionary (neighbouring rows of a kNN graph share most of their
-//     columns once cells are ordered along a space-filling curve);
-//   * warp 0 (one lane) is the TMA producer: per block it bulk-copies values, local indices,
-//     row pointers, the dictionary and the rows' own T_{k-1} / T_{k-2} / R slices into one of
-//     n_stage shared-memory stages (cp.async.bulk + mbarrier complete_tx);
-//   * gather warps wait for a stage's dictionary and pull the P-wide rows of T_{k-1} for the
-//     distinct columns into the stage with cp.async (LDGSTS): no registers are held while the
-//     L2 gathers are in flight and each distinct row is fetched once per block;
-//   * compute warps multiply out of shared memory only (G lanes per row, warp-shuffle
-//     reduction), apply the fused three-term update and R accumulation, and release the stage;
-//   * T_k is written over T_{k-2} (row i of T_{k-2} is only ever read by row i).
-// Blocks that do not fit a stage (a row longer than the stage, too many distinct columns) take
-// the direct path: same arithmetic, operands read straight from global memory.
+// One launch per recurrence term; T_k is written over T_{k-2} (row i of T_{k-2} is only ever read by row i).
+// Three kernel families, selected by Tuning::x_mode (the graph remembers the mode it was finalised for):
+//   x_mode 2 (default)  cheby_flat_kernel / cheby_flat_pipe_kernel: no shared memory, no roles; 32 warps per SM
+//                       walk their own rows (G lanes per row), gather the neighbours' signal rows into registers
+//                       with 256-bit loads and stream values / columns with vectorised evict-first loads.  The
+//                       gather is bound by memory-level parallelism and the L1 tag stage (measured:
+//                       tools/microbench/gather_bench.cu), so staging buys nothing and occupancy everything.
+//   x_mode 0            cheby_step_kernel, dictionary-staged: a persistent 512-thread CTA per SM; warp 0 is a TMA
+//                       producer (cp.async.bulk of values, uint16 dictionary positions, row pointers, the block's
+//                       column dictionary and the rows' own T/R slices into an mbarrier ring), gather warps pull
+//                       the distinct signal rows with cp.async, compute teams multiply out of shared memory.
+//   x_mode 1            cheby_step_kernel with the matrix staged the same way but direct register gathers.
+// The staged kernels were the first design of the round (286 us per launch at 500k cells, the flat kernel 154);
+// they remain as cross-checked variants (tests/test_gpu_filter.py::test_filter_kernel_variants_agree).
 #include "common.cuh"
 
 #include <math.h>

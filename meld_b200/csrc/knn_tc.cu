@@ -1,4 +1,5 @@
-// tcgen05 candidate search: the pairwise-distance contraction on 5th-gen tensor cores.
+// tcgen05 candidate search: the pairwise-distance contraction on 5th-gen tensor cores, restricted to the
+// (row tile, column tile) pairs a one-level ball tree cannot rule out.
 //
 // s_ij = x_i . x_j - n_j/2 for all pairs is one bf16 GEMM  S = A' B'^T  with fp32 accumulation:
 //   A'_i = [ hi(x_i) | hi(x_i) | lo(x_i) | 1 1 1 | 0.. ]      (x = hi + lo, both bf16)
@@ -6,14 +7,17 @@
 // so the epilogue needs ONE compare per element: pass 1 keeps the k1 largest s per row, pass 2
 // appends every column with s >= key2_i.  K' = 3d+3 is padded to a multiple of 64.
 //
-// Kernel: persistent, warp-specialised, one CTA per SM (192 threads):
+// Kernel: persistent, warp-specialised, one CTA per SM (320 threads), 2-CTA clusters sharing B tiles by multicast:
 //   warp 0     TMA producer  (cp.async.bulk.tensor 2-D, 128B swizzle, mbarrier complete_tx)
 //   warp 1     MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16; TMEM alloc)
-//   warps 2-5  epilogue      (tcgen05.ld 32x32b: thread = row, 32 columns per load)
-// A work unit is (128-row tile, column segment).  When K' <= 384 the row tile's A operand stays
-// resident in shared memory for the whole unit and only B tiles stream through a 3-stage ring;
-// otherwise A and B stream together.  The 512 TMEM columns hold two 128x256 fp32 accumulators so
-// the epilogue of tile t overlaps the MMAs of tile t+1.
+//   warps 2-9  epilogue      (tcgen05.ld 32x32b: thread = row, 32 columns per load; two warps per TMEM lane
+//                             quadrant, each scanning half of a tile's columns)
+// A work unit is (128-row tile, chunk of the column-tile list of its 256-row group) -- or, with pruning off,
+// (row tile, column segment).  When K' <= 384 the row tile's A operand stays resident in shared memory for the
+// whole unit and only B tiles stream through a 4-stage ring; otherwise A and B stream together.  The 512 TMEM
+// columns hold two 128x256 fp32 accumulators so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Which tiles are listed: tile_balls_kernel / tile_proj_kernel / tile_lists_kernel below (bounding balls and
+// centroid-axis projections of 256-cell tiles of the k-means + Morton cell order, triangle inequality).
 #include "knn_search.cuh"
 
 #include <cuda.h>
