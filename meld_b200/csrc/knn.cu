@@ -9,8 +9,10 @@
 //   W     = K - diag(K) ;  L = diag(W 1) - W
 //
 // How it is computed here:
-//   1. candidate search in reduced precision (tcgen05 bf16-split GEMM, or the SIMT fp32
-//      cross-check): pass 1 finds an upper bound of eps_i^2, pass 2 emits every j whose
+//   0. cells are re-ordered: k-means cluster first, Morton curve inside a cluster (cell_order), so that
+//      256-cell tiles are compact and the search can skip tile pairs that are provably too far apart;
+//   1. candidate search in reduced precision (tcgen05 bf16-split GEMM over the surviving tile pairs, or
+//      the SIMT fp32 cross-check): pass 1 finds an upper bound of eps_i^2, pass 2 emits every j whose
 //      approximate distance is inside the kernel radius plus a rigorous error margin, so
 //      the candidate set is a superset of the exact neighbourhood;
 //   2. exact float64 distances for the candidates only, summed in the same order as
@@ -18,7 +20,8 @@
 //   3. K_ij and K_ji both follow from d_ij (= d_ji bit for bit), eps_i and eps_j, so the
 //      symmetrised value needs no transpose lookup; entries whose reverse edge is missing
 //      are appended to the other row;
-//   4. rows sorted by column (CUB segmented sort), then anisotropy + Laplacian in place.
+//   4. rows brought into column order by rank (merge_rows_kernel: own entries are already ascending, the
+//      few mirrored ones are placed by counting), then anisotropy + Laplacian in place.
 #include "common.cuh"
 #include "knn_search.cuh"
 
