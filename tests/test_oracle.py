@@ -131,3 +131,34 @@ def test_indicator_errors():
         om.transform(L, 1.0, np.ones((6, 2), dtype=str))
     with pytest.raises(ValueError, match="Found only one unqiue sample label"):
         om.transform(L, 1.0, np.ones(5))
+
+
+def test_tile_pruning_bounds_are_lower_bounds():
+    """The two inequalities the pruned candidate search relies on, restated in numpy and checked by
+    brute force: for cells x of one tile segment and y of another,
+      |x - y| >= |c_R - c_C| - rho_R - rho_C                      (balls around the segments' own centroids)
+      |x - y| >= -max_x p_AB(x) - max_y p_BA(y), p_AB(x) = w.(x - m)   (axis between ANY two centroids A != B)
+    hold for arbitrary centroids -- the k-means clustering is only a heuristic and cannot break exactness."""
+    rng = np.random.default_rng(42)
+    d, C = 12, 5
+    cent = rng.normal(size=(C, d)) * 3.0  # "k-means centroids": any vectors will do
+    pts = [cent[k] + rng.normal(size=(rng.integers(20, 60), d)) * rng.uniform(0.3, 1.5) for k in range(C)]
+    cnorm = (cent ** 2).sum(1)
+    worst_ball = worst_proj = np.inf
+    for A in range(C):
+        for B in range(C):
+            X, Y = pts[A], pts[B]
+            D = np.sqrt(((X[:, None, :] - Y[None, :, :]) ** 2).sum(-1))
+            cR, cC = X.mean(0), Y.mean(0)
+            rhoR = np.sqrt(((X - cR) ** 2).sum(1)).max()
+            rhoC = np.sqrt(((Y - cC) ** 2).sum(1)).max()
+            lb_ball = np.linalg.norm(cR - cC) - rhoR - rhoC
+            worst_ball = min(worst_ball, (D - lb_ball).min())
+            if A != B:
+                dist = np.linalg.norm(cent[B] - cent[A])
+                # the kernel's form: p_AB(x) = (g_B - g_A - (|c_B|^2 - |c_A|^2)/2) / |c_B - c_A|, g_K = c_K . x
+                pAB = (X @ cent[B] - X @ cent[A] - 0.5 * (cnorm[B] - cnorm[A])) / dist
+                pBA = (Y @ cent[A] - Y @ cent[B] - 0.5 * (cnorm[A] - cnorm[B])) / dist
+                lb_proj = -pAB.max() - pBA.max()
+                worst_proj = min(worst_proj, (D - lb_proj).min())
+    assert worst_ball >= -1e-9 and worst_proj >= -1e-9, (worst_ball, worst_proj)
