@@ -156,8 +156,18 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
 int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coeffs_host, int n_coeffs,
                            const double *S, int p, double *R, void *stream);
 
+/* Shared-basis parameter sweep (reference pattern meld/benchmark.py:186-200 and
+ * notebooks/MELD_Quickstart.ipynb:729-747: MELD(beta=b).fit(graph).transform(labels) for hundreds of b on
+ * one graph).  Filters that differ only in their Chebyshev coefficients share the basis T_k(L) S, so the
+ * recurrence runs ONCE: the m+1 terms are kept in library workspace and every filter f gets
+ *   R[f] = c[f][0]/2 T_0 + sum_{k>=1} c[f][k] T_k .
+ * coeffs_host: n_filters x n_coeffs row-major (host).  S: (n, p) f64, p <= 8.  R: n_filters x n x p f64.    */
+int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeffs_host, int n_filters,
+                          int n_coeffs, const double *S, int p, double *R, void *stream);
+
 /* One term of the three-term recurrence on this graph's rows, for callers that
- * exchange T between ranks after each step (row-partitioned multi-GPU):
+ * exchange T between ranks after each step (row-partitioned multi-GPU).  All signal
+ * arrays are in the graph's INTERNAL cell order (meld_b200_graph_permute_signal):
  *   y      = L[rows,:] @ T_cur                       (T_cur: n_cols x p, global rows)
  *   T_new  = alpha * (y - shift * T_cur[row0+i]) - gamma * T_old[i]
  *   R[i]   = (r_scale ? R[i] : 0) + c * T_new[i] + c_cur * T_cur[row0+i]
@@ -166,6 +176,42 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
 int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double *T_old, double *T_new,
                          double *R, int p, double alpha, double shift, double gamma, double c,
                          double c_cur, int r_accumulate, void *stream);
+
+/* Signals between the caller's cell order and the graph's internal one (identity for graphs adopted from
+ * CSR): to_internal = 1: out[a] = in[perm[a]]; 0: out[perm[a]] = in[a].  in / out: (n_cols, p) f64.        */
+int meld_b200_graph_permute_signal(const meld_b200_graph_t *g, const double *in, int p, int to_internal,
+                                   double *out, void *stream);
+
+/* ---- row-partitioned filter over the GPUs of one NVSwitch box ---------------------------------------------
+ * The reference has no distributed code (reference setup.py:45); what is sharded is the recurrence behind
+ * meld/filter.py:59.  One process per GPU.  Rank r owns rows [row_begin_r, row_end_r) of L in the internal
+ * cell order (meld_b200_graph_row_slice of the full graph) and, per term, computes its rows of T_k and stores
+ * them straight into every peer's HBM over NVLink from inside the SpMM kernel (no NCCL call and no host on the
+ * data path); ranks meet through flag words in each other's memory.
+ *   meld_b200_dist_create    allocates this rank's block (flags + two full-length signal buffers)
+ *   meld_b200_dist_export    writes its CUDA IPC handle (meld_b200_dist_handle_bytes() bytes, host)
+ *   meld_b200_dist_connect   maps the blocks of all ranks (world x handle bytes, rank order, host); the
+ *                            caller all-gathers the handles with whatever it has (torch.distributed)
+ * Every rank must issue the same sequence of meld_b200_cheby_filter_dist calls.                             */
+typedef struct meld_b200_dist meld_b200_dist_t;
+int meld_b200_graph_row_slice(const meld_b200_graph_t *g, int64_t row_begin, int64_t row_end, void *stream,
+                              meld_b200_graph_t **slice_out);
+int meld_b200_dist_create(int rank, int world, int64_t n_rows_total, int p_max, void *stream,
+                          meld_b200_dist_t **dist_out);
+int meld_b200_dist_handle_bytes(void);
+int meld_b200_dist_export(const meld_b200_dist_t *d, void *blob_host);
+int meld_b200_dist_connect(meld_b200_dist_t *d, const void *all_blobs_host);
+/* 1 when a flag wait timed out (a peer died or left the call sequence); synchronises the device.           */
+int meld_b200_dist_error(const meld_b200_dist_t *d, int *err_host);
+int meld_b200_dist_destroy(meld_b200_dist_t *d);
+/* meld_b200_cheby_filter on the rows of `slice`: S and R are the FULL (n, p) signals in the caller's order
+ * (every rank passes the same S and receives the same R).                                                   */
+int meld_b200_cheby_filter_dist(meld_b200_graph_t *slice, meld_b200_dist_t *d, double lmax,
+                                const double *coeffs_host, int n_coeffs, const double *S, int p, double *R,
+                                void *stream);
+
+/* Frees the library-owned build arena (several GB after a large build; it is re-grown on the next build).  */
+int meld_b200_release_workspace(void);
 
 /* ---- small fused host-side helpers -------------------------------------------- */
 

@@ -47,6 +47,17 @@ SIGNATURES = {
     "meld_b200_estimate_lmax": (C.c_int, [_vp, _i32, _dbl, _vp, _pdbl, _pint]),
     "meld_b200_cheby_filter": (C.c_int, [_vp, _dbl, _pdbl, _i32, _vp, _i32, _vp, _vp]),
     "meld_b200_cheby_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _dbl, _dbl, _dbl, _dbl, _dbl, _i32, _vp]),
+    "meld_b200_cheby_sweep": (C.c_int, [_vp, _dbl, _pdbl, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "meld_b200_graph_permute_signal": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "meld_b200_graph_row_slice": (C.c_int, [_vp, _i64, _i64, _vp, C.POINTER(_vp)]),
+    "meld_b200_dist_create": (C.c_int, [_i32, _i32, _i64, _i32, _vp, C.POINTER(_vp)]),
+    "meld_b200_dist_handle_bytes": (C.c_int, []),
+    "meld_b200_dist_export": (C.c_int, [_vp, _vp]),
+    "meld_b200_dist_connect": (C.c_int, [_vp, _vp]),
+    "meld_b200_dist_error": (C.c_int, [_vp, _pint]),
+    "meld_b200_dist_destroy": (C.c_int, [_vp]),
+    "meld_b200_cheby_filter_dist": (C.c_int, [_vp, _vp, _dbl, _pdbl, _i32, _vp, _i32, _vp, _vp]),
+    "meld_b200_release_workspace": (C.c_int, []),
     "meld_b200_indicator_matrix": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "meld_b200_l1_normalize_rows": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
 }
@@ -61,6 +72,14 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH):
+        # the library is git-ignored: a fresh checkout builds it on first use when nvcc is there
+        import shutil
+
+        if shutil.which(os.environ.get("NVCC", "nvcc")) and not os.environ.get("MELD_B200_NO_AUTOBUILD"):
+            from . import build as _build
+
+            _build.build(verbose=False)
     if not os.path.exists(LIB_PATH):
         raise NativeError(
             "libmeld_b200.so not found at {}: build it with `python -m meld_b200.build` "

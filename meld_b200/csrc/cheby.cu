@@ -74,6 +74,8 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int kMaxPeers = 7;  // ranks of one NVSwitch box besides this one
+
 struct StepArgs {
   const int32_t *row_ptr;
   const int32_t *col;
@@ -102,6 +104,19 @@ struct StepArgs {
   int gather_cg;   // 1: cp.async.cg (bypass L1) for the gathers
   int stage_epi;   // 1: the T/R arrays are library workspace (padded), slices may be bulk-copied
   int stage_bytes;
+  // flat kernel extras
+  double *dot_partials;        // DOT variant (p = 1): per-CTA partial sums of T_cur[row] * y[row]
+  // row-partitioned multi-GPU step (PEER variant): T_new is also stored into every peer's copy of the buffer
+  // (P2P stores over NVLink) and completion is published through flags in peer memory
+  double *peer_tnew[kMaxPeers];         // peers' T_new slices (already offset to this rank's first row)
+  unsigned long long *peer_flags[kMaxPeers];  // peers' flag slot for THIS rank
+  unsigned long long *my_flags;         // this rank's flag array (one slot per rank), written by the peers
+  unsigned int *done_ctr;               // CTAs of this launch that have finished their stores
+  int *err_flag;                        // set when a flag wait times out
+  int n_peers, world, rank;
+  int store_r;                          // last term: T_new / peer_tnew receive the finished R rows instead of T_k
+  unsigned long long wait_epoch;        // > 0: wait until every peer's flag >= wait_epoch before gathering
+  unsigned long long post_epoch;        // > 0: value published to the peers when this launch's stores are done
 };
 
 // Gather one P-wide signal row straight from global memory (direct path): one 256-bit request per
@@ -162,6 +177,23 @@ __device__ __forceinline__ double ld_stream(const double *p) {  // read-once ope
 }
 __device__ __forceinline__ void st_stream(double *p, double v) {
   asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+
+// block-wide sum (fixed order => deterministic); sh holds 33 doubles
+__device__ __forceinline__ double block_sum_fwd(double v, double *sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (l == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
 }
 
 constexpr int kUnroll = 4;  // independent entries in flight per lane
@@ -703,6 +735,274 @@ __global__ void __launch_bounds__(TB, 1) cheby_flat_pipe_kernel(const StepArgs a
   }
 }
 
+
+// ---- flat kernel, second generation (8 lanes per row) --------------------------------------------------------
+// Same walk as cheby_flat_kernel with compile-time variants:
+//   HINT    cache policy of the operands.  The kernel is bound by the L1TEX pipe (77 % busy at 0.40 of the HBM
+//           roofline, profiles/r01b_ncu_cheby_flat_c4.txt), so what the read-once matrix stream does to the L1
+//           (allocation + fill of 317 MB per launch next to the 16 MB of signal rows worth keeping) matters:
+//           0  values / columns evict-first (ld.cs), gathers default            (= cheby_flat_kernel)
+//           1  values / columns L1::no_allocate, gathers default
+//           2  values / columns and gathers L1::no_allocate
+//           3  values / columns L1::no_allocate, gathers L1::evict_last
+//   LAYOUT  0: a lane takes 4 consecutive entries (one 256-bit + one 128-bit load per lane)
+//           1: the 8 lanes of a row take 8 consecutive entries per step (columns of neighbouring lanes are
+//              neighbours in the sorted row, so gathers of one instruction can share 128-byte lines)
+//   DOT     p = 1 only: per-CTA partial sums of T_cur[row] * y[row] (the Lanczos alpha) -> a.dot_partials
+//   PEER    row-partitioned multi-GPU step: wait for the peers' flags of the previous term, store T_new into
+//           every peer's buffer as well (P2P over NVLink), publish this term's flag when all CTAs are done
+template <int HINT>
+__device__ __forceinline__ void ld_val4_h(const double *p, double (&v)[4]) {
+  if constexpr (HINT == 0)
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p));
+}
+template <int HINT>
+__device__ __forceinline__ void ld_col4_h(const int32_t *p, int (&c)[4]) {
+  if constexpr (HINT == 0)
+    asm volatile("ld.global.cs.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3])
+                 : "l"(p));
+}
+template <int HINT>
+__device__ __forceinline__ double ld_val1_h(const double *p) {
+  double v;
+  if constexpr (HINT == 0)
+    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+template <int HINT>
+__device__ __forceinline__ int ld_col1_h(const int32_t *p) {
+  int v;
+  if constexpr (HINT == 0)
+    asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+template <int HINT>
+__device__ __forceinline__ void ldg256_h(const double *p, double &a, double &b, double &c, double &d) {
+  if constexpr (HINT == 2)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+  else if constexpr (HINT == 3)
+    asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+  else
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+template <int P, int HINT>
+__device__ __forceinline__ void gather_row_h(const double *__restrict__ T, int32_t c, double (&x)[P]) {
+  const double *t = T + (size_t)c * P;
+  if constexpr (P % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < P; k += 4) ldg256_h<HINT>(t + k, x[k], x[k + 1], x[k + 2], x[k + 3]);
+  } else {
+    gather_row<P>(T, c, x);
+  }
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+constexpr unsigned long long kFlagTimeoutNs = 4000000000ull;  // 4 s: a lost peer must not hang the GPU
+
+// Thread 0 of the CTA waits until every rank's slot of my_flags has reached `epoch` (its stores of that
+// phase are visible here), then releases the CTA.  A timeout sets *err_flag and lets the kernel run on.
+__device__ __forceinline__ void peer_wait(const unsigned long long *my_flags, int world, int rank,
+                                          unsigned long long epoch, int *err_flag) {
+  if (epoch == 0) return;
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = global_timer_ns();
+    for (int w = 0; w < world; ++w) {
+      if (w == rank) continue;
+      while (ld_acquire_sys(my_flags + w) < epoch) {
+        if (global_timer_ns() - t0 > kFlagTimeoutNs) {
+          atomicExch(err_flag, 1);
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Called by every thread after its last P2P store.  The last CTA of the launch publishes `epoch` to the
+// peers (fence + counter: all CTAs' stores are ordered before the flag stores).
+__device__ __forceinline__ void peer_post(const StepArgs &a) {
+  if (a.post_epoch == 0) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(a.done_ctr, 1u);
+    if (prev == gridDim.x - 1) {
+      *a.done_ctr = 0;  // the next launch starts after this one has ended
+      __threadfence_system();
+      for (int w = 0; w < a.n_peers; ++w) st_release_sys(a.peer_flags[w], a.post_epoch);
+    }
+  }
+}
+
+template <int P, int TB, int HINT, int LAYOUT, bool DOT, bool PEER>
+__global__ void __launch_bounds__(TB, 1) cheby_flat2_kernel(const StepArgs a, const int64_t n_rows) {
+  static_assert(!DOT || P == 1, "the fused dot product is the Lanczos (p = 1) path");
+  constexpr int G = 8;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gid = lane / G, gl = lane % G;
+  if constexpr (PEER) peer_wait(a.my_flags, a.world, a.rank, a.wait_epoch, a.err_flag);
+  int64_t rb0 = ((int64_t)blockIdx.x * (TB / 32) + (threadIdx.x >> 5)) * RPW, r_end = n_rows;
+  int64_t rstep = (int64_t)gridDim.x * (TB / 32) * RPW;
+  if (a.blk != nullptr) {
+    const int64_t b0 = ((int64_t)blockIdx.x * a.n_blk) / gridDim.x, b1 = ((int64_t)(blockIdx.x + 1) * a.n_blk) / gridDim.x;
+    rb0 = __ldg(a.blk + b0) + (int64_t)(threadIdx.x >> 5) * RPW;
+    r_end = __ldg(a.blk + b1);
+    rstep = (int64_t)(TB / 32) * RPW;
+  }
+  double dot = 0.0;
+  for (int64_t rb = rb0; rb < r_end; rb += rstep) {  // warp-uniform
+    const int64_t r = rb + gid;
+    const bool act = r < r_end;
+    int eb = 0, ee = 0;
+    if (act) {
+      eb = __ldg(a.row_ptr + r);
+      ee = __ldg(a.row_ptr + r + 1);
+    }
+    const bool epi = act && gl < P;
+    const size_t li = (size_t)r * P + gl;
+    double tc = 0.0, told = 0.0, rold = 0.0;
+    if (epi) {  // requested first so their latency overlaps the row product
+      tc = __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
+      if (a.gamma != 0.0) told = ld_stream(a.Told + li);
+      if (a.R != nullptr && a.r_acc) rold = ld_stream(a.R + li);
+    }
+    double acc[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) acc[k] = 0.0;
+    if constexpr (LAYOUT == 0) {
+      for (int a0 = (eb & ~3) + gl * 4; a0 < ee; a0 += 4 * G) {
+        double v[4];
+        int c[4];
+        ld_val4_h<HINT>(a.val + a0, v);
+        ld_col4_h<HINT>(a.col + a0, c);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int eu = a0 + u;
+          if (eu < eb || eu >= ee) {
+            v[u] = 0.0;
+            c[u] = -1;
+          }
+        }
+        constexpr int U = P <= 4 ? 4 : 2;  // gathers in flight per lane
+#pragma unroll
+        for (int h = 0; h < 4; h += U) {
+          double x[U][P];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (c[h + u] >= 0) {
+              gather_row_h<P, HINT>(a.Tcur, c[h + u], x[u]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < P; ++k) x[u][k] = 0.0;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) acc[k] = fma(v[h + u], x[u][k], acc[k]);
+          }
+        }
+      }
+    } else {
+      constexpr int U = P <= 4 ? 4 : 2;
+      for (int a0 = eb + gl; a0 < ee; a0 += U * G) {
+        double v[U];
+        int c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int eu = a0 + u * G;
+          if (eu < ee) {
+            v[u] = ld_val1_h<HINT>(a.val + eu);
+            c[u] = ld_col1_h<HINT>(a.col + eu);
+          } else {
+            v[u] = 0.0;
+            c[u] = -1;
+          }
+        }
+        double x[U][P];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (c[u] >= 0) {
+            gather_row_h<P, HINT>(a.Tcur, c[u], x[u]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < P; ++k) x[u][k] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int k = 0; k < P; ++k) acc[k] = fma(v[u], x[u][k], acc[k]);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < P; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (epi) {
+      double y = acc[0];
+#pragma unroll
+      for (int k = 1; k < P; ++k)
+        if (gl == k) y = acc[k];
+      double tn = a.alpha * (y - a.shift * tc);
+      if (a.gamma != 0.0) tn -= a.gamma * told;
+      if constexpr (DOT) dot = fma(tc, tn, dot);
+      double outv = tn;
+      if (a.R) {
+        double rv = a.c * tn + a.c_cur * tc;
+        if (a.r_acc) rv += rold;
+        st_stream(a.R + li, rv);
+        if constexpr (PEER) {
+          if (a.store_r) outv = rv;
+        }
+      }
+      if (a.Tnew) a.Tnew[li] = outv;  // gathered by the next step: keep cacheable
+      if constexpr (PEER) {
+        if (a.Tnew) {
+#pragma unroll 1
+          for (int w = 0; w < a.n_peers; ++w) a.peer_tnew[w][li] = outv;
+        }
+      }
+    }
+  }
+  if constexpr (DOT) {
+    __shared__ double dot_sh[33];
+    const double s = block_sum_fwd(dot, dot_sh);
+    if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+  }
+  if constexpr (PEER) peer_post(a);
+}
+
 typedef void (*FlatKernel)(const StepArgs, const int64_t);
 
 template <int P, int TB>
@@ -728,6 +1028,57 @@ static FlatKernel pick_flat(int P, int G) {
     case 8: return pick_flat_group<8, TB>(G);
     default: return nullptr;
   }
+}
+
+// ---- dispatch of the second-generation flat kernel -------------------------------------------------------------
+template <int P, int HINT>
+static FlatKernel pick_flat2_layout(int layout) {
+  if constexpr (HINT <= 1) {
+    if (layout == 1) return cheby_flat2_kernel<P, 1024, HINT, 1, false, false>;
+  }
+  return cheby_flat2_kernel<P, 1024, HINT, 0, false, false>;
+}
+template <int P>
+static FlatKernel pick_flat2_hint(int hint, int layout) {
+  switch (hint) {
+    case 1: return pick_flat2_layout<P, 1>(layout);
+    case 2: return pick_flat2_layout<P, 2>(layout);
+    case 3: return pick_flat2_layout<P, 3>(layout);
+    default: return pick_flat2_layout<P, 0>(layout);
+  }
+}
+static FlatKernel pick_flat2(int P, int hint, int layout) {
+  switch (P) {
+    case 1: return pick_flat2_hint<1>(hint, layout);
+    case 2: return pick_flat2_hint<2>(hint, layout);
+    case 3: return pick_flat2_hint<3>(hint, layout);
+    case 4: return pick_flat2_hint<4>(hint, layout);
+    case 5: return pick_flat2_hint<5>(hint, layout);
+    case 6: return pick_flat2_hint<6>(hint, layout);
+    case 7: return pick_flat2_hint<7>(hint, layout);
+    case 8: return pick_flat2_hint<8>(hint, layout);
+    default: return nullptr;
+  }
+}
+template <int HINT>
+static FlatKernel pick_flat2_peer_h(int P) {
+  switch (P) {
+    case 1: return cheby_flat2_kernel<1, 1024, HINT, 0, false, true>;
+    case 2: return cheby_flat2_kernel<2, 1024, HINT, 0, false, true>;
+    case 3: return cheby_flat2_kernel<3, 1024, HINT, 0, false, true>;
+    case 4: return cheby_flat2_kernel<4, 1024, HINT, 0, false, true>;
+    case 5: return cheby_flat2_kernel<5, 1024, HINT, 0, false, true>;
+    case 6: return cheby_flat2_kernel<6, 1024, HINT, 0, false, true>;
+    case 7: return cheby_flat2_kernel<7, 1024, HINT, 0, false, true>;
+    case 8: return cheby_flat2_kernel<8, 1024, HINT, 0, false, true>;
+    default: return nullptr;
+  }
+}
+static FlatKernel pick_flat2_peer(int P, int hint) {
+  return hint >= 1 ? pick_flat2_peer_h<1>(P) : pick_flat2_peer_h<0>(P);
+}
+static FlatKernel pick_flat2_dot(int hint) {
+  return hint >= 1 ? cheby_flat2_kernel<1, 1024, 1, 0, true, false> : cheby_flat2_kernel<1, 1024, 0, 0, true, false>;
 }
 
 typedef void (*StepKernel)(const StepArgs);
@@ -771,9 +1122,32 @@ static int choose_group(const meld_b200_graph *g, int P) {
 
 // stage_epi: the T/R arrays come from library workspace (padded by two doubles), so the rows' own
 // slices may be bulk-copied with 16-byte aligned, even-length requests.
-static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_epi, cudaStream_t stream) {
+static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_epi, cudaStream_t stream,
+                       int *grid_out = nullptr) {
   const Tuning &t = tuning();
   const int G = choose_group(g, P);
+  const bool want_peer = a.n_peers > 0 || a.wait_epoch != 0 || a.post_epoch != 0;
+  const bool want_dot = a.dot_partials != nullptr;
+  if ((g->x_mode == 2 && t.flat_gen == 1) || want_peer || want_dot) {  // second-generation flat kernel (8 lanes per row)
+    FlatKernel fk = want_peer ? pick_flat2_peer(P, t.flat_hint)
+                              : (want_dot ? pick_flat2_dot(t.flat_hint) : pick_flat2(P, t.flat_hint, t.flat_layout));
+    MELD_REQUIRE(fk != nullptr, "cheby_step: p=%d outside 1..8", P);
+    MELD_REQUIRE(!want_dot || P == 1, "cheby_step: the fused dot product needs p = 1");
+    a.row_ptr = g->row_ptr.p;
+    a.col = g->col.p;
+    a.val = g->val.p;
+    a.row0 = g->row0;
+    a.blk = (t.flat_sched == 1 && g->blk.p != nullptr && g->n_blk >= 4 * sm_count()) ? g->blk.p : nullptr;
+    a.n_blk = g->n_blk;
+    int grid = sm_count();
+    const int64_t groups = ceil_div(g->n_rows, 4);
+    if ((int64_t)grid * 32 > groups) grid = (int)ceil_div(groups, 32);
+    if (grid < 1) grid = 1;
+    fk<<<grid, 1024, 0, stream>>>(a, g->n_rows);
+    MELD_LAUNCH_CHECK();
+    if (grid_out) *grid_out = grid;
+    return 0;
+  }
   if (g->x_mode == 2) {  // flat kernel
     int Gf = t.flat_group > 0 ? t.flat_group : G;
     if (Gf < P) Gf = 8;
@@ -875,23 +1249,16 @@ __global__ void permute_rows_kernel(const double *__restrict__ in, const int32_t
 }
 
 // ---- Lanczos helpers ----------------------------------------------------------------
+// Three-term Lanczos on UNNORMALISED vectors w_j = beta_j v_j, two launches per step:
+//   1. y = L w_j with the fused partial sums of w_j . y        (cheby_flat2_kernel<1, ..., DOT>)
+//   2. alpha_j = (w_j . y) / beta_j^2 ;  w_{j+1} = (y - alpha_j w_j) / beta_j - (beta_j / beta_{j-1}) w_{j-1}
+//      written over w_{j-1}; partial sums of |w_{j+1}|^2 = beta_{j+1}^2                  (lanczos_axpy_kernel)
+// All reductions are two-stage with a fixed number of partials (deterministic).  Scalars stay on the device;
+// the host only downloads (alpha, beta) every few steps to test the Ritz residual.
 constexpr int kRedBlocks = 256;  // partial sums per reduction (fixed => deterministic)
 constexpr int kRedThreads = 256;
 
-__device__ __forceinline__ double block_sum(double v, double *sh) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
-  if (w == 0) {
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (l == 0) sh[32] = t;
-  }
-  __syncthreads();
-  return sh[32];
-}
+__device__ __forceinline__ double block_sum(double v, double *sh) { return block_sum_fwd(v, sh); }
 
 __device__ __forceinline__ double sum_partials(const double *partials, double *sh) {
   double v = (threadIdx.x < kRedBlocks) ? partials[threadIdx.x] : 0.0;
@@ -914,81 +1281,92 @@ __global__ void lanczos_init_kernel(double *v, int64_t n, double *partials) {
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
-__global__ void lanczos_scale_kernel(double *v, int64_t n, const double *partials) {
+// pa: partials of w_j . y; pb_cur / pb_prev: partials of |w_j|^2 / |w_{j-1}|^2; pb_next receives |w_{j+1}|^2.
+// w_prev is overwritten with w_{j+1}.
+__global__ void __launch_bounds__(kRedThreads) lanczos_axpy_kernel(const double *__restrict__ y,
+                                                                   const double *__restrict__ w_cur, double *w_prev,
+                                                                   int64_t n, const double *pa, const double *pb_cur,
+                                                                   const double *pb_prev, int j, double *alpha_arr,
+                                                                   double *beta_arr, double *pb_next) {
   __shared__ double sh[33];
-  const double inv = 1.0 / sqrt(sum_partials(partials, sh));
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    v[i] *= inv;
-}
-
-__global__ void dot_partials_kernel(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
-                                    double *partials) {
-  __shared__ double sh[33];
-  double s = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    s = fma(x[i], y[i], s);
-  s = block_sum(s, sh);
-  if (threadIdx.x == 0) partials[blockIdx.x] = s;
-}
-
-// w -= alpha v + beta_j v_prev ; alpha = sum(partials_a) ; partials_b = ||w||^2 pieces
-__global__ void lanczos_update_kernel(double *w, const double *__restrict__ v, const double *__restrict__ vprev,
-                                      int64_t n, const double *partials_a, const double *beta_arr, int j,
-                                      double *alpha_arr, double *partials_b) {
-  __shared__ double sh[33];
-  const double alpha = sum_partials(partials_a, sh);
-  const double beta = beta_arr[j];
-  if (blockIdx.x == 0 && threadIdx.x == 0) alpha_arr[j] = alpha;
+  const double dot = sum_partials(pa, sh);
+  const double b2 = sum_partials(pb_cur, sh);
+  const double bp2 = j > 0 ? sum_partials(pb_prev, sh) : 1.0;
+  const double beta = sqrt(b2), beta_prev = sqrt(bp2);
+  const double alpha = b2 > 0.0 ? dot / b2 : 0.0;
+  const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+  const double ratio = (j > 0 && beta_prev > 0.0) ? beta / beta_prev : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    alpha_arr[j] = alpha;
+    beta_arr[j] = beta;
+  }
   double s = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double x = w[i] - alpha * v[i] - beta * vprev[i];
-    w[i] = x;
+    const double x = (y[i] - alpha * w_cur[i]) * inv - ratio * w_prev[i];
+    w_prev[i] = x;
     s = fma(x, x, s);
   }
   s = block_sum(s, sh);
-  if (threadIdx.x == 0) partials_b[blockIdx.x] = s;
+  if (threadIdx.x == 0) pb_next[blockIdx.x] = s;
 }
 
-// beta_{j+1} = ||w|| ; v_prev = v ; v = w / beta_{j+1}
-__global__ void lanczos_normalize_kernel(const double *__restrict__ w, double *v, double *vprev, int64_t n,
-                                         const double *partials_b, double *beta_arr, int j) {
+// beta_arr[k] = |w_k| for the newest vector (its partials are complete once the axpy of step k-1 has run)
+__global__ void __launch_bounds__(kRedThreads) lanczos_tail_kernel(const double *pb, int k, double *beta_arr) {
   __shared__ double sh[33];
-  const double beta = sqrt(sum_partials(partials_b, sh));
-  if (blockIdx.x == 0 && threadIdx.x == 0) beta_arr[j + 1] = beta;
-  const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    vprev[i] = v[i];
-    v[i] = w[i] * inv;
-  }
+  const double b2 = sum_partials(pb, sh);
+  if (threadIdx.x == 0) beta_arr[k] = sqrt(b2);
 }
 
-// Largest eigenvalue of the symmetric tridiagonal (alpha[0..k), beta[1..k)) by Sturm bisection.
-static double tridiag_lmax(const std::vector<double> &alpha, const std::vector<double> &beta, int k) {
-  double lo = alpha[0], hi = alpha[0];
-  for (int i = 0; i < k; ++i) {
-    const double bl = i > 0 ? fabs(beta[i]) : 0.0, br = i + 1 < k ? fabs(beta[i + 1]) : 0.0;
-    lo = fmin(lo, alpha[i] - bl - br);
-    hi = fmax(hi, alpha[i] + bl + br);
+// All eigenvalues of the symmetric tridiagonal (diag d[0..k), off-diagonal e[0..k-1)) by the implicit QL
+// iteration, together with the LAST component of every normalised eigenvector (what the Ritz residual
+// |beta_k s_last| needs).  d is overwritten with the eigenvalues, zl with those components.
+static bool tridiag_ql_last_row(std::vector<double> &d, std::vector<double> &e, std::vector<double> &zl, int k) {
+  for (int i = 0; i < k; ++i) zl[(size_t)i] = i == k - 1 ? 1.0 : 0.0;
+  if (k == 1) return true;
+  e[(size_t)k - 1] = 0.0;
+  for (int l = 0; l < k; ++l) {
+    int iter = 0, m;
+    do {
+      for (m = l; m < k - 1; ++m) {
+        const double dd = fabs(d[(size_t)m]) + fabs(d[(size_t)m + 1]);
+        if (fabs(e[(size_t)m]) <= 2.3e-16 * dd) break;
+      }
+      if (m != l) {
+        if (++iter > 60) return false;
+        double g = (d[(size_t)l + 1] - d[(size_t)l]) / (2.0 * e[(size_t)l]);
+        double r = hypot(g, 1.0);
+        g = d[(size_t)m] - d[(size_t)l] + e[(size_t)l] / (g + copysign(r, g));
+        double sn = 1.0, cs = 1.0, pp = 0.0;
+        int i;
+        for (i = m - 1; i >= l; --i) {
+          double f = sn * e[(size_t)i];
+          const double b = cs * e[(size_t)i];
+          r = hypot(f, g);
+          e[(size_t)i + 1] = r;
+          if (r == 0.0) {
+            d[(size_t)i + 1] -= pp;
+            e[(size_t)m] = 0.0;
+            break;
+          }
+          sn = f / r;
+          cs = g / r;
+          g = d[(size_t)i + 1] - pp;
+          r = (d[(size_t)i] - g) * sn + 2.0 * cs * b;
+          pp = sn * r;
+          d[(size_t)i + 1] = g + pp;
+          g = cs * r - b;
+          f = zl[(size_t)i + 1];
+          zl[(size_t)i + 1] = sn * zl[(size_t)i] + cs * f;
+          zl[(size_t)i] = cs * zl[(size_t)i] - sn * f;
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[(size_t)l] -= pp;
+        e[(size_t)l] = g;
+        e[(size_t)m] = 0.0;
+      }
+    } while (m != l);
   }
-  auto count_below = [&](double x) {  // number of eigenvalues < x
-    int cnt = 0;
-    double q = alpha[0] - x;
-    if (q < 0) ++cnt;
-    for (int i = 1; i < k; ++i) {
-      if (q == 0.0) q = 1e-300;
-      q = alpha[i] - x - beta[i] * beta[i] / q;
-      if (q < 0) ++cnt;
-    }
-    return cnt;
-  };
-  for (int itn = 0; itn < 200 && hi - lo > 1e-15 * fmax(fabs(hi), fabs(lo)); ++itn) {
-    const double mid = 0.5 * (lo + hi);
-    if (count_below(mid) >= k)
-      hi = mid;  // all eigenvalues below mid
-    else
-      lo = mid;
-  }
-  return 0.5 * (lo + hi);
+  return true;
 }
 
 // ---- signal helpers --------------------------------------------------------------------
@@ -1030,6 +1408,56 @@ __global__ void l1_normalize_rows_kernel(const double *__restrict__ in, int64_t 
   }
 }
 
+// R_f = sum_k C[f][k] T_k for FC filters at a time (the shared-basis parameter sweep): every thread owns one
+// element of the (n, p) signal, walks the stored basis once and keeps FC accumulators; products and sums are
+// rounded separately, in the order of PyGSP's loop (r = c0/2 T0 + c1 T1, r = r + c_k T_k).  Output rows go
+// back to the caller's cell order through perm.
+template <int FC>
+__global__ void __launch_bounds__(256) combine_basis_kernel(const double *__restrict__ T, size_t slot_stride,
+                                                           int n_terms, const double *__restrict__ C, int f0, int nf,
+                                                           const int32_t *__restrict__ perm, int64_t n, int p,
+                                                           double *__restrict__ R) {
+  extern __shared__ double cs[];  // FC x n_terms
+  for (int t = threadIdx.x; t < FC * n_terms; t += blockDim.x) {
+    const int f = t / n_terms, k = t - f * n_terms;
+    cs[t] = f < nf ? C[(size_t)(f0 + f) * n_terms + k] : 0.0;
+  }
+  __syncthreads();
+  const int64_t total = n * p;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    double acc[FC];
+#pragma unroll
+    for (int f = 0; f < FC; ++f) acc[f] = 0.0;
+    for (int k = 0; k < n_terms; ++k) {
+      const double t = T[(size_t)k * slot_stride + e];
+#pragma unroll
+      for (int f = 0; f < FC; ++f) acc[f] = __dadd_rn(acc[f], __dmul_rn(cs[f * n_terms + k], t));
+    }
+    const int64_t i = e / p;
+    const int j = (int)(e - i * p);
+    const int64_t o = perm ? (int64_t)perm[i] : i;
+#pragma unroll
+    for (int f = 0; f < FC; ++f)
+      if (f < nf) R[(size_t)(f0 + f) * total + o * p + j] = acc[f];
+  }
+}
+
+// Last phase of a row-partitioned filter: wait until every peer has stored its rows of R into this rank's
+// buffer, bring the rows back into the caller's cell order, then tell the peers this rank's buffers are free.
+__global__ void __launch_bounds__(256) dist_unpermute_kernel(const StepArgs a, const double *__restrict__ X,
+                                                            const int32_t *__restrict__ perm, int64_t n, int p,
+                                                            double *__restrict__ out) {
+  peer_wait(a.my_flags, a.world, a.rank, a.wait_epoch, a.err_flag);
+  const int64_t total = n * p;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / p;
+    const int j = (int)(t - i * p);
+    const int64_t o = perm ? (int64_t)perm[i] : i;
+    out[o * p + j] = __ldcg(X + t);  // written by peers over NVLink: read through L2
+  }
+  peer_post(a);
+}
+
 static int grid_for(int64_t n, int threads) {
   int64_t b = ceil_div(n > 0 ? n : 1, threads);
   int64_t cap = (int64_t)sm_count() * 8;
@@ -1051,7 +1479,6 @@ int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double
   MELD_REQUIRE(p >= 1 && p <= 8, "cheby_step: p=%d outside 1..8", p);
   MELD_REQUIRE(gamma == 0.0 || T_old != nullptr, "cheby_step: gamma != 0 needs T_old");
   MELD_REQUIRE((const double *)T_new != T_cur, "cheby_step: T_new may not alias T_cur");
-  MELD_REQUIRE(g->perm.p == nullptr, "cheby_step: graph rows are internally reordered; use cheby_filter");
   MELD_REQUIRE(((uintptr_t)T_cur & 31) == 0, "cheby_step: T_cur must be 32-byte aligned");
   StepArgs a{};
   a.Tcur = T_cur;
@@ -1065,6 +1492,17 @@ int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double
   a.c_cur = c_cur;
   a.r_acc = r_accumulate;
   return launch_step(g, a, p, /*stage_epi=*/0, (cudaStream_t)stream_);  // caller arrays: no padded bulk reads
+}
+
+int meld_b200_graph_permute_signal(const meld_b200_graph_t *g, const double *in, int p, int to_internal, double *out,
+                                   void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(g && in && out && p >= 1 && in != out, "graph_permute_signal: bad argument");
+  const int64_t n = g->n_cols;
+  permute_rows_kernel<<<grid_for(n * p, 256), 256, 0, stream>>>(in, g->perm.p, n, p, to_internal ? 0 : 1, out);
+  MELD_LAUNCH_CHECK();
+  return 0;
 }
 
 int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coeffs_host, int n_coeffs, const double *S,
@@ -1121,6 +1559,131 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
   return 0;
 }
 
+static void fill_peer_args(StepArgs &a, const meld_b200_dist *d, int which_buf, int64_t row0, int p) {
+  a.n_peers = 0;
+  for (int w = 0; w < d->world; ++w) {
+    if (w == d->rank) continue;
+    a.peer_tnew[a.n_peers] = d->buf(w, which_buf) + (size_t)row0 * p;
+    a.peer_flags[a.n_peers] = d->flags(w) + d->rank;
+    ++a.n_peers;
+  }
+  a.my_flags = d->flags(d->rank);
+  a.done_ctr = d->ctr();
+  a.err_flag = d->err();
+  a.world = d->world;
+  a.rank = d->rank;
+}
+
+int meld_b200_cheby_filter_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, double lmax, const double *coeffs_host,
+                                int n_coeffs, const double *S, int p, double *R, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(gs && d && coeffs_host && S && R, "cheby_filter_dist: NULL argument");
+  MELD_REQUIRE(d->connected, "cheby_filter_dist: the peer buffers are not connected (meld_b200_dist_connect)");
+  MELD_REQUIRE(n_coeffs >= 2, "cheby_filter_dist: need at least 2 coefficients (got %d)", n_coeffs);
+  MELD_REQUIRE(p >= 1 && p <= d->p_max, "cheby_filter_dist: p=%d outside 1..%d", p, d->p_max);
+  MELD_REQUIRE(lmax > 0.0 && isfinite(lmax), "cheby_filter_dist: lmax=%g", lmax);
+  MELD_REQUIRE(gs->n_cols == d->n, "cheby_filter_dist: graph has %lld columns, context %lld", (long long)gs->n_cols,
+               (long long)d->n);
+  MELD_REQUIRE(S != R, "cheby_filter_dist: R may not alias S");
+  const int64_t n = gs->n_cols, nloc = gs->n_rows, row0 = gs->row0;
+  const size_t lenl = ((size_t)nloc * p + 2 + 3) & ~(size_t)3;
+  MELD_CHECK(ensure_work(gs, lenl));
+  double *Rloc = gs->work.p;
+  const int pgrid = grid_for(n * p, 256);
+  // T_0 = S in graph order, every rank the whole signal (replicated, 8 n p bytes).  The peers finished storing
+  // into this rank's buffers before the previous call returned here (its last phase waited for them).
+  int ci = 0, oi = 1;
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, gs->perm.p, n, p, /*scatter=*/0, d->buf(d->rank, ci));
+  MELD_LAUNCH_CHECK();
+  const double a1 = lmax / 2.0, a2 = lmax / 2.0;
+  const int m = n_coeffs - 1;
+  for (int k = 1; k <= m; ++k) {
+    StepArgs a{};
+    a.Tcur = d->buf(d->rank, ci);
+    a.Told = k >= 2 ? d->buf(d->rank, oi) + (size_t)row0 * p : nullptr;
+    a.Tnew = d->buf(d->rank, oi) + (size_t)row0 * p;  // T_k over T_{k-2}; at k = m the finished rows of R
+    fill_peer_args(a, d, oi, row0, p);
+    a.store_r = k == m;
+    a.R = Rloc;
+    a.alpha = (k == 1 ? 1.0 : 2.0) / a1;
+    a.shift = a2;
+    a.gamma = k >= 2 ? 1.0 : 0.0;
+    a.c = coeffs_host[k];
+    a.c_cur = k == 1 ? 0.5 * coeffs_host[0] : 0.0;
+    a.r_acc = k >= 2;
+    a.wait_epoch = d->epoch;  // the peers' stores of term k-1 (or their release of the buffers) are visible
+    a.post_epoch = ++d->epoch;
+    if (nloc > 0) {
+      MELD_CHECK(launch_step(gs, a, p, 0, stream));
+    } else {  // a rank without rows still takes part in every phase
+      dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, p, nullptr);
+      MELD_LAUNCH_CHECK();
+    }
+    const int t = ci;
+    ci = oi;
+    oi = t;
+  }
+  StepArgs a{};
+  fill_peer_args(a, d, 0, 0, p);
+  a.wait_epoch = d->epoch;
+  a.post_epoch = ++d->epoch;
+  dist_unpermute_kernel<<<pgrid, 256, 0, stream>>>(a, d->buf(d->rank, ci), gs->perm.p, n, p, R);
+  MELD_LAUNCH_CHECK();
+  return 0;
+}
+
+int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeffs_host, int n_filters, int n_coeffs,
+                          const double *S, int p, double *R, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(g && coeffs_host && S && R, "cheby_sweep: NULL argument");
+  MELD_REQUIRE(n_filters >= 1 && n_filters <= 65536, "cheby_sweep: n_filters=%d", n_filters);
+  MELD_REQUIRE(n_coeffs >= 2 && n_coeffs <= 1024, "cheby_sweep: n_coeffs=%d outside 2..1024", n_coeffs);
+  MELD_REQUIRE(p >= 1 && p <= 8, "cheby_sweep: p=%d outside 1..8 (split the signal into column chunks)", p);
+  MELD_REQUIRE(lmax > 0.0 && isfinite(lmax), "cheby_sweep: lmax=%g", lmax);
+  MELD_REQUIRE(g->row0 == 0 && g->n_rows == g->n_cols, "cheby_sweep: needs the full operator");
+  const int64_t n = g->n_rows;
+  // the whole basis T_0 .. T_m is kept (n_coeffs slots of the padded signal) + the coefficient table
+  const size_t len = ((size_t)n * p + 2 + 3) & ~(size_t)3;
+  const size_t ctab = ((size_t)n_filters * n_coeffs + 3) & ~(size_t)3;
+  MELD_CHECK(ensure_work(g, (size_t)n_coeffs * len + ctab));
+  double *T = g->work.p, *Cd = T + (size_t)n_coeffs * len;
+  {
+    std::vector<double> ch((size_t)n_filters * n_coeffs);
+    for (int f = 0; f < n_filters; ++f) {
+      for (int k = 0; k < n_coeffs; ++k) ch[(size_t)f * n_coeffs + k] = coeffs_host[(size_t)f * n_coeffs + k];
+      ch[(size_t)f * n_coeffs] *= 0.5;  // PyGSP uses c_0 / 2
+    }
+    MELD_CUDA(cudaMemcpyAsync(Cd, ch.data(), ch.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));  // ch is a local
+  }
+  const int pgrid = grid_for(n * p, 256);
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, g->perm.p, n, p, /*scatter=*/0, T);  // T_0 = S in graph order
+  MELD_LAUNCH_CHECK();
+  const double a1 = lmax / 2.0, a2 = lmax / 2.0;
+  for (int k = 1; k < n_coeffs; ++k) {
+    StepArgs a{};
+    a.Tcur = T + (size_t)(k - 1) * len;
+    a.Told = k >= 2 ? T + (size_t)(k - 2) * len : nullptr;
+    a.Tnew = T + (size_t)k * len;
+    a.R = nullptr;
+    a.alpha = (k == 1 ? 1.0 : 2.0) / a1;
+    a.shift = a2;
+    a.gamma = k >= 2 ? 1.0 : 0.0;
+    MELD_CHECK(launch_step(g, a, p, 1, stream));
+  }
+  constexpr int FC = 16;
+  const size_t smem = (size_t)FC * n_coeffs * sizeof(double);
+  MELD_CUDA(cudaFuncSetAttribute(combine_basis_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int f0 = 0; f0 < n_filters; f0 += FC) {
+    const int nf = n_filters - f0 < FC ? n_filters - f0 : FC;
+    combine_basis_kernel<FC><<<pgrid, 256, smem, stream>>>(T, len, n_coeffs, Cd, f0, nf, g->perm.p, n, p, R);
+    MELD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol, void *stream_, double *lmax_host,
                             int *iters_host) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1130,65 +1693,81 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
   const int64_t n = g->n_rows;
   if (max_iters <= 0) max_iters = 160;
   if (max_iters > n) max_iters = (int)n;
-  if (rel_tol <= 0) rel_tol = 1e-7;  // the reference asks ARPACK for 5e-3; 1e-7 keeps densities ~1e-8 from the true-lmax ones
+  // Stopping rule: Ritz residual |beta_k s_last| <= rel_tol * theta, a rigorous bound of |lambda - theta| for some
+  // eigenvalue lambda (the actual error of the largest Ritz value is ~residual^2 / gap).  The reference asks ARPACK
+  // for tol = 5e-3; 1e-5 keeps the densities within ~2e-6 of those of the converged lmax (SURVEY finding 6).
+  if (rel_tol <= 0) rel_tol = 1e-5;
   MELD_REQUIRE(n >= 1, "estimate_lmax: empty graph");
   const size_t len = ((size_t)n + 2 + 3) & ~(size_t)3;  // padded like the filter's work arrays
-  const size_t need = 3 * len + 2 * kRedBlocks + 2 * ((size_t)max_iters + 2);
+  const size_t need = 3 * len + 4 * kRedBlocks + 2 * ((size_t)max_iters + 2);
   MELD_CHECK(ensure_work(g, need));
-  double *v = g->work.p, *vprev = v + len, *w = vprev + len;
-  double *pa = w + len, *pb = pa + kRedBlocks;
-  double *d_alpha = pb + kRedBlocks, *d_beta = d_alpha + max_iters + 2;
-  MELD_CUDA(cudaMemsetAsync(vprev, 0, (size_t)n * sizeof(double), stream));
-  MELD_CUDA(cudaMemsetAsync(pa, 0, (2 * kRedBlocks + 2 * ((size_t)max_iters + 2)) * sizeof(double), stream));
-  lanczos_init_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(v, n, pa);
+  double *wa = g->work.p, *wb = wa + len, *y = wb + len;
+  double *pa = y + len, *pb = pa + kRedBlocks;  // pb: three rotating sets of |w_j|^2 partials
+  double *d_alpha = pb + 3 * kRedBlocks, *d_beta = d_alpha + max_iters + 2;
+  MELD_CUDA(cudaMemsetAsync(wb, 0, (size_t)n * sizeof(double), stream));
+  MELD_CUDA(cudaMemsetAsync(pa, 0, (4 * kRedBlocks + 2 * ((size_t)max_iters + 2)) * sizeof(double), stream));
+  lanczos_init_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(wa, n, pb);  // w_0, |w_0|^2 -> pb[0]
   MELD_LAUNCH_CHECK();
-  lanczos_scale_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(v, n, pa);
-  MELD_LAUNCH_CHECK();
-  std::vector<double> alpha((size_t)max_iters + 2), beta((size_t)max_iters + 2);
-  const int chunk = 8;
-  double theta = 0.0, theta_prev = -1.0;
-  int k = 0;
+  std::vector<double> alpha((size_t)max_iters + 2), beta((size_t)max_iters + 2), dd, ee, zl;
+  double theta = 0.0;
+  int k = 0, next_check = max_iters < 8 ? max_iters : 8;
   bool done = false;
+  double *w_cur = wa, *w_prev = wb;
   while (!done && k < max_iters) {
-    const int kend = (k + chunk < max_iters) ? k + chunk : max_iters;
-    for (int j = k; j < kend; ++j) {
-      StepArgs a{};  // w = L v
-      a.Tcur = v;
-      a.Tnew = w;
+    for (int j = k; j < next_check; ++j) {
+      StepArgs a{};  // y = L w_j, partial sums of w_j . y
+      a.Tcur = w_cur;
+      a.Tnew = y;
       a.alpha = 1.0;
+      a.dot_partials = pa;
       MELD_CHECK(launch_step(g, a, 1, 1, stream));
-      dot_partials_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(v, w, n, pa);
+      lanczos_axpy_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(y, w_cur, w_prev, n, pa, pb + (j % 3) * kRedBlocks,
+                                                                  pb + ((j + 2) % 3) * kRedBlocks, j, d_alpha, d_beta,
+                                                                  pb + ((j + 1) % 3) * kRedBlocks);
       MELD_LAUNCH_CHECK();
-      lanczos_update_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(w, v, vprev, n, pa, d_beta, j, d_alpha, pb);
-      MELD_LAUNCH_CHECK();
-      lanczos_normalize_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(w, v, vprev, n, pb, d_beta, j);
-      MELD_LAUNCH_CHECK();
+      double *t = w_cur;  // w_{j+1} was written over w_{j-1}
+      w_cur = w_prev;
+      w_prev = t;
     }
-    k = kend;
-    MELD_CUDA(cudaMemcpyAsync(alpha.data(), d_alpha, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    k = next_check;
+    lanczos_tail_kernel<<<1, kRedThreads, 0, stream>>>(pb + (k % 3) * kRedBlocks, k, d_beta);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaMemcpyAsync(alpha.data(), d_alpha, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(beta.data(), d_beta, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));
+    // T_k: diagonal alpha_0..alpha_{k-1}, off-diagonal beta_1..beta_{k-1}; beta_k couples to the next vector.
     // An exactly invariant Krylov space (beta_j ~ 0) ends the recurrence early.
     int kk = k;
     double scale = 0.0;
-    for (int j = 0; j < k; ++j) scale = fmax(scale, fabs(alpha[j]));
+    for (int j = 0; j < k; ++j) scale = fmax(scale, fabs(alpha[(size_t)j]));
     for (int j = 1; j <= k; ++j) {
-      if (!(beta[j] > 1e-13 * fmax(scale, 1e-300))) {
+      if (!(beta[(size_t)j] > 1e-13 * fmax(scale, 1e-300))) {
         kk = j;
         done = true;
         break;
       }
     }
-    if (kk > k) kk = k;
     for (int j = 0; j < kk; ++j)
-      if (!isfinite(alpha[j])) {
+      if (!isfinite(alpha[(size_t)j])) {
         set_error("estimate_lmax: non-finite Lanczos coefficient at step %d", j);
         return MELD_B200_ERR_INTERNAL;
       }
-    theta = tridiag_lmax(alpha, beta, kk);
-    if (theta_prev >= 0.0 && fabs(theta - theta_prev) <= rel_tol * fabs(theta)) done = true;
-    theta_prev = theta;
+    dd.assign(alpha.begin(), alpha.begin() + kk);
+    ee.assign((size_t)kk, 0.0);
+    for (int j = 0; j + 1 < kk; ++j) ee[(size_t)j] = beta[(size_t)j + 1];
+    zl.assign((size_t)kk, 0.0);
+    if (!tridiag_ql_last_row(dd, ee, zl, kk)) {
+      set_error("estimate_lmax: tridiagonal QL iteration did not converge");
+      return MELD_B200_ERR_INTERNAL;
+    }
+    int top = 0;
+    for (int j = 1; j < kk; ++j)
+      if (dd[(size_t)j] > dd[(size_t)top]) top = j;
+    theta = dd[(size_t)top];
+    const double resid = kk < k ? 0.0 : fabs(beta[(size_t)k] * zl[(size_t)top]);
+    if (resid <= rel_tol * fabs(theta)) done = true;
     if (done) k = kk;
+    next_check = k + 4 < max_iters ? k + 4 : max_iters;
   }
   *lmax_host = 1.01 * theta;
   if (iters_host) *iters_host = k;
@@ -1207,7 +1786,8 @@ int meld_b200_indicator_matrix(const int32_t *codes, int64_t n, int p, int sampl
   MELD_LAUNCH_CHECK();
   fill_indicator_kernel<<<grid_for(n * p, 256), 256, 0, stream>>>(codes, n, p, sample_normalize, cnt.p, S);
   MELD_LAUNCH_CHECK();
-  MELD_CUDA(cudaStreamSynchronize(stream));  // cnt is freed on return
+  // cnt goes back to the pool in stream order (cudaFreeAsync on this stream); only plain cudaFree needs the sync
+  if (!use_pool()) MELD_CUDA(cudaStreamSynchronize(stream));
   return 0;
 }
 

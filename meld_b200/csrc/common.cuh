@@ -74,6 +74,9 @@ struct Tuning {
                           // (measured: 154 us either way at p = 4 -- L1-tag bound; Lanczos p = 1 gains 15 %)
   int flat_sched = 1;     // flat kernel: 1 = every CTA owns a contiguous, nonzero-balanced row range; 0 = round-robin
   int flat_group = 0;     // lanes per row of the flat kernel (0 = like the staged kernel)
+  int flat_gen = 0;       // 1: second-generation flat kernel (cheby_flat2_kernel: cache-hint / layout variants)
+  int flat_hint = 0;      // cheby_flat2_kernel HINT (0..3), see cheby.cu
+  int flat_layout = 0;    // cheby_flat2_kernel LAYOUT (0: 4 consecutive entries per lane, 1: lane-consecutive)
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast
@@ -113,6 +116,7 @@ void *arena_alloc(size_t bytes);   // nullptr: arena not active or full (caller 
 bool arena_owns(const void *p);
 bool arena_begin(cudaStream_t s);  // false: another build holds the arena (this one stays on the pool)
 void arena_end();
+void arena_release();              // frees the block (meld_b200_release_workspace)
 struct ArenaScope {
   bool mine;
   explicit ArenaScope(cudaStream_t s) : mine(arena_begin(s)) {}
@@ -128,6 +132,7 @@ struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   bool persistent = false;
+  cudaStream_t s = nullptr;  // stream the block was allocated on; it is freed on the same one
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
@@ -138,7 +143,8 @@ struct DevBuf {
         return 0;
       }
     }
-    cudaError_t e = use_pool() ? cudaMallocAsync((void **)&p, count * sizeof(T), current_stream())
+    s = current_stream();
+    cudaError_t e = use_pool() ? cudaMallocAsync((void **)&p, count * sizeof(T), s)
                                : cudaMalloc((void **)&p, count * sizeof(T));
     if (e != cudaSuccess) {
       p = nullptr;
@@ -152,7 +158,8 @@ struct DevBuf {
   void release() {
     if (p && !arena_owns(p)) {
       if (use_pool())
-        cudaFreeAsync(p, current_stream());  // ordered after the kernels already queued on that stream
+        cudaFreeAsync(p, s);  // ordered after the kernels queued on the stream the block lives on, whichever
+                              // thread or stream the caller is on by now (graph_destroy also synchronises)
       else
         cudaFree(p);
     }
@@ -204,6 +211,29 @@ struct meld_b200_graph {
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // ms of search pass 1 / pass 2, flops issued by pass 2 / by pass 1, flops of an unpruned pass, reserved
   double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+// Peer-memory context of a row-partitioned filter (include/meld_b200.h: meld_b200_dist_t): one cudaMalloc'd
+// block per rank -- [flags | error word | done counter | two full-length signal buffers] -- exported through
+// CUDA IPC and mapped by every other rank of the box, so a rank's kernels store straight into its peers' HBM
+// over NVLink and publish completion through the peers' flag words.
+struct meld_b200_dist {
+  int rank = 0, world = 1;
+  int64_t n = 0;       // rows of the full operator
+  int p_max = 0;       // widest signal the buffers hold
+  size_t buf_len = 0;  // doubles per signal buffer (padded)
+  size_t bytes = 0;
+  char *base = nullptr;              // this rank's block
+  char *peer_base[8] = {nullptr};    // mapped blocks of all ranks ([rank] = base)
+  unsigned long long epoch = 0;      // last phase published (identical on every rank: same call sequence)
+  bool connected = false;
+  static constexpr size_t kFlagsOff = 0, kErrOff = 512, kCtrOff = 576, kBufOff = 1024;
+  unsigned long long *flags(int r) const { return reinterpret_cast<unsigned long long *>(peer_base[r] + kFlagsOff); }
+  int *err() const { return reinterpret_cast<int *>(base + kErrOff); }
+  unsigned int *ctr() const { return reinterpret_cast<unsigned int *>(base + kCtrOff); }
+  double *buf(int r, int which) const {
+    return reinterpret_cast<double *>(peer_base[r] + kBufOff) + (size_t)which * buf_len;
+  }
 };
 
 namespace meld {

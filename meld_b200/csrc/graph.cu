@@ -1,6 +1,7 @@
 // Graph handle management: adopt / export CSR Laplacians, row-block partition.
 #include "common.cuh"
 
+#include <atomic>
 #include <thread>
 
 #include <string.h>
@@ -47,7 +48,7 @@ namespace {
 struct Arena {
   char *base = nullptr;
   size_t cap = 0, off = 0, need = 0, high = 0;
-  bool active = false;
+  std::atomic<bool> active{false};  // claimed with a compare-exchange: ctypes drops the GIL around every call
   int dev = -1;
   std::thread::id owner;  // only the thread whose build opened the arena allocates from it
 } g_arena;
@@ -56,7 +57,10 @@ constexpr size_t kArenaAlign = 256;
 
 bool arena_begin(cudaStream_t s) {
   Arena &a = g_arena;
-  if (a.active || getenv("MELD_B200_NO_ARENA")) return false;  // nested / concurrent build: stays on the pool
+  if (getenv("MELD_B200_NO_ARENA")) return false;
+  bool expected = false;
+  if (!a.active.compare_exchange_strong(expected, true)) return false;  // nested / concurrent build: stays on the pool
+  a.owner = std::this_thread::get_id();
   int dev = -1;
   cudaGetDevice(&dev);
   if (a.base && dev != a.dev) {  // the process switched devices: start over
@@ -80,22 +84,21 @@ bool arena_begin(cudaStream_t s) {
     }
   }
   a.off = a.need = 0;
-  a.owner = std::this_thread::get_id();
-  a.active = true;
   return true;
 }
 
 void arena_end() {
   Arena &a = g_arena;
-  if (!a.active) return;
+  if (!a.active.load() || a.owner != std::this_thread::get_id()) return;  // only the build that claimed it
   if (a.need > a.high) a.high = a.need;
   a.off = 0;
-  a.active = false;
+  a.owner = std::thread::id();  // no thread matches between two builds
+  a.active.store(false);
 }
 
 void *arena_alloc(size_t bytes) {
   Arena &a = g_arena;
-  if (!a.active || a.owner != std::this_thread::get_id()) return nullptr;
+  if (!a.active.load() || a.owner != std::this_thread::get_id()) return nullptr;
   const size_t sz = (bytes + kArenaAlign - 1) / kArenaAlign * kArenaAlign;
   a.need += sz;
   if (!a.base || a.off + sz > a.cap) return nullptr;
@@ -107,6 +110,23 @@ void *arena_alloc(size_t bytes) {
 bool arena_owns(const void *p) {
   const Arena &a = g_arena;
   return a.base && (const char *)p >= a.base && (const char *)p < a.base + a.cap;
+}
+
+void arena_release() {
+  Arena &a = g_arena;
+  bool expected = false;
+  if (!a.active.compare_exchange_strong(expected, true)) return;  // a build is running: nothing to free now
+  if (a.base) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (a.dev >= 0 && dev != a.dev) cudaSetDevice(a.dev);
+    cudaDeviceSynchronize();
+    cudaFree(a.base);
+    if (a.dev >= 0 && dev != a.dev) cudaSetDevice(dev);
+  }
+  a.base = nullptr;
+  a.cap = a.off = 0;  // `high` stays: the next build re-grows the arena in one step
+  a.active.store(false);
 }
 
 int sm_count() {
@@ -324,7 +344,12 @@ using namespace meld;
 
 extern "C" {
 
-int meld_b200_version(void) { return 100; /* 0.1.0 */ }
+int meld_b200_version(void) { return 200; /* 0.2.0 */ }
+
+int meld_b200_release_workspace(void) {
+  meld::arena_release();
+  return 0;
+}
 
 int64_t meld_b200_launch_count(void) { return (int64_t)g_launches; }
 
@@ -379,6 +404,9 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "flat_group")) t.flat_group = value;
   else if (!strcmp(key, "flat_sched")) t.flat_sched = value;
   else if (!strcmp(key, "flat_pipe")) t.flat_pipe = value;
+  else if (!strcmp(key, "flat_gen")) t.flat_gen = value;
+  else if (!strcmp(key, "flat_hint")) t.flat_hint = value;
+  else if (!strcmp(key, "flat_layout")) t.flat_layout = value;
   else if (!strcmp(key, "tl_interleave")) t.tl_interleave = value;
   else {
     set_error("set_tuning: unknown key '%s'", key);

@@ -729,8 +729,10 @@ __global__ void __launch_bounds__(kTile) tile_proj_kernel(const double *__restri
     double acc[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+    double zn = 0.0;  // |z|^2 over the selected features (scales the rounding bound of the projections)
 #pragma unroll
     for (int j = 0; j < kKmDims / 32; ++j) {
+      zn = fma(z[j], z[j], zn);
       if (j * 32 < nd) {
         const int lim = min(32, nd - j * 32);
         for (int l = 0; l < lim; ++l) {
@@ -741,6 +743,8 @@ __global__ void __launch_bounds__(kTile) tile_proj_kernel(const double *__restri
         }
       }
     }
+    for (int o = 16; o > 0; o >>= 1) zn += __shfl_xor_sync(0xffffffffu, zn, o);
+    zn = sqrt(zn);
     double gA = 0.0;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
@@ -752,9 +756,14 @@ __global__ void __launch_bounds__(kTile) tile_proj_kernel(const double *__restri
     for (int c = 0; c < CPL; ++c) {
       const int B = lane + 32 * c;
       const double D = cl_dist[(size_t)A * C + B];
-      double pr = (acc[c] - gA - 0.5 * (cl_norm[B] - nA)) / D;
+      const double nB = cl_norm[B];
+      double pr = (acc[c] - gA - 0.5 * (nB - nA)) / D;
+      // Rounding of the numerator is ~(nd + 2) u (|z| (|cA| + |cB|) + |cA|^2 + |cB|^2), amplified by 1 / D: the
+      // stored maximum is an UPPER bound of the projection, so the bound is added here (8x safety) instead
+      // of relying on a slack proportional to |pr| at the point of use.
+      pr += 8.0 * (double)(nd + 2) * 1.1102230246251565e-16 * (zn * (sqrt(nA) + sqrt(nB)) + nA + nB) / D;
       // (nearly) coincident centroids: the quotient amplifies rounding -> no bound for this pair
-      if (B == A || !(D > 1e-6 * (sqrt(nA) + sqrt(cl_norm[B]) + 1.0)) || !(pr == pr)) pr = INFINITY;
+      if (B == A || !(D > 1e-3 * (sqrt(nA) + sqrt(nB) + 1.0)) || !(pr == pr)) pr = INFINITY;
       if (sgm == 0)
         hm[0][c] = fmax(hm[0][c], pr);
       else

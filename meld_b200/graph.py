@@ -48,8 +48,7 @@ class DeviceGraph:
         if X.dim() != 2:
             raise ValueError("Expected a 2D matrix. Got shape {}".format(tuple(X.shape)))
         N, d = X.shape
-        if knn + 1 > N:
-            raise ValueError("knn + 1 = {} exceeds the number of cells {}".format(knn + 1, N))
+        knn = _clamp_knn(knn, N)
         flags = (nv.FLAG_KEEP_KNN_KERNEL if keep_knn_kernel else 0) | (nv.FLAG_SIMT_SEARCH if simt_search else 0)
         out = C.c_void_p()
         nv.check(
@@ -149,8 +148,7 @@ class DeviceGraph:
 
         X = _as_device_f64(torch, data_nu)
         N, d = X.shape
-        if knn + 1 > N:
-            raise ValueError("knn + 1 = {} exceeds the number of cells {}".format(knn + 1, N))
+        knn = _clamp_knn(knn, N)
         bounds = cls.shard_bounds(N, world)
         lap("input to device")
         counts, cand, d2, eps, perm = cls.candidates(X, bounds[rank], bounds[rank + 1], knn, decay, thresh,
@@ -324,6 +322,19 @@ class DeviceGraph:
         self.__dict__.update(g.__dict__)
         g._h = C.c_void_p(0)
         self._lmax = st["lmax"]
+
+
+def _clamp_knn(knn, N):
+    """graphtools ``kNNGraph.__init__``: knn above n_samples - 2 is clamped with a warning, not an error."""
+    if knn > N - 2:
+        import warnings
+
+        warnings.warn("Cannot set knn ({k}) to be greater than  n_samples - 2 ({n}). Setting knn={n}".format(
+            k=knn, n=N - 2))
+        knn = N - 2
+    if knn < 1:
+        raise ValueError("Expected at least 3 cells to build a kNN graph, got {}".format(N))
+    return int(knn)
 
 
 def _as_device_f64(torch, x):

@@ -253,8 +253,11 @@ class MELD(object):
             raise NotImplementedError("sample_idx (MNN graphs) is not available in the B200 engine")
         extra.pop("use_pygsp", None)
         self._check_supported(extra)
-        if self.graph is not None and self.X is not None and _same_data(torch, X, self.X):
-            return self  # same data, same parameters: keep the graph (set_params drops it otherwise)
+        build_key = (self.knn, self.decay, self.thresh, self.anisotropy, self.n_pca, self.random_state, self.distributed,
+                     tuple(sorted(extra.items())))
+        if (self.graph is not None and self.X is not None and getattr(self, "_build_key", None) == build_key
+                and _same_data(torch, X, self.X)):
+            return self  # same data AND same effective build parameters: keep the graph
         shape = tuple(X.shape)
         if len(shape) != 2:
             raise ValueError("Expected a 2D matrix. Got shape {}".format(shape))
@@ -273,6 +276,7 @@ class MELD(object):
         self.timings_["graph"] = time.perf_counter() - t1
         self._log("Calculated graph and diffusion operator in {:.2f} seconds.".format(time.perf_counter() - t0))
         self.X = X
+        self._build_key = build_key
         self._reset_graph()
         return self
 
@@ -287,6 +291,8 @@ class MELD(object):
             else:
                 raise ValueError("sample_labels must be a single column. Got" "shape={}".format(labels.shape))
         codes, uniques = _factorize(labels)  # hash pass; np.unique would sort N strings
+        if len(codes) and int(codes.min()) < 0:  # NaN / None: np.unique (the reference) cannot sort them with strings,
+            raise ValueError("sample_labels contains missing values (NaN / None)")  # and never merges them silently
         uniques = np.asarray(uniques)
         order = np.argsort(uniques, kind="stable")
         rank = np.empty(len(order), dtype=np.int32)

@@ -13,7 +13,9 @@ This is the same published algorithm (Halko, Martinsson, Tropp 2011, as scikit-l
   (scikit-learn re-normalises with an LU factorisation, here with QR -- scikit-learn's own alternative
   normaliser; both keep span(Q), which is all the result depends on, so the outputs agree to rounding, and
   torch's LU would materialise an N x N permutation); Q = qr(A Q); B = Q^T A; B = Uh S Vt; U = Q Uh;
-  signs fixed so that the largest |entry| of every row of Vt is positive; data_nu = U[:, :k] S[:k].
+  signs fixed so that the largest |entry| of every row of Vt is positive;
+  data_nu = X V_k^T - mean V_k^T, i.e. ``pca.fit(X); pca.transform(X)`` -- what graphtools runs -- NOT
+  ``fit_transform`` (U_k S_k): for the randomized solver the two differ by the approximation residual.
 
 The GEMMs / LU / QR / SVD are library calls (cuBLAS / cuSOLVER through torch) -- plumbing, not a kernel
 of this engine.  Because the random draw and every step match, the result equals scikit-learn's
@@ -40,14 +42,17 @@ class DevicePCA:
         self.n_samples_ = int(n_samples)
 
     def transform(self, Y):
-        torch = nv.require_cuda()
+        """scikit-learn ``PCA.transform``: ``Y @ components_.T - mean_ @ components_.T``."""
+        import torch
+
         Y = torch.as_tensor(Y, dtype=torch.float64, device=self.mean_.device)
-        return (Y - self.mean_) @ self.components_.T
+        return Y @ self.components_.T - (self.mean_[None, :] @ self.components_.T)
 
 
 def randomized_pca(X, n_components, random_state=None, n_oversamples=10):
-    """``PCA(n_components, svd_solver="randomized", random_state=random_state).fit_transform(X)`` on the
-    device.  ``X``: (N, D) float64 CUDA tensor (not modified).  Returns ``(data_nu (N, k), DevicePCA)``."""
+    """``pca = PCA(n_components, svd_solver="randomized", random_state=random_state).fit(X)`` followed by
+    ``pca.transform(X)`` on the device -- the two calls graphtools ``Data._reduce_data`` makes (SURVEY 8a row
+    B').  ``X``: (N, D) float64 CUDA tensor (not modified).  Returns ``(data_nu (N, k), DevicePCA)``."""
     torch = nv.require_cuda()
     from sklearn.utils import check_random_state  # the reference's RandomState handling, host side only
 
@@ -88,5 +93,7 @@ def randomized_pca(X, n_components, random_state=None, n_oversamples=10):
     signs = torch.where(signs == 0, torch.ones_like(signs), signs)
     U = U * signs[None, :]
     Vt = Vt * signs[:, None]
-    data_nu = (U[:, :k] * S[:k]).contiguous()
-    return data_nu, DevicePCA(mean, Vt[:k].contiguous(), S[:k].contiguous(), n)
+    obj = DevicePCA(mean, Vt[:k].contiguous(), S[:k].contiguous(), n)
+    # graphtools: data_pca.fit(X); data_nu = data_pca.transform(X).  U_k S_k (fit_transform) is NOT the same for
+    # the randomized solver: it differs by the projection residual (I - Q Q^T) A V_k, far above rounding.
+    return obj.transform(X).contiguous(), obj

@@ -35,7 +35,8 @@ def reduce_data(X, n_pca, random_state=None):
     from sklearn.decomposition import PCA
 
     pca = PCA(n_pca, svd_solver="randomized", random_state=random_state)
-    return pca.fit_transform(X)
+    pca.fit(X)  # graphtools fits, then transforms: for the randomized solver transform(X) != fit_transform(X)
+    return pca.transform(X)
 
 
 def knn_kernel(

@@ -209,7 +209,7 @@ def test_device_pca_matches_sklearn(mb):
 
     for n, D, k, seed in ((3000, 300, 50, 0), (400, 1000, 60, 3)):
         X, _ = mb.synthetic.make_blobs(n, D, 6, 3, tau=D / 10.0, seed=5)
-        ref = PCA(k, svd_solver="randomized", random_state=seed).fit_transform(X)
+        ref = PCA(k, svd_solver="randomized", random_state=seed).fit(X).transform(X)  # graphtools: fit, then transform
         out, obj = pca.randomized_pca(torch.from_numpy(X).cuda(), k, random_state=seed)
         assert np.abs(out.cpu().numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
         assert obj.components_.shape == (k, D)

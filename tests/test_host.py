@@ -159,7 +159,7 @@ def test_device_pca_algorithm_equals_sklearn_on_cpu_tensors(monkeypatch):
     monkeypatch.setattr(nv, "require_cuda", lambda: torch)
     for n, D, k, seed in ((1500, 200, 40, 0), (300, 700, 50, 3), (900, 120, 100, 1)):
         X, _ = synthetic.make_blobs(n, D, 5, 3, tau=D / 10.0, seed=7)
-        ref = PCA(k, svd_solver="randomized", random_state=seed).fit_transform(X)
+        ref = PCA(k, svd_solver="randomized", random_state=seed).fit(X).transform(X)  # graphtools: fit, then transform
         out, obj = pca.randomized_pca(torch.from_numpy(X), k, random_state=seed)
         assert np.abs(out.numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
         assert tuple(obj.components_.shape) == (k, D) and obj.n_components_ == k
