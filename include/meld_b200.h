@@ -201,6 +201,10 @@ int meld_b200_dist_create(int rank, int world, int64_t n_rows_total, int p_max, 
 int meld_b200_dist_handle_bytes(void);
 int meld_b200_dist_export(const meld_b200_dist_t *d, void *blob_host);
 int meld_b200_dist_connect(meld_b200_dist_t *d, const void *all_blobs_host);
+/* Test hook: contexts of all "ranks" created in ONE process on one device (CUDA IPC cannot map a block into
+ * the process that exported it) are connected by pointer; the ranks' call sequences then run on different
+ * streams of that device and meet through the same flag protocol.                                          */
+int meld_b200_dist_connect_local(meld_b200_dist_t *d, meld_b200_dist_t *const *all, int count);
 /* 1 when a flag wait timed out (a peer died or left the call sequence); synchronises the device.           */
 int meld_b200_dist_error(const meld_b200_dist_t *d, int *err_host);
 int meld_b200_dist_destroy(meld_b200_dist_t *d);

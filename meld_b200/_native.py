@@ -54,6 +54,7 @@ SIGNATURES = {
     "meld_b200_dist_handle_bytes": (C.c_int, []),
     "meld_b200_dist_export": (C.c_int, [_vp, _vp]),
     "meld_b200_dist_connect": (C.c_int, [_vp, _vp]),
+    "meld_b200_dist_connect_local": (C.c_int, [_vp, C.POINTER(_vp), _i32]),
     "meld_b200_dist_error": (C.c_int, [_vp, _pint]),
     "meld_b200_dist_destroy": (C.c_int, [_vp]),
     "meld_b200_cheby_filter_dist": (C.c_int, [_vp, _vp, _dbl, _pdbl, _i32, _vp, _i32, _vp, _vp]),

@@ -145,6 +145,18 @@ int meld_b200_dist_connect(meld_b200_dist_t *d, const void *all_blobs_host) {
   return 0;
 }
 
+int meld_b200_dist_connect_local(meld_b200_dist_t *d, meld_b200_dist_t *const *all, int count) {
+  MELD_REQUIRE(d && all && count == d->world, "dist_connect_local: bad argument");
+  for (int r = 0; r < count; ++r) {
+    MELD_REQUIRE(all[r] && all[r]->rank == r && all[r]->world == d->world && all[r]->n == d->n &&
+                     all[r]->p_max == d->p_max,
+                 "dist_connect_local: context %d does not belong to this group", r);
+    d->peer_base[r] = all[r]->base;
+  }
+  d->connected = true;
+  return 0;
+}
+
 int meld_b200_dist_error(const meld_b200_dist_t *d, int *err_host) {
   MELD_REQUIRE(d && err_host, "dist_error: NULL argument");
   MELD_CUDA(cudaMemcpy(err_host, d->err(), sizeof(int), cudaMemcpyDeviceToHost));

@@ -1,14 +1,26 @@
-"""Row-partitioned Chebyshev filter across ranks (one process per GPU, ``torch.distributed``).
+"""Row-partitioned Chebyshev filter across the GPUs of one box (one process per GPU, ``torch.distributed``).
 
-SURVEY 8e: the recurrence shards by rows of L with ONE exchange per term -- every rank needs the
-whole ``T_{k-1}`` (its rows reference arbitrary columns), so after each term the ranks all-gather
-their row slices.  north_star asks for this only "where N outgrows one GPU"; on a single GPU the
-full-operator ``meld_b200_cheby_filter`` is used instead.  The driver below is backend-agnostic:
-on GPUs ``step`` is ``meld_b200_cheby_step`` on the rank's row slice (``DeviceGraph.from_scipy(L[a:b],
-row0=a, n_cols=N)``) and the collective is NCCL; the CPU test runs it over gloo with a reference step.
+SURVEY 8e: the recurrence shards by rows of L with ONE exchange per term -- every rank needs the whole
+``T_{k-1}`` (its rows reference arbitrary columns).  The reference has nothing to match (no distributed code,
+reference ``setup.py:45``); the operation being sharded is the recurrence behind ``meld/filter.py:59``.
+
+Two data paths over the same row partition (rank r owns rows ``[r * chunk, (r + 1) * chunk)`` of L in the graph's
+INTERNAL cell order, ``chunk = ceil(N / world)``):
+
+* ``mode="p2p"`` (default): ``meld_b200_cheby_filter_dist`` -- the SpMM kernel stores its rows of ``T_k``
+  straight into every peer's HBM over NVLink (CUDA IPC mapped buffers) and the ranks meet through flag words
+  in each other's memory; no NCCL call and no host on the data path.  torch.distributed only carries the
+  64-byte IPC handles once.
+* ``mode="nccl"``: north_star's wording -- ``meld_b200_cheby_step`` on the rank's rows followed by an in-place
+  NCCL all-gather of the ``T_k`` slices per term (pre-allocated buffers, one stream).  Kept as the baseline
+  the fused path is measured against, and it is what the CPU (gloo) test drives with a numpy step.
+
+``cheby_recurrence`` is the backend-agnostic statement of the order of operations (PyGSP ``cheby_op``).
 """
 
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -20,6 +32,12 @@ def row_partition(n, world):
     for r in range(world):
         bounds.append(bounds[-1] + base + (1 if r < rem else 0))
     return bounds
+
+
+def chunk_partition(n, world):
+    """Equal chunks (what an all-gather needs): rank r owns [min(n, r*chunk), min(n, (r+1)*chunk))."""
+    chunk = -(-int(n) // int(world))
+    return chunk, [min(int(n), r * chunk) for r in range(world + 1)]
 
 
 def cheby_recurrence(step, allgather, T0_full, row_range, lmax, coeffs):
@@ -84,3 +102,186 @@ def make_torch_allgather(bounds, p, group=None):
         return torch.cat([out[r * longest: r * longest + (bounds[r + 1] - bounds[r])] for r in range(world)])
 
     return allgather
+
+
+class PeerContext:
+    """This rank's peer-memory block (``meld_b200_dist_t``), connected to the blocks of all ranks of the group."""
+
+    def __init__(self, n_rows_total, p_max=8, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as nv
+
+        lib = nv.lib()
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        h = C.c_void_p()
+        nv.check(lib.meld_b200_dist_create(self.rank, self.world, int(n_rows_total), int(p_max),
+                                           nv.current_stream_ptr(), C.byref(h)), "dist_create")
+        self._h = h
+        self.n, self.p_max = int(n_rows_total), int(p_max)
+        if self.world > 1:
+            nb = lib.meld_b200_dist_handle_bytes()
+            blob = (C.c_ubyte * nb)()
+            nv.check(lib.meld_b200_dist_export(self._h, blob), "dist_export")
+            dev = torch.device("cuda", torch.cuda.current_device())
+            mine = torch.tensor(list(bytes(blob)), dtype=torch.uint8, device=dev)
+            allb = torch.empty(self.world * nb, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allb, mine, group=group)  # plumbing: 64 bytes per rank, once
+            raw = bytes(allb.cpu().numpy().tobytes())
+            buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+            nv.check(lib.meld_b200_dist_connect(self._h, buf), "dist_connect")
+            dist.barrier(group=group)  # every rank has mapped every block before anyone stores into one
+
+    def error(self):
+        from . import _native as nv
+
+        e = C.c_int(0)
+        nv.check(nv.lib().meld_b200_dist_error(self._h, C.byref(e)), "dist_error")
+        return e.value
+
+    def close(self):
+        from . import _native as nv
+
+        if getattr(self, "_h", None) is not None and self._h.value:
+            nv.lib().meld_b200_dist_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_CTX_CACHE = {}
+
+
+def shared_context(n_rows_total, p_max=8, group=None):
+    """One PeerContext per (N, p_max, group) and process: mapping peer memory costs a cudaMalloc, IPC opens and
+    a barrier, far more than a filter; successive graphs of the same size reuse the buffers."""
+    key = (int(n_rows_total), int(p_max), id(group))
+    ctx = _CTX_CACHE.get(key)
+    if ctx is None:
+        ctx = _CTX_CACHE[key] = PeerContext(n_rows_total, p_max, group)
+    return ctx
+
+
+class ShardedFilter:
+    """Row-partitioned ``cheby_apply`` for one graph: every rank passes the same (N, p) signal in the caller's cell
+    order and gets the same (N, p) result.  ``graph`` is the FULL DeviceGraph (every rank holds one after a
+    sharded build); its rows are sliced here."""
+
+    def __init__(self, graph, group=None, mode="p2p", p_max=8):
+        import torch.distributed as dist
+
+        if mode not in ("p2p", "nccl"):
+            raise ValueError("mode value {} not recognized. Choose from ['p2p', 'nccl']".format(mode))
+        self.graph, self.group, self.mode, self.p_max = graph, group, mode, int(p_max)
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.N = graph.N
+        self.chunk, self.bounds = chunk_partition(self.N, self.world)
+        self.row_range = (self.bounds[self.rank], self.bounds[self.rank + 1])
+        self._nccl_bufs = {}
+        self._attach()
+
+    def _attach(self):
+        """Native state: this rank's row slice and (p2p) the peer-memory context."""
+        self.slice = self.graph.row_slice(*self.row_range)
+        self.ctx = shared_context(self.N, self.p_max, self.group) if self.mode == "p2p" else None
+
+    # ---- the two native operations of the NCCL path (overridden by the CPU / gloo test) -----------------
+    def _permute(self, src, p, to_internal, dst):
+        from . import _native as nv
+
+        nv.check(nv.lib().meld_b200_graph_permute_signal(self.graph._h, nv.ptr(src), p, int(to_internal), nv.ptr(dst),
+                                                         nv.current_stream_ptr()), "graph_permute_signal")
+
+    def _step(self, cur, told, tnew, Rloc, p, alpha, shift, gamma, c, c_cur, accumulate):
+        from . import _native as nv
+
+        nv.check(
+            nv.lib().meld_b200_cheby_step(self.slice._h, nv.ptr(cur), nv.ptr(told), nv.ptr(tnew), nv.ptr(Rloc), p,
+                                          float(alpha), float(shift), float(gamma), float(c), float(c_cur),
+                                          int(bool(accumulate)), nv.current_stream_ptr()),
+            "cheby_step",
+        )
+
+    # ---- p2p ---------------------------------------------------------------------------------------------
+    def _apply_p2p(self, lmax, coeffs, S):
+        import torch
+
+        from . import _native as nv
+
+        R = torch.empty_like(S)
+        cptr = coeffs.ctypes.data_as(C.POINTER(C.c_double))
+        nv.check(
+            nv.lib().meld_b200_cheby_filter_dist(self.slice._h, self.ctx._h, float(lmax), cptr, len(coeffs), nv.ptr(S),
+                                                 int(S.shape[1]), nv.ptr(R), nv.current_stream_ptr()),
+            "cheby_filter_dist",
+        )
+        return R
+
+    # ---- nccl --------------------------------------------------------------------------------------------
+    def _apply_nccl(self, lmax, coeffs, S):
+        import torch
+        import torch.distributed as dist
+
+        p = int(S.shape[1])
+        a, b = self.row_range
+        nloc = b - a
+        rows = self.world * self.chunk
+        if p not in self._nccl_bufs:
+            z = lambda r: torch.zeros((r, p), dtype=torch.float64, device=S.device)  # noqa: E731
+            self._nccl_bufs[p] = (z(rows), z(rows), z(self.chunk))
+        bufA, bufB, Rloc = self._nccl_bufs[p]
+        self._permute(S, p, True, bufA)  # T_0 = S in graph order (every rank the whole signal)
+        cur, old = bufA, bufB
+        a1 = float(lmax) / 2.0
+        m = len(coeffs) - 1
+        lo = self.rank * self.chunk
+        for k in range(1, m + 1):
+            mine = old[lo:lo + self.chunk]  # T_k over T_{k-2}, in place; the in-place all-gather publishes it
+            if nloc > 0:
+                self._step(cur, mine if k >= 2 else None, mine if k < m else None, Rloc, p,
+                           (1.0 if k == 1 else 2.0) / a1, a1, 1.0 if k >= 2 else 0.0, coeffs[k],
+                           0.5 * coeffs[0] if k == 1 else 0.0, k >= 2)
+            if k < m:
+                if self.world > 1:
+                    dist.all_gather_into_tensor(old, mine, group=self.group)
+                cur, old = old, cur
+        if self.world > 1:
+            dist.all_gather_into_tensor(old, Rloc, group=self.group)
+        else:
+            old[: self.chunk] = Rloc
+        R = torch.empty_like(S)
+        self._permute(old, p, False, R)
+        return R
+
+    def apply(self, lmax, coeffs, S):
+        import torch
+
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        if coeffs.shape[0] < 2:
+            raise TypeError("The coefficients have an invalid shape")
+        S = S.contiguous()
+        N, p = S.shape
+        if N != self.N:
+            raise ValueError("signal has {} rows, graph has {} nodes".format(N, self.N))
+        fn = self._apply_p2p if self.mode == "p2p" else self._apply_nccl
+        if p <= self.p_max:
+            return fn(lmax, coeffs, S)
+        R = torch.empty_like(S)
+        for j in range(0, p, self.p_max):
+            R[:, j:j + self.p_max] = fn(lmax, coeffs, S[:, j:j + self.p_max].contiguous())
+        return R
+
+    def close(self):
+        self.slice.close()  # the peer context is shared (shared_context) and lives until the process ends

@@ -43,9 +43,10 @@ def cheby_coefficients(h, lmax, m):
     return np.array([2.0 / n * np.dot(hv, np.cos(np.pi * o * (q + 0.5) / n)) for o in range(m + 1)])
 
 
-def filter(signal, graph, filter, beta, offset=0, order=1, solver="chebyshev", chebyshev_order=None):
+def filter(signal, graph, filter, beta, offset=0, order=1, solver="chebyshev", chebyshev_order=None, apply=None):
     """Low-pass filter ``signal`` (N, p) over ``graph``; returns an ndarray (or a CUDA tensor
-    when ``signal`` is one)."""
+    when ``signal`` is one).  ``apply(lmax, coeffs, S)`` replaces the single-GPU recurrence (row-partitioned
+    multi-GPU filter, ``meld_b200.distributed.ShardedFilter.apply``)."""
     if not isinstance(graph, DeviceGraph):
         raise TypeError("graph must be a meld_b200.DeviceGraph")
     h = filter_kernel(filter, beta, offset, order)  # NotImplementedError for unknown kernels
@@ -62,7 +63,7 @@ def filter(signal, graph, filter, beta, offset=0, order=1, solver="chebyshev", c
     squeeze = S.dim() == 1
     if squeeze:
         S = S[:, None]
-    R = cheby_apply(graph, lmax, coeffs, S)
+    R = cheby_apply(graph, lmax, coeffs, S) if apply is None else apply(lmax, coeffs, S)
     if squeeze:
         R = R[:, 0]
     return R if on_device else R.cpu().numpy()
@@ -95,3 +96,32 @@ def cheby_apply(graph, lmax, coeffs, S):
         )
         R[:, j:j + MAX_P] = Rj
     return R
+
+
+def cheby_sweep(graph, lmax, coeff_matrix, S):
+    """Shared-basis sweep: ``coeff_matrix`` is (F, m+1) -- one Chebyshev coefficient vector per filter -- and
+    ``S`` an (N, p) float64 CUDA tensor.  The recurrence runs once per chunk of 8 signal columns; returns the
+    (F, N, p) densities ``R[f] = sum_k c[f, k] T_k(L) S`` (reference pattern ``meld/benchmark.py:186-200``:
+    one graph, many ``MELD(beta=b).transform(labels)``)."""
+    torch = nv.require_cuda()
+    N, p = S.shape
+    if N != graph.N:
+        raise ValueError("signal has {} rows, graph has {} nodes".format(N, graph.N))
+    cm = np.ascontiguousarray(coeff_matrix, dtype=np.float64)
+    if cm.ndim != 2 or cm.shape[1] < 2:
+        raise TypeError("The coefficients have an invalid shape")
+    F, nc = cm.shape
+    cptr = cm.ctypes.data_as(C.POINTER(C.c_double))
+    out = torch.empty((F, N, p), dtype=torch.float64, device=S.device)
+    for j in range(0, p, MAX_P):
+        Sj = S[:, j:j + MAX_P].contiguous()
+        pj = Sj.shape[1]
+        Rj = out if pj == p else torch.empty((F, N, pj), dtype=torch.float64, device=S.device)
+        nv.check(
+            nv.lib().meld_b200_cheby_sweep(graph._h, float(lmax), cptr, F, nc, nv.ptr(Sj), pj, nv.ptr(Rj),
+                                           nv.current_stream_ptr()),
+            "cheby_sweep",
+        )
+        if Rj is not out:
+            out[:, :, j:j + pj] = Rj
+    return out

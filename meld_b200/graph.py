@@ -172,9 +172,12 @@ class DeviceGraph:
         eps = gather_var(eps, rows)
         cand = gather_var(cand, tots)
         d2 = gather_var(d2, tots)
-        if perm is None and N >= 4096:  # a rank with an empty row range did not compute the order
-            perm = torch.empty(N, dtype=torch.int32, device=X.device)
-        if N >= 4096:
+        # whether the native build re-ordered the cells is the library's decision (tuning): ask the ranks
+        has = torch.tensor([1 if perm is not None else 0], dtype=torch.int64, device=X.device)
+        dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
+        if int(has.item()):
+            if perm is None:  # a rank with an empty row range did not compute the order
+                perm = torch.empty(N, dtype=torch.int32, device=X.device)
             src = next(r for r in range(world) if rows[r] > 0)
             dist.broadcast(perm, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
         lap("all-gather")
@@ -205,6 +208,25 @@ class DeviceGraph:
         )
         torch.cuda.current_stream().synchronize()
         return cls(out.value, params, device=dev)
+
+    def row_slice(self, row_begin, row_end):
+        """Rows [row_begin, row_end) of L in the INTERNAL cell order as their own handle (what one rank of a
+        row-partitioned filter holds); it keeps the full graph's cell order for signal conversion."""
+        out = C.c_void_p()
+        nv.check(nv.lib().meld_b200_graph_row_slice(self._h, int(row_begin), int(row_end), nv.current_stream_ptr(),
+                                                    C.byref(out)), "graph_row_slice")
+        g = DeviceGraph(out.value, self.params, device=self.device)
+        g._lmax = self._lmax
+        return g
+
+    def permute_signal(self, x, to_internal=True):
+        """(N, p) float64 CUDA tensor between the caller's cell order and the graph's internal one."""
+        torch = nv.require_cuda()
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        nv.check(nv.lib().meld_b200_graph_permute_signal(self._h, nv.ptr(x), int(x.shape[1]), int(bool(to_internal)),
+                                                         nv.ptr(out), nv.current_stream_ptr()), "graph_permute_signal")
+        return out
 
     # ---- the protocol meld/filter.py relies on ----------------------------------------
     @property

@@ -100,6 +100,11 @@ class MELD(object):
         self.verbose = kwargs.pop("verbose", 1)
         # engine extension: shard the graph build over torch.distributed ranks (one process per GPU)
         self.distributed = bool(kwargs.pop("distributed", False))
+        # how a distributed estimator filters: "p2p" = row-partitioned recurrence with peer stores over NVLink,
+        # "nccl" = row-partitioned with an NCCL all-gather per term, "replicated" = every rank filters alone
+        self.dist_mode = kwargs.pop("dist_mode", "p2p")
+        _check_in(["p2p", "nccl", "replicated"], dist_mode=self.dist_mode)
+        self._sharded = None
         self.anisotropy = anisotropy
         self.n_landmark = n_landmark
         self.kwargs = kwargs  # remaining graphtools.Graph keywords, checked at fit time
@@ -243,6 +248,9 @@ class MELD(object):
         if isinstance(X, DeviceGraph):
             self.graph = X
             self.X = None
+            if self._sharded is not None:
+                self._sharded.close()
+                self._sharded = None
             self._reset_graph()
             return self
         if hasattr(X, "tocsr") or hasattr(X, "todense"):
@@ -254,7 +262,7 @@ class MELD(object):
         extra.pop("use_pygsp", None)
         self._check_supported(extra)
         build_key = (self.knn, self.decay, self.thresh, self.anisotropy, self.n_pca, self.random_state, self.distributed,
-                     tuple(sorted(extra.items())))
+                     self.dist_mode, tuple(sorted(extra.items())))
         if (self.graph is not None and self.X is not None and getattr(self, "_build_key", None) == build_key
                 and _same_data(torch, X, self.X)):
             return self  # same data AND same effective build parameters: keep the graph
@@ -273,6 +281,13 @@ class MELD(object):
             data_nu, knn=self.knn, decay=self.decay, thresh=self.thresh, anisotropy=self.anisotropy,
             bandwidth_scale=extra.get("bandwidth_scale", 1.0),
         )
+        if self._sharded is not None:
+            self._sharded.close()
+            self._sharded = None
+        if self.distributed and self.dist_mode != "replicated":
+            from .distributed import ShardedFilter
+
+            self._sharded = ShardedFilter(self.graph, mode=self.dist_mode)
         self.timings_["graph"] = time.perf_counter() - t1
         self._log("Calculated graph and diffusion operator in {:.2f} seconds.".format(time.perf_counter() - t0))
         self.X = X
@@ -419,12 +434,90 @@ class MELD(object):
         densities = _filter.filter(
             signal=S, graph=self.graph, filter=self.filter, beta=self.beta, offset=self.offset, order=self.order,
             solver=self.solver, chebyshev_order=self.chebyshev_order,
+            apply=self._sharded.apply if self._sharded is not None else None,
         )
         if events is not None:
             e1.record()
             events.append((e0, e1, int(self.chebyshev_order)))
         self.sample_densities_device = densities
         return densities
+
+    def transform_sweep(self, sample_labels, betas=None, filter_params=None, as_tensor=False):
+        """Densities of one or several label vectors under MANY filter settings on the fitted graph.
+
+        The reference's dominant workload is a parameter search: one graph, thousands of
+        ``MELD(beta=b).fit(graph).transform(labels)`` calls (``meld/benchmark.py:186-200``,
+        ``notebooks/MELD_Quickstart.ipynb:729-747``: 25 label draws x 199 beta per graph).  Filters that differ
+        only in ``beta / offset / order / filter`` share the Chebyshev basis ``T_k(L) S``, so the recurrence
+        runs once per 8 signal columns and every setting only costs its coefficient vector
+        (``meld_b200_cheby_sweep``).
+
+        sample_labels : one label vector, or a list of label vectors (each as for ``transform``).
+        betas : iterable of beta values (other filter parameters are the estimator's), or
+        filter_params : list of dicts with any of ``beta, offset, order, filter``.
+        as_tensor : return ``(R, columns)`` with ``R`` a CUDA tensor (n_settings, N, total columns) and
+            ``columns`` a list of (label-vector index, sample name) instead of DataFrames on the host.
+
+        Returns ``out[i][f]`` = DataFrame (N, p_i) of label vector ``i`` under setting ``f``; each equals
+        what ``transform`` returns for that setting.
+        """
+        torch = nv.require_cuda()
+        self.graph = utils._check_pygsp_graph(self.graph)
+        if self.solver != "chebyshev":
+            raise NotImplementedError(
+                "solver='{}' is not available in the B200 engine; use solver='chebyshev'".format(self.solver)
+            )
+        if (betas is None) == (filter_params is None):
+            raise ValueError("pass exactly one of betas / filter_params")
+        settings = [dict(beta=b) for b in betas] if betas is not None else [dict(fp) for fp in filter_params]
+        if not settings:
+            raise ValueError("empty parameter sweep")
+        single = not isinstance(sample_labels, (list, tuple))
+        label_sets = [sample_labels] if single else list(sample_labels)
+        dev = self.graph.device
+        cols, blocks, meta = [], [], []
+        for i, labels in enumerate(label_sets):
+            if labels.shape[0] != self.graph.N:
+                raise ValueError(
+                    "Input data ({}) and input graph ({}) "
+                    "are not of the same size".format(labels.shape, self.graph.N)
+                )
+            samples, codes = self._label_codes(labels)
+            if len(samples) == 1:
+                raise ValueError("Found only one unqiue sample label. Cannot estimate density " "of a single sample.")
+            d_codes = torch.from_numpy(np.ascontiguousarray(codes, dtype=np.int32)).to(dev)
+            S = torch.empty((len(codes), len(samples)), dtype=torch.float64, device=dev)
+            nv.check(
+                nv.lib().meld_b200_indicator_matrix(nv.ptr(d_codes), len(codes), len(samples),
+                                                    int(bool(self.sample_normalize)), nv.ptr(S),
+                                                    nv.current_stream_ptr()),
+                "indicator_matrix",
+            )
+            blocks.append(S)
+            meta.append((samples, getattr(labels, "index", None)))
+            cols.extend((i, s) for s in samples)
+        S_all = torch.cat(blocks, dim=1) if len(blocks) > 1 else blocks[0]
+        lmax = self.graph.estimate_lmax()
+        m = int(self.chebyshev_order)
+        coeff = np.empty((len(settings), m + 1), dtype=np.float64)
+        for f, st in enumerate(settings):
+            unknown = set(st) - {"beta", "offset", "order", "filter"}
+            if unknown:
+                raise ValueError("Invalid sweep parameter(s): {}".format(sorted(unknown)))
+            h = _filter.filter_kernel(st.get("filter", self.filter), st.get("beta", self.beta),
+                                      st.get("offset", self.offset), st.get("order", self.order))
+            coeff[f] = _filter.cheby_coefficients(h, lmax, m)
+        R = _filter.cheby_sweep(self.graph, lmax, coeff, S_all)  # (F, N, sum p_i)
+        if as_tensor:
+            return R, cols
+        host = R.cpu().numpy()
+        out, c0 = [], 0
+        for samples, index in meta:
+            pi = len(samples)
+            out.append([pd.DataFrame(host[f, :, c0:c0 + pi], index=index, columns=samples)
+                        for f in range(len(settings))])
+            c0 += pi
+        return out[0] if single else out
 
     def fit_transform(self, X, sample_labels, **kwargs):
         """Build the graph on ``X`` and estimate the density of each sample in ``sample_labels``."""

@@ -48,6 +48,7 @@ def knn_kernel(
     n_jobs=1,
     algorithm="ball_tree",
     return_stats=False,
+    timings=None,
 ):
     """``kNNGraph.build_kernel`` -> ``build_kernel_to_data(data, knn=knn + 1)``.
 
@@ -66,9 +67,14 @@ def knn_kernel(
     thresh = max(thresh, EPS)  # kNNGraph.__init__: thresh == 0 with decay -> eps
     knn_max = N  # knn_max=None upstream means "no cap"
 
+    import time as _time
+
+    t_search = _time.perf_counter()
     tree = NearestNeighbors(n_neighbors=knn_arg, algorithm=algorithm, n_jobs=n_jobs).fit(data)
     search_knn = min(knn_arg * SEARCH_MULTIPLIER, knn_max)
     distances, indices = tree.kneighbors(data, n_neighbors=search_knn)
+    if timings is not None:  # "KNN search" vs "affinities" of the reference's own log (bench.py stage split)
+        timings["knn_first_search_s"] = _time.perf_counter() - t_search
 
     bandwidth = distances[:, knn_arg - 1] * bandwidth_scale
     bandwidth = np.maximum(bandwidth, EPS)
@@ -132,6 +138,43 @@ def knn_kernel_bruteforce(data, knn=5, decay=40.0, thresh=1e-4, bandwidth_scale=
     K = np.exp(-1 * np.power(D / bandwidth[:, None], decay))
     K[K < thresh] = 0
     return sparse.csr_matrix(K)
+
+
+def knn_kernel_rows_bruteforce(data, rows, knn=5, decay=40.0, thresh=1e-4, bandwidth_scale=1.0, chunk=256):
+    """Rows ``rows`` of the un-symmetrised kernel by its DEFINITION (``knn_kernel_bruteforce`` restricted to a
+    sample of rows, usable at 500k - 2M cells where neither the ball tree nor a dense N x N matrix is an
+    option): all j with ``exp(-(d_ij / eps_i)^decay) >= thresh``, ``eps_i`` = distance to the knn-th non-self
+    neighbour.  A float64 GEMM expansion only pre-selects candidates (with a relative safety margin); every
+    kept distance is then recomputed as ``sqrt(sum_k (x_ik - x_jk)^2)`` in feature order like the ball tree.
+    Returns a list of (cols ascending, values) per requested row."""
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    rows = np.asarray(rows, dtype=np.int64)
+    N = data.shape[0]
+    thresh = max(thresh, EPS)
+    rho = np.power(-np.log(thresh), 1.0 / decay)
+    sq = np.einsum("ij,ij->i", data, data)
+    out = []
+    for s in range(0, len(rows), chunk):
+        r = rows[s:s + chunk]
+        d2 = sq[r][:, None] + sq[None, :] - 2.0 * (data[r] @ data.T)  # approximate, selection only
+        np.maximum(d2, 0.0, out=d2)
+        kth = np.partition(d2, knn, axis=1)[:, knn]  # ~ squared distance of the knn-th non-self neighbour
+        slack = 1e-6 * (sq[r] + sq.max()) + 1e-300
+        for t, i in enumerate(r):
+            lim = (kth[t] + slack[t]) * (rho * bandwidth_scale) ** 2 * (1.0 + 1e-6) + slack[t]
+            cand = np.flatnonzero(d2[t] <= max(lim, kth[t] + slack[t]))
+            diff = data[cand] - data[i]
+            acc = np.zeros(len(cand))
+            for k in range(data.shape[1]):  # sequential, unfused: sklearn's rdist order
+                acc = acc + diff[:, k] * diff[:, k]
+            dist = np.sqrt(acc)
+            eps = max(np.sort(dist)[knn] * bandwidth_scale, EPS)
+            val = np.exp(-1 * np.power(dist / eps, decay))
+            val = np.where(np.isnan(val), 1, val)
+            keep = val >= thresh
+            order = np.argsort(cand[keep], kind="stable")
+            out.append((cand[keep][order], val[keep][order]))
+    return out
 
 
 def traditional_kernel(data, knn=5, decay=40.0, thresh=0.0, bandwidth_scale=1.0):
@@ -204,11 +247,13 @@ def build_graph(
     bandwidth_scale=1.0,
     n_jobs=1,
     data_nu=None,
+    timings=None,
 ):
     """Stages B..F of SURVEY 8a.  Returns a dict with data_nu, K, W, L, dw."""
     if data_nu is None:
         data_nu = reduce_data(X, n_pca, random_state)
-    K0 = knn_kernel(data_nu, knn=knn, decay=decay, thresh=thresh, bandwidth_scale=bandwidth_scale, n_jobs=n_jobs)
+    K0 = knn_kernel(data_nu, knn=knn, decay=decay, thresh=thresh, bandwidth_scale=bandwidth_scale, n_jobs=n_jobs,
+                    timings=timings)
     K = apply_anisotropy(symmetrize(K0), anisotropy)
     K.sort_indices()
     W = weights_from_kernel(K)

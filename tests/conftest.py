@@ -46,3 +46,14 @@ def density_parity(R, Rref, rtol=1e-5):
     normwise = (err.max(axis=0) / colmax).max()
     elementwise_ok = np.all(err <= rtol * np.abs(Rref) + 1e-9 * colmax)
     return normwise, bool(elementwise_ok)
+
+
+def row_pattern_hash(L):
+    """Order-independent 64-bit hash of each row's column set (same as tests/golden/make_scale_digests.py)."""
+    L = L.tocsr()
+    h = (L.indices.astype(np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+    out = np.zeros(L.shape[0], dtype=np.uint64)
+    lens = np.diff(L.indptr)
+    nz = lens > 0
+    out[nz] = np.add.reduceat(h, L.indptr[:-1][nz])
+    return out

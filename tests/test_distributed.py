@@ -75,3 +75,73 @@ def test_row_partitioned_driver_two_ranks_gloo(tmp_path):
     assert out.shape == ref.shape
     assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
     assert mdist.row_partition(10, 3) == [0, 4, 7, 10]
+
+
+def _worker_sharded_filter(rank, world, port, out_dir):
+    """ShardedFilter's NCCL-mode host logic (chunk partition, ping-pong full buffers, in-place all-gather, final
+    gather of R, cell-order conversion) over gloo, with the two native operations replaced by numpy ones."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from meld_b200 import distributed as mdist, filter as mf
+
+    g = load_golden("blobs2k5_wagner")
+    L, lmax = g["L"].tocsr(), g["lmax"]
+    N = L.shape[0]
+    perm = np.random.default_rng(4).permutation(N)  # internal row a = caller's cell perm[a]
+    Lint = L[perm][:, perm].tocsr()
+
+    class CpuSharded(mdist.ShardedFilter):
+        def __init__(self):
+            self.graph, self.group, self.mode, self.p_max = None, None, "nccl", 4
+            self.rank, self.world, self.N = rank, world, N
+            self.chunk, self.bounds = mdist.chunk_partition(N, world)
+            self.row_range = (self.bounds[rank], self.bounds[rank + 1])
+            self._nccl_bufs = {}
+            self.Lr = Lint[self.row_range[0]:self.row_range[1]]
+
+        def _permute(self, src, p, to_internal, dst):
+            if to_internal:
+                dst[:N] = src[:N][torch.from_numpy(perm)]
+            else:
+                dst[torch.from_numpy(perm)] = src[:N]
+
+        def _step(self, cur, told, tnew, Rloc, p, alpha, shift, gamma, c, c_cur, accumulate):
+            a, b = self.row_range
+            Tc = cur.numpy()[:N]
+            tn = alpha * (self.Lr @ Tc - shift * Tc[a:b])
+            if gamma != 0.0:
+                tn = tn - gamma * told.numpy()[: b - a]
+            rv = c * tn + c_cur * Tc[a:b]
+            if accumulate:
+                rv = rv + Rloc.numpy()[: b - a]
+            Rloc[: b - a] = torch.from_numpy(rv)
+            if tnew is not None:
+                tnew[: b - a] = torch.from_numpy(tn)
+
+    sf = CpuSharded()
+    S = torch.from_numpy(np.random.default_rng(1).normal(size=(N, 6)))  # 6 columns with p_max 4: two chunks
+    coeffs = mf.cheby_coefficients(mf.filter_kernel("heat", 60), lmax, 16)
+    R = sf.apply(lmax, coeffs, S)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "R_sharded.npy"), R.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_filter_host_logic_gloo(tmp_path, world):
+    from oracle import cheby
+    from meld_b200 import filter as mf, distributed as mdist
+
+    mp.spawn(_worker_sharded_filter, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = load_golden("blobs2k5_wagner")
+    S = np.random.default_rng(1).normal(size=(g["L"].shape[0], 6))
+    coeffs = mf.cheby_coefficients(mf.filter_kernel("heat", 60), g["lmax"], 16)
+    ref = cheby.cheby_op(g["L"], g["lmax"], coeffs, S)
+    out = np.load(os.path.join(str(tmp_path), "R_sharded.npy"))
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert mdist.chunk_partition(10, 3) == (4, [0, 4, 8, 10])
+    assert mdist.chunk_partition(7, 8)[1] == [0, 1, 2, 3, 4, 5, 6, 7, 7]

@@ -1,0 +1,105 @@
+"""GPU-vs-oracle parity AT THE SIZES THAT ARE BENCHED, default tuning.
+
+* configs 2 and 3 (50k x 2000 with and without PCA, 90k x 100): the engine at full size against the digest of a
+  full-size oracle run (tests/golden/scale_*.npz, made by tests/golden/make_scale_digests.py in the build
+  container -- the GPU box has no reference and no reason to spend its minutes on a CPU ball tree): identical
+  sparsity pattern of L (per-row hash), diagonal to 1e-10, densities on 8192 sampled rows with the oracle's lmax.
+* configs 4 and 5 (500k x 100, 2M x 50): the CPU path cannot build these graphs in useful time, so
+  (a) 1024 random rows of the un-symmetrised kernel against the float64 brute-force DEFINITION ("all j with
+  K_ij >= thresh", oracle.graph.knn_kernel_rows_bruteforce), (b) the oracle's scipy symmetrise / anisotropy /
+  Laplacian stages applied to the exported kernel against the exported L, (c) the oracle's Chebyshev filter on the
+  exported L against the engine's densities.  Together: every stage of the 500k / 2M result is checked."""
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, density_parity, row_pattern_hash
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import torch
+
+    assert torch.cuda.is_available()
+    import meld_b200
+
+    return meld_b200
+
+
+@pytest.mark.parametrize("name", ["c3", "c2pca", "c2raw"])
+def test_full_size_run_matches_oracle_digest(mb, name):
+    path = os.path.join(GOLDEN_DIR, "scale_{}.npz".format(name))
+    if not os.path.exists(path):
+        pytest.skip("digest {} not generated".format(path))
+    z = np.load(path, allow_pickle=False)
+    n_pca = int(z["n_pca"])
+    X, y, kw = mb.synthetic.make_config(str(z["config"]))
+    assert kw == eval(str(z["meld_kwargs"]))
+    op = mb.MELD(verbose=0, n_pca=None if n_pca < 0 else n_pca, random_state=0, **kw)
+    op.fit(X)
+    L = op.graph.to_scipy_L()
+    # graph gate: identical pattern, values to 1e-10 (the diagonal sums every off-diagonal value of its row)
+    assert L.nnz == int(z["nnz"]), (L.nnz, int(z["nnz"]))
+    assert np.array_equal(row_pattern_hash(L), z["row_hash"])
+    scale = np.abs(z["diag"]).max()
+    assert np.abs(L.diagonal() - z["diag"]).max() <= 1e-10 * scale
+    assert abs(L - L.T).max() == 0.0
+    assert np.abs(L @ np.ones(L.shape[0])).max() <= 1e-12 * scale
+    # density gate with the oracle's lmax injected; the engine's own lmax is reported alongside
+    own = op.graph.estimate_lmax()
+    lmax = float(z["lmax"])
+    assert abs(own - lmax) <= 3e-4 * lmax, (own, lmax)
+    op.graph.lmax = lmax
+    dens = op.transform(y)
+    assert list(dens.columns) == list(z["samples"])
+    rows = z["dens_rows"]
+    err = np.abs(dens.values[rows] - z["dens"])
+    colmax = z["dens_colmax"]
+    assert (err.max(axis=0) / colmax).max() < 1e-8
+    assert np.all(err <= 1e-5 * np.abs(z["dens"]) + 1e-9 * colmax)
+    np.testing.assert_allclose(np.abs(dens.values).max(axis=0), colmax, rtol=1e-8)
+    np.testing.assert_allclose(dens.values.sum(axis=0), z["dens_colsum"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["c4", "c5"])
+def test_bench_size_graph_and_filter_against_cpu_stages(mb, name):
+    from oracle import graph as og, meld as om
+
+    X, y, kw = mb.synthetic.make_config(name)
+    N = X.shape[0]
+    knn = kw.get("knn", 5)
+    graph = mb.DeviceGraph.from_data(X, knn=knn, keep_knn_kernel=True)  # default tuning: what bench.py times
+    stats = graph.build_stats()
+    assert stats["search_impl"] == 0
+    # (a) sampled rows of the un-symmetrised kernel vs the brute-force definition
+    K = graph.to_scipy_knn_kernel()
+    rows = np.sort(np.random.default_rng(11).choice(N, size=1024, replace=False))
+    ref_rows = og.knn_kernel_rows_bruteforce(X, rows, knn=knn)
+    for i, (cols, vals) in zip(rows, ref_rows):
+        a, b = K.indptr[i], K.indptr[i + 1]
+        assert np.array_equal(K.indices[a:b], cols), (name, int(i), b - a, len(cols))
+        assert np.abs(K.data[a:b] - vals).max() <= 1e-12
+    assert np.all(K.diagonal() == 1.0)
+    # (b) symmetrise + anisotropy + Laplacian: oracle stages on the exported kernel vs the exported L
+    Lref = og.laplacian(og.weights_from_kernel(og.apply_anisotropy(og.symmetrize(K), 1.0)))
+    L = graph.to_scipy_L()
+    del K
+    assert L.nnz == Lref.nnz and np.array_equal(L.indptr, Lref.indptr) and np.array_equal(L.indices, Lref.indices)
+    scale = np.abs(Lref.data).max()
+    assert np.abs(L.data - Lref.data).max() <= 1e-10 * scale
+    assert abs(L - L.T).max() == 0.0
+    del Lref
+    # (c) the filter: CPU Chebyshev (scipy matvecs) on the exported graph vs the engine, same lmax
+    lmax = graph.estimate_lmax()
+    fkw = {k: v for k, v in kw.items() if k != "knn"}
+    op = mb.MELD(verbose=0, knn=knn, **fkw).fit(graph)
+    dens = op.transform(y)
+    ref = om.transform(L, lmax, y, **fkw)
+    normwise, ok = density_parity(dens.values, ref.values, 1e-5)
+    assert ok and normwise < 1e-9, (name, normwise)
+    true = float(np.abs(L.diagonal()).max())
+    assert lmax <= 1.01 * 2 * true  # Gershgorin: lambda_max <= 2 max degree
