@@ -64,6 +64,8 @@ int meld_b200_set_tuning(const char *key, int value);
  * Euclidean kNN, alpha-decay kernel K_ij = exp(-(d_ij/eps_i)^decay) for every j
  * with K_ij >= thresh, (K+K^T)/2, anisotropy K_ij/(q_i q_j)^a, W = K - diag,
  * L = diag(W 1) - W.  X is (n, d) row-major float64 (the post-PCA data_nu).
+ * decay = 0 stands for the reference's decay=None: the unweighted kernel K_ij = 1 for the knn nearest
+ * cells of i (self included), thresh and bandwidth_scale ignored (graphtools kNNGraph, binary branch).
  * flags: bit0 keep the un-symmetrised kernel for meld_b200_graph_export_knn_kernel,
  *        bit1 use the SIMT fp32 candidate search instead of the tcgen05 one
  *        (test cross-check only).
@@ -73,6 +75,12 @@ int meld_b200_set_tuning(const char *key, int value);
 int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay,
                               double thresh, double anisotropy, double bandwidth_scale,
                               int flags, void *stream, meld_b200_graph_t **graph_out);
+
+/* Stands in for graphtools.Graph(..., thresh=0) -> TraditionalGraph ("exact" dense graph; what the reference's
+ * own known-answer test builds, test/test_meld.py:58-67): the same kernel for EVERY pair whose value has not
+ * underflowed to zero, eps_i = distance to the knn-th non-self neighbour.  n <= 16384.  flags: bit0 as above. */
+int meld_b200_dense_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay, double anisotropy,
+                                double bandwidth_scale, int flags, void *stream, meld_b200_graph_t **graph_out);
 
 /* ---- sharded build: the two stages of meld_b200_knn_graph_build, for one-process-per-GPU drivers ------
  * Stage 1 is row-local: candidate search (pass 1 + pass 2 against ALL n cells), exact float64 distances

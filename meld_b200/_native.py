@@ -29,6 +29,7 @@ SIGNATURES = {
     "meld_b200_device_info": (C.c_int, [_pint, _pint, _pint]),
     "meld_b200_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "meld_b200_knn_graph_build": (C.c_int, [_vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _vp, C.POINTER(_vp)]),
+    "meld_b200_dense_graph_build": (C.c_int, [_vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _i32, _vp, C.POINTER(_vp)]),
     "meld_b200_knn_candidates": (C.c_int, [_vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _i64, _i64, _i32, _vp, C.POINTER(_vp)]),
     "meld_b200_cands_info": (C.c_int, [_vp, _pi64, _pi64, _pint, _pi64]),
     "meld_b200_cands_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -23,6 +23,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace meld {
@@ -1033,9 +1034,7 @@ static FlatKernel pick_flat(int P, int G) {
 // ---- dispatch of the second-generation flat kernel -------------------------------------------------------------
 template <int P, int HINT>
 static FlatKernel pick_flat2_layout(int layout) {
-  if constexpr (HINT <= 1) {
-    if (layout == 1) return cheby_flat2_kernel<P, 1024, HINT, 1, false, false>;
-  }
+  if (layout == 1) return cheby_flat2_kernel<P, 1024, HINT, 1, false, false>;
   return cheby_flat2_kernel<P, 1024, HINT, 0, false, false>;
 }
 template <int P>
@@ -1063,23 +1062,31 @@ static FlatKernel pick_flat2(int P, int hint, int layout) {
 template <int HINT>
 static FlatKernel pick_flat2_peer_h(int P) {
   switch (P) {
-    case 1: return cheby_flat2_kernel<1, 1024, HINT, 0, false, true>;
-    case 2: return cheby_flat2_kernel<2, 1024, HINT, 0, false, true>;
-    case 3: return cheby_flat2_kernel<3, 1024, HINT, 0, false, true>;
-    case 4: return cheby_flat2_kernel<4, 1024, HINT, 0, false, true>;
-    case 5: return cheby_flat2_kernel<5, 1024, HINT, 0, false, true>;
-    case 6: return cheby_flat2_kernel<6, 1024, HINT, 0, false, true>;
-    case 7: return cheby_flat2_kernel<7, 1024, HINT, 0, false, true>;
-    case 8: return cheby_flat2_kernel<8, 1024, HINT, 0, false, true>;
+    case 1: return cheby_flat2_kernel<1, 1024, HINT, 1, false, true>;
+    case 2: return cheby_flat2_kernel<2, 1024, HINT, 1, false, true>;
+    case 3: return cheby_flat2_kernel<3, 1024, HINT, 1, false, true>;
+    case 4: return cheby_flat2_kernel<4, 1024, HINT, 1, false, true>;
+    case 5: return cheby_flat2_kernel<5, 1024, HINT, 1, false, true>;
+    case 6: return cheby_flat2_kernel<6, 1024, HINT, 1, false, true>;
+    case 7: return cheby_flat2_kernel<7, 1024, HINT, 1, false, true>;
+    case 8: return cheby_flat2_kernel<8, 1024, HINT, 1, false, true>;
     default: return nullptr;
   }
 }
 static FlatKernel pick_flat2_peer(int P, int hint) {
-  return hint >= 1 ? pick_flat2_peer_h<1>(P) : pick_flat2_peer_h<0>(P);
+  return hint >= 2 ? pick_flat2_peer_h<2>(P) : pick_flat2_peer_h<1>(P);
 }
 static FlatKernel pick_flat2_dot(int hint) {
-  return hint >= 1 ? cheby_flat2_kernel<1, 1024, 1, 0, true, false> : cheby_flat2_kernel<1, 1024, 0, 0, true, false>;
+  (void)hint;
+  return cheby_flat2_kernel<1, 1024, 1, 1, true, false>;
 }
+
+// Measured on the 500k-cell graph of config 4 (tools/r02_probe.py, profiles/r02_probe_spmm_variants.txt): the cache
+// policy of the matrix stream does not move the p <= 4 time (the kernel is bound by L1TEX data-pipe wavefronts, one
+// per gathered row, not by what the L1 holds); lane-consecutive entries gain 3 % at p = 4 and 15 % at p = 1;
+// at p = 8 (two wavefronts per gathered row) not allocating the gathers in L1 gains 12 %.
+static int auto_hint(int P, int hint) { return hint >= 0 ? hint : (P > 4 ? 2 : 1); }
+static int auto_layout(int P, int layout) { return layout >= 0 ? layout : (P > 4 ? 0 : 1); }
 
 typedef void (*StepKernel)(const StepArgs);
 
@@ -1128,9 +1135,11 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
   const int G = choose_group(g, P);
   const bool want_peer = a.n_peers > 0 || a.wait_epoch != 0 || a.post_epoch != 0;
   const bool want_dot = a.dot_partials != nullptr;
-  if ((g->x_mode == 2 && t.flat_gen == 1) || want_peer || want_dot) {  // second-generation flat kernel (8 lanes per row)
-    FlatKernel fk = want_peer ? pick_flat2_peer(P, t.flat_hint)
-                              : (want_dot ? pick_flat2_dot(t.flat_hint) : pick_flat2(P, t.flat_hint, t.flat_layout));
+  // very short (<= 12 entries) or very long (> 256) rows keep the round-1 kernels with 4 / 32 lanes per row
+  const bool g8 = (t.flat_group > 0 ? t.flat_group : G) == 8 || (t.flat_group <= 0 && G == 16);
+  if ((g->x_mode == 2 && t.flat_gen == 1 && g8) || want_peer || want_dot) {  // second-generation flat kernel (8 lanes per row)
+    const int hint = auto_hint(P, t.flat_hint), layout = auto_layout(P, t.flat_layout);
+    FlatKernel fk = want_peer ? pick_flat2_peer(P, hint) : (want_dot ? pick_flat2_dot(hint) : pick_flat2(P, hint, layout));
     MELD_REQUIRE(fk != nullptr, "cheby_step: p=%d outside 1..8", P);
     MELD_REQUIRE(!want_dot || P == 1, "cheby_step: the fused dot product needs p = 1");
     a.row_ptr = g->row_ptr.p;
@@ -1765,6 +1774,13 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
       if (dd[(size_t)j] > dd[(size_t)top]) top = j;
     theta = dd[(size_t)top];
     const double resid = kk < k ? 0.0 : fabs(beta[(size_t)k] * zl[(size_t)top]);
+    if (getenv("MELD_B200_LANCZOS_DEBUG")) {
+      double second = -INFINITY;
+      for (int j = 0; j < kk; ++j)
+        if (j != top && dd[(size_t)j] > second) second = dd[(size_t)j];
+      fprintf(stderr, "[meld_b200 lanczos] k=%d theta=%.15g resid/theta=%.3e ritz gap/theta=%.3e\n", k, theta,
+              resid / fabs(theta), (theta - second) / fabs(theta));
+    }
     if (resid <= rel_tol * fabs(theta)) done = true;
     if (done) k = kk;
     next_check = k + 4 < max_iters ? k + 4 : max_iters;

@@ -74,9 +74,9 @@ struct Tuning {
                           // (measured: 154 us either way at p = 4 -- L1-tag bound; Lanczos p = 1 gains 15 %)
   int flat_sched = 1;     // flat kernel: 1 = every CTA owns a contiguous, nonzero-balanced row range; 0 = round-robin
   int flat_group = 0;     // lanes per row of the flat kernel (0 = like the staged kernel)
-  int flat_gen = 0;       // 1: second-generation flat kernel (cheby_flat2_kernel: cache-hint / layout variants)
-  int flat_hint = 0;      // cheby_flat2_kernel HINT (0..3), see cheby.cu
-  int flat_layout = 0;    // cheby_flat2_kernel LAYOUT (0: 4 consecutive entries per lane, 1: lane-consecutive)
+  int flat_gen = 1;       // 1: second-generation flat kernel (cheby_flat2_kernel), 0: the round-1 flat kernels
+  int flat_hint = -1;     // cheby_flat2_kernel HINT (0..3, see cheby.cu); -1: chosen from the signal width
+  int flat_layout = -1;   // cheby_flat2_kernel LAYOUT (0: 4 consecutive entries per lane, 1: lane-consecutive); -1: auto
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
   int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast

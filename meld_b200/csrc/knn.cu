@@ -415,6 +415,9 @@ __global__ void refine_dist_kernel(const double *__restrict__ X, int64_t row_beg
 }
 
 __device__ __forceinline__ double alpha_decay(double dist, double eps, double decay) {
+  // decay == 0 stands for the reference's decay=None: the unweighted kNN kernel (graphtools kNNGraph with
+  // decay=None -> kneighbors_graph(mode="connectivity")): 1 for the knn nearest (self included), else 0
+  if (decay == 0.0) return dist <= eps ? 1.0 : 0.0;
   double v = exp(-pow(dist / eps, decay));
   if (isnan(v)) v = 1.0;
   return v;
@@ -1035,7 +1038,11 @@ static int parse_build_params(const char *who, int64_t n, int64_t d, int knn, do
   MELD_REQUIRE(n < (int64_t)2000000000, "%s: n too large for int32 columns", who);
   MELD_REQUIRE(knn >= 1 && (int64_t)knn + 1 <= n, "%s: knn=%d with n=%lld", who, knn, (long long)n);
   MELD_REQUIRE(knn + 1 <= kMaxK1, "%s: knn + 1 = %d exceeds the engine limit %d", who, knn + 1, kMaxK1);
-  MELD_REQUIRE(decay > 0 && isfinite(decay), "%s: decay=%g (decay=None is not supported)", who, decay);
+  MELD_REQUIRE(decay >= 0 && isfinite(decay), "%s: decay=%g (pass 0 for the reference's decay=None)", who, decay);
+  if (decay == 0.0) {  // binary kNN kernel: the bandwidth is the knn-th neighbour itself, nothing to threshold
+    thresh = 0.5;
+    bandwidth_scale = 1.0;
+  }
   MELD_REQUIRE(thresh > 0 && thresh < 1, "%s: thresh=%g outside (0, 1)", who, thresh);
   MELD_REQUIRE(anisotropy >= 0 && anisotropy <= 1, "%s: anisotropy=%g outside [0, 1]", who, anisotropy);
   MELD_REQUIRE(bandwidth_scale > 0, "%s: bandwidth_scale=%g", who, bandwidth_scale);
@@ -1045,7 +1052,7 @@ static int parse_build_params(const char *who, int64_t n, int64_t d, int knn, do
   bp->anisotropy = anisotropy;
   bp->bandwidth_scale = bandwidth_scale;
   bp->thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
-  const double rho = pow(-log(bp->thresh_eff), 1.0 / decay);  // kernel radius in units of eps_i
+  const double rho = decay == 0.0 ? 1.0 : pow(-log(bp->thresh_eff), 1.0 / decay);  // kernel radius in units of eps_i
   bp->radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
   if (bp->radius_factor < 1.0) bp->radius_factor = 1.0;  // the k1 nearest must be candidates to get eps_i
   bp->simt = (flags & MELD_B200_FLAG_SIMT_SEARCH) != 0;
@@ -1270,6 +1277,51 @@ int meld_b200_knn_graph_build(const double *X, int64_t n, int64_t d, int knn, do
   return 0;
 }
 
+// every cell is a candidate of every row (dense graphs): cand[i * n + j] = j
+__global__ void dense_candidates_kernel(int64_t n, int64_t *__restrict__ cptr, int32_t *__restrict__ cand) {
+  const int64_t total = n * n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+    cand[t] = (int32_t)(t % n);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x)
+    cptr[i] = i * n;
+}
+
+int meld_b200_dense_graph_build(const double *X, int64_t n, int64_t d, int knn, double decay, double anisotropy,
+                                double bandwidth_scale, int flags, void *stream_, meld_b200_graph_t **graph_out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  meld::ArenaScope arena_scope(stream);
+  MELD_REQUIRE(graph_out != nullptr && X != nullptr, "dense_graph_build: NULL argument");
+  *graph_out = nullptr;
+  MELD_REQUIRE(n <= 16384, "dense_graph_build: n=%lld; the dense exact graph (thresh = 0) is for n <= 16384",
+               (long long)n);
+  MELD_REQUIRE(decay > 0, "dense_graph_build: decay=%g", decay);
+  BuildParams bp;
+  MELD_CHECK(parse_build_params("dense_graph_build", n, d, knn, decay, 0.5, anisotropy, bandwidth_scale, flags, &bp));
+  bp.thresh_eff = 4.9406564584124654e-324;  // thresh = 0: every pair whose kernel value has not underflowed to 0
+  DevBuf<int64_t> cptr;
+  DevBuf<int32_t> cand, noperm;
+  DevBuf<double> d2, eps;
+  DevBuf<int> err;
+  MELD_CHECK(cptr.alloc((size_t)n + 1));
+  MELD_CHECK(cand.alloc((size_t)n * n));
+  MELD_CHECK(d2.alloc((size_t)n * n));
+  MELD_CHECK(eps.alloc((size_t)n));
+  MELD_CHECK(err.alloc(1));
+  MELD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
+  dense_candidates_kernel<<<sm_count() * 8, 256, 0, stream>>>(n, cptr.p, cand.p);
+  MELD_LAUNCH_CHECK();
+  refine_dist_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(X, 0, n, d, cand.p, cptr.p, bp.k1, bp.bandwidth_scale, d2.p,
+                                                           eps.p, err.p);
+  MELD_LAUNCH_CHECK();
+  meld_b200_graph *g = nullptr;
+  MELD_CHECK(build_stage2(n, cptr.p, cand.p, d2.p, n * n, eps.p, bp, noperm, stream, &g));
+  g->stats[0] = 0;  // no search passes
+  g->stats[1] = n;
+  *graph_out = g;
+  return 0;
+}
+
 int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, double decay, double thresh,
                              double bandwidth_scale, int64_t row_begin, int64_t row_end, int flags, void *stream_,
                              meld_b200_cands_t **cands_out) {
@@ -1414,7 +1466,7 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   MELD_REQUIRE(X && key2_out && cnt_out && n >= 2 && d >= 1 && knn >= 1 && knn + 1 <= n && knn + 1 <= kMaxK1,
                "debug_candidate_search: bad argument");
   const double thresh_eff = thresh > DBL_EPSILON ? thresh : DBL_EPSILON;
-  const double rho = pow(-log(thresh_eff), 1.0 / decay);
+  const double rho = decay == 0.0 ? 1.0 : pow(-log(thresh_eff), 1.0 / decay);
   double radius_factor = rho * rho * bandwidth_scale * bandwidth_scale;
   if (radius_factor < 1.0) radius_factor = 1.0;
   Candidates cs;

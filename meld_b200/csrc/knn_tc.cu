@@ -33,7 +33,7 @@ constexpr int kABytes = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;   // 32 KB
 constexpr int kMaxResidentKb = 6;      // A resident up to K' = 384
 constexpr float kPadSentinel = -1e30f;
-constexpr int kQueueCap = 128;          // pass 2: per-warp queue of hit pairs (flushed when half full)
+constexpr int kQueueCap = 256;          // pass 2: per-warp queue of hit pairs (flushed when the next chunk would not fit)
 
 // ---- operand preparation ------------------------------------------------------------------------
 __global__ void tc_prep_kernel(const double *__restrict__ X, const double *__restrict__ mu,
@@ -447,26 +447,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       } else {
         thr = row < a.row_end ? a.key2[row] : INFINITY;
       }
-      // pass 2: hits are queued per warp in shared memory and appended to the global pair buffer 32+ at a
-      // time (one global atomic per flush), so the scan never waits on an atomic's round trip per hit
+      // pass 2: hits are queued per warp in shared memory and appended to the global pair buffer in bulk (one
+      // global atomic per flush).  The queue length lives in a warp-uniform register: a chunk's hits are placed by
+      // a warp prefix sum over the per-lane hit counts -- ONE reservation per warp per chunk, no shared-memory atomic
+      // (round 1 did atomicAdd(wqn, 1) per hit: 32 lanes on one bank, 71 % of the kernel's shared wavefronts were
+      // bank conflicts, profiles/r01d_ncu_tc_search_pruned_c4.txt).
       unsigned long long *wq = reinterpret_cast<unsigned long long *>(lst) + (size_t)(warp - 2) * kQueueCap;
-      int *wqn = reinterpret_cast<int *>(reinterpret_cast<unsigned long long *>(lst) + kEpiWarps * kQueueCap) + (warp - 2);
-      if (a.mode == 2) {
-        if (lane == 0) *wqn = 0;
-        __syncwarp();
-      }
+      int qn = 0;  // warp-uniform
       auto flush_queue = [&]() {  // warp-uniform
         __syncwarp();
-        int nq = *wqn;
-        if (nq > kQueueCap) nq = kQueueCap;
-        unsigned long long base = 0;
-        if (lane == 0 && nq > 0) base = atomicAdd(a.count, (unsigned long long)nq);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int i = lane; i < nq; i += 32)
-          if ((long long)(base + i) < a.cap) a.pairs[base + i] = wq[i];
+        if (qn > 0) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(a.count, (unsigned long long)qn);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          for (int i = lane; i < qn; i += 32)
+            if ((long long)(base + i) < a.cap) a.pairs[base + i] = wq[i];
+        }
         __syncwarp();
-        if (lane == 0) *wqn = 0;
-        __syncwarp();
+        qn = 0;
       };
       for (int j = 0; j < up.len; ++j) {
         const int ct = up.tile(j);
@@ -532,25 +530,43 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               }
             }
           } else {
-            if (mx >= thr) {
+            // warp-uniform vote first: most chunks of a surviving tile hold no hit for any of the 32 rows
+            if (__ballot_sync(0xffffffffu, mx >= thr) != 0u) {
               unsigned m = 0;
+              if (mx >= thr) {
 #pragma unroll  // branch-free hit mask (static register indices)
-              for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[c]) >= thr) ? (1u << c) : 0u;
-              while (m) {
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned long long key = ((unsigned long long)row << 32) | (unsigned long long)(col0 + c);
-                const int slot = atomicAdd(wqn, 1);
-                if (slot < kQueueCap) {
-                  wq[slot] = key;
-                } else {  // queue full inside one chunk (dense hits): append directly
-                  const unsigned long long pos = atomicAdd(a.count, 1ull);
-                  if ((long long)pos < a.cap) a.pairs[pos] = key;
+                for (int c = 0; c < 32; ++c) m |= (__uint_as_float(v[c]) >= thr) ? (1u << c) : 0u;
+              }
+              const int cnt = __popc(m);
+              int pre = cnt;  // inclusive prefix sum of the lanes' hit counts
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += t;
+              }
+              const int total = __shfl_sync(0xffffffffu, pre, 31);
+              pre -= cnt;
+              if (total > kQueueCap) {  // dense chunk: straight to the pair buffer, still one reservation per warp
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.count, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)pre;
+                while (m) {
+                  const int c = __ffs(m) - 1;
+                  m &= m - 1;
+                  if ((long long)base < a.cap) a.pairs[base] = ((unsigned long long)row << 32) | (unsigned long long)(col0 + c);
+                  ++base;
                 }
+              } else {
+                if (qn + total > kQueueCap) flush_queue();
+                int pos = qn + pre;
+                while (m) {
+                  const int c = __ffs(m) - 1;
+                  m &= m - 1;
+                  wq[pos++] = ((unsigned long long)row << 32) | (unsigned long long)(col0 + c);
+                }
+                qn += total;
               }
             }
-            __syncwarp();
-            if (*wqn >= kQueueCap / 2) flush_queue();
           }
         };
         uint32_t va[32], vb[32];

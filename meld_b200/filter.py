@@ -50,12 +50,15 @@ def filter(signal, graph, filter, beta, offset=0, order=1, solver="chebyshev", c
     if not isinstance(graph, DeviceGraph):
         raise TypeError("graph must be a meld_b200.DeviceGraph")
     h = filter_kernel(filter, beta, offset, order)  # NotImplementedError for unknown kernels
-    if solver != "chebyshev":
-        raise NotImplementedError(
-            "solver='{}' is not available in the B200 engine (dense O(N^3) eigendecomposition); "
-            "use solver='chebyshev'".format(solver)
-        )
     torch = nv.require_cuda()
+    if solver == "exact":
+        on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
+        S = _as_device_f64(torch, signal)
+        R = exact_apply(graph, h, S[:, None] if S.dim() == 1 else S)
+        R = R[:, 0] if S.dim() == 1 else R
+        return R if on_device else R.cpu().numpy()
+    if solver != "chebyshev":
+        raise ValueError("solver value {} not recognized. Choose from ['chebyshev', 'exact']".format(solver))
     lmax = graph.estimate_lmax()
     coeffs = np.ascontiguousarray(cheby_coefficients(h, lmax, int(chebyshev_order)), dtype=np.float64)
     on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
@@ -125,3 +128,20 @@ def cheby_sweep(graph, lmax, coeff_matrix, S):
         if Rj is not out:
             out[:, :, j:j + pj] = Rj
     return out
+
+
+def exact_apply(graph, h, S):
+    """``solver="exact"`` (PyGSP ``Filter.filter(method="exact")`` reached from ``meld/filter.py:59``):
+    ``U h(e / lmax) U^T S`` with the full eigendecomposition of L.  PyGSP's ``compute_fourier_basis`` clears the
+    rounding of the zero eigenvalue and OVERWRITES lmax with the largest eigenvalue (no 1.01 factor), which is what
+    the reference's filter closure then reads (SURVEY finding 7).  Test-scale only (N <= 16384): the dense ``eigh``
+    and the two GEMMs are library calls (cuSOLVER / cuBLAS through torch), not kernels of this engine."""
+    torch = nv.require_cuda()
+    Ld = graph.to_dense_L()
+    e, U = torch.linalg.eigh(Ld)
+    if abs(float(e[0])) < 1e-12:
+        e[0] = 0.0
+    lmax = float(e[-1])
+    graph.lmax = lmax  # like PyGSP, the graph's lmax is now the exact one
+    hv = torch.from_numpy(np.asarray(h(e.cpu().numpy() / lmax), dtype=np.float64)).to(S.device)
+    return U @ (hv[:, None] * (U.T @ S))

@@ -49,6 +49,7 @@ class DeviceGraph:
             raise ValueError("Expected a 2D matrix. Got shape {}".format(tuple(X.shape)))
         N, d = X.shape
         knn = _clamp_knn(knn, N)
+        decay = 0.0 if decay is None else decay  # C-ABI: 0 = the reference's decay=None (binary kNN kernel)
         flags = (nv.FLAG_KEEP_KNN_KERNEL if keep_knn_kernel else 0) | (nv.FLAG_SIMT_SEARCH if simt_search else 0)
         out = C.c_void_p()
         nv.check(
@@ -60,6 +61,56 @@ class DeviceGraph:
         )
         params = dict(knn=knn, decay=decay, thresh=thresh, anisotropy=anisotropy, bandwidth_scale=bandwidth_scale)
         return cls(out.value, params, device=X.device)
+
+    @classmethod
+    def from_data_dense(cls, data_nu, knn=5, decay=40.0, anisotropy=1.0, bandwidth_scale=1.0, keep_knn_kernel=False):
+        """``graphtools.Graph(..., thresh=0)``: the dense "exact" graph (TraditionalGraph) -- the same kernel for
+        every pair of cells whose value has not underflowed to zero.  Test-scale only (N <= 16384); it is what the
+        reference's own known-answer test builds (``test/test_meld.py:58-67``)."""
+        torch = nv.require_cuda()
+        X = _as_device_f64(torch, data_nu)
+        if X.dim() != 2:
+            raise ValueError("Expected a 2D matrix. Got shape {}".format(tuple(X.shape)))
+        N, d = X.shape
+        knn = _clamp_knn(knn, N)
+        if decay is None:
+            raise ValueError("the dense exact graph needs a decay (decay=None selects the binary kNN kernel)")
+        out = C.c_void_p()
+        nv.check(
+            nv.lib().meld_b200_dense_graph_build(nv.ptr(X), N, d, int(knn), float(decay), float(anisotropy),
+                                                 float(bandwidth_scale), nv.FLAG_KEEP_KNN_KERNEL if keep_knn_kernel else 0,
+                                                 nv.current_stream_ptr(), C.byref(out)),
+            "dense_graph_build",
+        )
+        params = dict(knn=knn, decay=decay, thresh=0, anisotropy=anisotropy, bandwidth_scale=bandwidth_scale)
+        return cls(out.value, params, device=X.device)
+
+    def to_dense_L(self):
+        """L as a dense (N, N) float64 CUDA tensor in the CALLER's cell order (exact solver, N <= 16384)."""
+        torch = nv.require_cuda()
+        if self.n_rows != self.n_cols or self.row0 != 0:
+            raise ValueError("needs the full operator")
+        if self.n_cols > 16384:
+            raise NotImplementedError(
+                "solver='exact' needs the dense eigendecomposition of L (O(N^3)); it is limited to N <= 16384 "
+                "(got {}); use solver='chebyshev'".format(self.n_cols))
+        dev = self.device
+        indptr = torch.empty(self.n_rows + 1, dtype=torch.int64, device=dev)
+        indices = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        data = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=dev)
+        nv.check(nv.lib().meld_b200_graph_export_csr(self._h, nv.ptr(indptr), nv.ptr(indices), nv.ptr(data),
+                                                     nv.current_stream_ptr()), "graph_export_csr")
+        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=dev), indptr[1:] - indptr[:-1])
+        cols = indices[: self.nnz].long()
+        ident = C.c_int(1)
+        perm = torch.empty(self.n_rows, dtype=torch.int32, device=dev)
+        nv.check(nv.lib().meld_b200_graph_permutation(self._h, nv.ptr(perm), C.byref(ident), nv.current_stream_ptr()),
+                 "graph_permutation")
+        if not ident.value:
+            rows, cols = perm.long()[rows], perm.long()[cols]
+        Ld = torch.zeros((self.n_rows, self.n_cols), dtype=torch.float64, device=dev)
+        Ld[rows, cols] = data[: self.nnz]
+        return Ld
 
     # ---- sharded construction (one process per GPU) ------------------------------------------------
     @staticmethod
@@ -149,6 +200,7 @@ class DeviceGraph:
         X = _as_device_f64(torch, data_nu)
         N, d = X.shape
         knn = _clamp_knn(knn, N)
+        decay = 0.0 if decay is None else decay
         bounds = cls.shard_bounds(N, world)
         lap("input to device")
         counts, cand, d2, eps, perm = cls.candidates(X, bounds[rank], bounds[rank + 1], knn, decay, thresh,

@@ -60,8 +60,8 @@ class MELD(object):
     filter : str, optional, Default: 'heat'
         'heat' or 'laplacian'.
     solver : str, optional, Default: 'chebyshev'
-        Only 'chebyshev' runs on the B200 engine; 'exact' is validated but raises
-        NotImplementedError at transform time.
+        'chebyshev' is the engine's hot path; 'exact' (dense eigendecomposition, library ``eigh``) is
+        available for test-scale graphs (N <= 16384), e.g. the reference's own known-answer test.
     chebyshev_order : int, optional, Default: 50
     lap_type : ('combinatorial', 'normalized'), Default: 'combinatorial'
         Validated and stored; like the reference it is never forwarded to the graph,
@@ -210,10 +210,8 @@ class MELD(object):
     def _check_supported(self, extra):
         if self.distance != "euclidean":
             raise NotImplementedError("distance='{}': only 'euclidean' runs on the B200 engine".format(self.distance))
-        if self.decay is None:
-            raise NotImplementedError("decay=None (unweighted kNN kernel) is not available in the B200 engine")
-        if not (self.thresh > 0):
-            raise NotImplementedError("thresh=0 selects graphtools' dense exact graph; the B200 engine needs thresh > 0")
+        if self.thresh < 0:
+            raise ValueError("Expected thresh >= 0, got {}".format(self.thresh))
         if self.n_landmark is not None:
             raise NotImplementedError("landmark graphs are not available in the B200 engine")
         known = {"bandwidth_scale"}
@@ -274,13 +272,19 @@ class MELD(object):
         data_nu = self._reduce_data(X)
         self._log("Calculating graph and diffusion operator...")
         t1 = time.perf_counter()
-        build = DeviceGraph.from_data
-        if self.distributed:  # candidate search sharded over the ranks of torch.distributed (same data on every rank)
-            build = DeviceGraph.from_data_sharded
-        self.graph = build(
-            data_nu, knn=self.knn, decay=self.decay, thresh=self.thresh, anisotropy=self.anisotropy,
-            bandwidth_scale=extra.get("bandwidth_scale", 1.0),
-        )
+        if self.thresh == 0 and self.decay is not None:
+            # graphtools.api.Graph: thresh == 0 with a decay selects the dense "exact" graph (TraditionalGraph)
+            self.graph = DeviceGraph.from_data_dense(data_nu, knn=self.knn, decay=self.decay, anisotropy=self.anisotropy,
+                                                     bandwidth_scale=extra.get("bandwidth_scale", 1.0))
+        else:
+            build = DeviceGraph.from_data
+            if self.distributed:  # candidate search sharded over the ranks of torch.distributed (same data everywhere)
+                build = DeviceGraph.from_data_sharded
+            self.graph = build(
+                data_nu, knn=self.knn, decay=0.0 if self.decay is None else self.decay, thresh=self.thresh,
+                anisotropy=self.anisotropy,
+                bandwidth_scale=extra.get("bandwidth_scale", 1.0),
+            )
         if self._sharded is not None:
             self._sharded.close()
             self._sharded = None
@@ -385,10 +389,6 @@ class MELD(object):
         self._indicators = None  # rebuilt lazily by the sample_indicators property
 
         _filter.filter_kernel(self.filter, self.beta, self.offset, self.order)
-        if self.solver != "chebyshev":
-            raise NotImplementedError(
-                "solver='{}' is not available in the B200 engine; use solver='chebyshev'".format(self.solver)
-            )
         t0 = time.perf_counter()
         dev = self.graph.device
         d_codes = torch.from_numpy(codes).to(dev, non_blocking=True)
@@ -415,10 +415,6 @@ class MELD(object):
                 "are not of the same size".format(tuple(codes.shape), self.graph.N)
             )
         _filter.filter_kernel(self.filter, self.beta, self.offset, self.order)
-        if self.solver != "chebyshev":
-            raise NotImplementedError(
-                "solver='{}' is not available in the B200 engine; use solver='chebyshev'".format(self.solver)
-            )
         codes = codes.to(torch.int32).contiguous()
         S = torch.empty((codes.shape[0], int(n_samples)), dtype=torch.float64, device=codes.device)
         nv.check(
@@ -427,14 +423,14 @@ class MELD(object):
             "indicator_matrix",
         )
         events = self.profile_events
-        if events is not None:
+        if events is not None and self.solver == "chebyshev":
             self.graph.estimate_lmax()  # keep the Lanczos launches out of the filter bracket
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         densities = _filter.filter(
             signal=S, graph=self.graph, filter=self.filter, beta=self.beta, offset=self.offset, order=self.order,
             solver=self.solver, chebyshev_order=self.chebyshev_order,
-            apply=self._sharded.apply if self._sharded is not None else None,
+            apply=self._sharded.apply if (self._sharded is not None and self.solver == "chebyshev") else None,
         )
         if events is not None:
             e1.record()

@@ -85,6 +85,8 @@ def exact_filter(L, signal, filter="heat", beta=60, offset=0, order=1):
     """``solver='exact'``: PyGSP ``compute_fourier_basis`` overwrites lmax with the
     true largest eigenvalue (no 1.01 factor) before the kernel is evaluated."""
     e, U = np.linalg.eigh(L.toarray() if sparse.issparse(L) else np.asarray(L))
+    if -1e-12 < e[0] < 1e-12:  # compute_fourier_basis: "smallest eigenvalue should be zero: correct numerical errors"
+        e[0] = 0
     lmax = e[-1]
     h = filter_kernel(filter, beta, offset, order)
     return U @ (h(e / lmax)[:, None] * (U.T @ np.asarray(signal, dtype=np.float64)))

@@ -64,6 +64,12 @@ def knn_kernel(
     knn_arg = knn + 1  # build_kernel passes knn + 1 (self is its own neighbour)
     if knn_arg > N:
         raise ValueError("knn + 1 = {} exceeds the number of cells {}".format(knn_arg, N))
+    if decay is None or thresh == 1:
+        # kNNGraph.build_kernel_to_data, binary branch: unweighted connectivity of the knn + 1 nearest (self included)
+        tree = NearestNeighbors(n_neighbors=knn_arg, algorithm=algorithm, n_jobs=n_jobs).fit(data)
+        K = tree.kneighbors_graph(data, n_neighbors=knn_arg, mode="connectivity").tocsr()
+        K.sort_indices()
+        return (K, {}) if return_stats else K
     thresh = max(thresh, EPS)  # kNNGraph.__init__: thresh == 0 with decay -> eps
     knn_max = N  # knn_max=None upstream means "no cap"
 

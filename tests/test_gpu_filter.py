@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 
 DEFAULT_X_MODE = 2  # the shipped kernel variant (common.cuh Tuning::x_mode)
 DEFAULT_FLAT_PIPE = 2
-DEFAULT_FLAT_GEN = 0
-DEFAULT_FLAT_HINT = 0
+DEFAULT_FLAT_GEN = 1
+DEFAULT_FLAT_HINT = -1
+DEFAULT_FLAT_LAYOUT = -1
 
 RTOL = 1e-5  # north_star tolerance
 TIGHT = 1e-9  # what the fp64 kernel should actually deliver
@@ -208,8 +209,8 @@ def test_api_contract_on_device(mb):
     assert op.sample_densities is not None
     op.set_params(knn=op.knn + 1)
     assert op.graph is None and op.sample_densities is None
-    with pytest.raises(NotImplementedError):
-        mb.MELD(verbose=0, solver="exact").fit(graph).transform(labels)
+    exact = mb.MELD(verbose=0, solver="exact").fit(graph).transform(labels)  # test-scale dense path
+    assert exact.shape == dens.shape
 
 
 @pytest.mark.parametrize("tuning", [
@@ -220,8 +221,8 @@ def test_api_contract_on_device(mb):
     dict(x_mode=2), dict(x_mode=2, flat_threads=768, flat_group=4), dict(x_mode=2, flat_group=16), dict(x_mode=2, flat_group=32),  # flat kernel
     dict(x_mode=0),                                        # the dictionary-staged kernel
     dict(flat_pipe=1), dict(flat_pipe=1, flat_threads=768), dict(flat_pipe=0),  # software-pipelined flat kernel
-    dict(flat_gen=1), dict(flat_gen=1, flat_hint=1), dict(flat_gen=1, flat_hint=2), dict(flat_gen=1, flat_hint=3),
-    dict(flat_gen=1, flat_layout=1), dict(flat_gen=1, flat_hint=1, flat_layout=1),  # second-generation flat kernel
+    dict(flat_gen=0), dict(flat_gen=1, flat_hint=0, flat_layout=0), dict(flat_gen=1, flat_hint=2, flat_layout=1),
+    dict(flat_gen=1, flat_hint=3, flat_layout=0),  # round-1 flat kernel / explicit variants of the second generation
 ])
 def test_filter_kernel_variants_agree(mb, tuning):
     """Every launch configuration of the Chebyshev kernel computes the same filter (1e-12)."""
@@ -231,7 +232,7 @@ def test_filter_kernel_variants_agree(mb, tuning):
     defaults = dict(blk_chunk=768, stage_cap=1024, dict_cap=768, row_cap=64, n_stage=0, threads=512, gather_warps=3,
                     team_warps=4, gather_rows=0, ctas_per_sm=1, group=0, use_dict=1, x_mode=DEFAULT_X_MODE, flat_threads=1024,
                     flat_group=0, flat_pipe=DEFAULT_FLAT_PIPE, flat_gen=DEFAULT_FLAT_GEN, flat_hint=DEFAULT_FLAT_HINT,
-                    flat_layout=0)
+                    flat_layout=DEFAULT_FLAT_LAYOUT)
     g = load_golden("blobs2k5_wagner")
     S = np.random.default_rng(9).normal(size=(g["L"].shape[0], 4))
     ref = cheby.cheby_filter(g["L"], g["lmax"], S, "heat", beta=60, chebyshev_order=32)
@@ -257,14 +258,14 @@ def test_flat2_variants_all_widths(mb, p):
     S = np.random.default_rng(40 + p).normal(size=(g["L"].shape[0], p))
     ref = cheby.cheby_filter(g["L"], g["lmax"], S, "heat", beta=45, chebyshev_order=24)
     try:
-        for hint, layout in [(0, 0), (1, 0), (2, 0), (3, 0), (0, 1), (1, 1)]:
+        for hint, layout in [(0, 0), (1, 0), (2, 0), (3, 0), (0, 1), (1, 1), (2, 1), (3, 1), (-1, -1)]:
             nv.set_tuning(flat_gen=1, flat_hint=hint, flat_layout=layout)
             graph = mb.DeviceGraph.from_scipy(g["L"])
             graph.lmax = g["lmax"]
             out = mb.filter.filter(S, graph, "heat", beta=45, solver="chebyshev", chebyshev_order=24)
             assert np.abs(out - ref).max() <= 1e-11 * np.abs(ref).max(), (hint, layout)
     finally:
-        nv.set_tuning(flat_gen=DEFAULT_FLAT_GEN, flat_hint=DEFAULT_FLAT_HINT, flat_layout=0)
+        nv.set_tuning(flat_gen=DEFAULT_FLAT_GEN, flat_hint=DEFAULT_FLAT_HINT, flat_layout=DEFAULT_FLAT_LAYOUT)
 
 
 def test_transform_sweep_matches_looping_the_oracle(mb):
@@ -374,3 +375,48 @@ def test_peer_store_filter_ranks_in_one_process(mb, world):
             assert _close(outs[r], ref), (rep, r)
     for h in ctxs:
         lib.meld_b200_dist_destroy(h)
+
+
+@pytest.mark.parametrize("filt", ["heat", "laplacian"])
+def test_reference_kat_532_on_the_product(mb, filt):
+    """The reference's own numeric known-answer (test/test_meld.py:43-81), run against the PRODUCT: dense graph
+    (thresh=0 -> graphtools TraditionalGraph), exact solver, sum of the 'treat' densities == 532."""
+    cheby, og, omeld = _oracle()
+    np.random.seed(42)
+    data = np.random.normal(0, 2, (1000, 2))
+    sample_labels = np.random.choice(["treat", "ctrl"], size=data.shape[0])
+    op = mb.MELD(knn=20, decay=10, thresh=0, anisotropy=0, filter=filt, solver="exact", sample_normalize=False, verbose=0)
+    dens = op.fit_transform(data, sample_labels)
+    assert list(dens.columns) == ["ctrl", "treat"]
+    np.testing.assert_allclose(np.sum(dens.iloc[:, 1]), 532)  # the reference's assertion, default rtol 1e-7
+    np.testing.assert_allclose(np.sum(dens.iloc[:, 0]), 468)
+    # and the whole density matrix against the oracle's restatement of that path
+    K = og.traditional_kernel(data, knn=20, decay=10.0, thresh=0.0)
+    Lref = og.laplacian(og.weights_from_kernel(og.apply_anisotropy(og.symmetrize(K), 0)))
+    L = op.graph.to_scipy_L()
+    assert np.abs((L - Lref)).max() <= 1e-12 * np.abs(Lref.data).max()
+    ref = omeld.transform(Lref, None, sample_labels, filter=filt, solver="exact", sample_normalize=False)
+    assert np.abs(dens.values - ref.values).max() <= 1e-9 * np.abs(ref.values).max()
+    # reset semantics of the same reference test (:83-93)
+    op.set_params(beta=op.beta + 1)
+    assert op.sample_densities is None
+    op.transform(sample_labels)
+    op.set_params(knn=op.knn + 1)
+    assert op.graph is None
+
+
+def test_decay_none_binary_knn_kernel(mb):
+    """decay=None: the unweighted kNN kernel (graphtools kNNGraph, binary branch) -> same Laplacian and densities as
+    the oracle's kneighbors_graph path."""
+    _, og, omeld = _oracle()
+    X, labels = mb.synthetic.make_blobs(3000, 25, 5, 3, 7.0, seed=17)
+    ref, g, lmax = omeld.fit_transform(X, labels, knn=8, decay=None, n_pca=None)
+    op = mb.MELD(verbose=0, knn=8, decay=None, n_pca=None)
+    op.fit(X)
+    L = op.graph.to_scipy_L()
+    assert L.nnz == g["L"].nnz and np.array_equal(L.indptr, g["L"].indptr) and np.array_equal(L.indices, g["L"].indices)
+    assert np.abs(L.data - g["L"].data).max() <= 1e-12 * np.abs(g["L"].data).max()
+    op.graph.lmax = lmax
+    dens = op.transform(labels)
+    normwise, ok = density_parity(dens.values, ref.values, RTOL)
+    assert ok and normwise < TIGHT

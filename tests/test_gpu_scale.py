@@ -52,7 +52,9 @@ def test_full_size_run_matches_oracle_digest(mb, name):
     # density gate with the oracle's lmax injected; the engine's own lmax is reported alongside
     own = op.graph.estimate_lmax()
     lmax = float(z["lmax"])
-    assert abs(own - lmax) <= 3e-4 * lmax, (own, lmax)
+    # the oracle's value is ARPACK at tol = 5e-3 (the reference's own setting): a LOWER bound that may sit a few
+    # 1e-3 below the converged eigenvalue the engine's Lanczos reaches (config 3: 2.9e-3)
+    assert -1e-6 * lmax <= own - lmax <= 6e-3 * lmax, (own, lmax)
     op.graph.lmax = lmax
     dens = op.transform(y)
     assert list(dens.columns) == list(z["samples"])
