@@ -152,7 +152,8 @@ int meld_b200_graph_destroy(meld_b200_graph_t *g);
 
 /* Stands in for pygsp Graph.estimate_lmax() (reference meld/filter.py:39):
  * Lanczos on L, returns 1.01 * largest Ritz value (the reference's 1.01 factor).
- * Converged to `rel_tol` or `max_iters`, whichever first.  Synchronous.
+ * Stops when the bound min(r, r^2 / gap) of the Ritz value's error (r = Ritz residual, gap = distance to the
+ * second Ritz value; Kato-Temple) is below rel_tol * theta (default 1e-5), or at max_iters.  Synchronous.
  * Only for full (row0 == 0, n_rows == n_cols) graphs.                            */
 int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol, void *stream,
                             double *lmax_host, int *iters_host);

@@ -108,7 +108,6 @@ class PeerContext:
     """This rank's peer-memory block (``meld_b200_dist_t``), connected to the blocks of all ranks of the group."""
 
     def __init__(self, n_rows_total, p_max=8, group=None):
-        import torch
         import torch.distributed as dist
 
         from . import _native as nv
@@ -128,11 +127,9 @@ class PeerContext:
             nb = lib.meld_b200_dist_handle_bytes()
             blob = (C.c_ubyte * nb)()
             nv.check(lib.meld_b200_dist_export(self._h, blob), "dist_export")
-            dev = torch.device("cuda", torch.cuda.current_device())
-            mine = torch.tensor(list(bytes(blob)), dtype=torch.uint8, device=dev)
-            allb = torch.empty(self.world * nb, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(allb, mine, group=group)  # plumbing: 64 bytes per rank, once
-            raw = bytes(allb.cpu().numpy().tobytes())
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, bytes(blob), group=group)  # plumbing: 64 bytes per rank, once
+            raw = b"".join(blobs)
             buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
             nv.check(lib.meld_b200_dist_connect(self._h, buf), "dist_connect")
             dist.barrier(group=group)  # every rank has mapped every block before anyone stores into one

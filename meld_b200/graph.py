@@ -411,17 +411,50 @@ def _clamp_knn(knn, N):
     return int(knn)
 
 
+_STAGE_BYTES = 32 << 20  # pinned staging buffer of the pageable-input copy pipeline
+_stage_bufs = []
+
+
+def _pageable_to_device(torch, t):
+    """Host tensor in PAGEABLE memory -> device, through a 3-deep ring of pinned staging buffers: the (multi-threaded)
+    host copy of chunk i + 1 into a staging buffer overlaps the DMA of chunk i.  A plain ``.cuda()`` of pageable
+    memory lets the driver stage it on one thread (~15 GB/s); this is the drop-in case -- users hand over ordinary
+    numpy arrays."""
+    flat = t.reshape(-1)
+    n = flat.numel()
+    per = max(1, _STAGE_BYTES // flat.element_size())
+    out = torch.empty(n, dtype=flat.dtype, device="cuda")
+    while len(_stage_bufs) < 3:
+        _stage_bufs.append([torch.empty(_STAGE_BYTES, dtype=torch.uint8).pin_memory(), None])
+    stream = torch.cuda.current_stream()
+    for i, s in enumerate(range(0, n, per)):
+        e = min(n, s + per)
+        slot = _stage_bufs[i % 3]
+        if slot[1] is not None:
+            slot[1].synchronize()  # the DMA that last read this staging buffer has finished
+        stage = slot[0].view(flat.dtype)[: e - s]
+        stage.copy_(flat[s:e])
+        out[s:e].copy_(stage, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        slot[1] = ev
+    return out.reshape(t.shape)
+
+
 def _as_device_f64(torch, x):
     """numpy / DataFrame / torch tensor -> contiguous float64 CUDA tensor."""
     if isinstance(x, torch.Tensor):
         t = x
-        if not t.is_cuda:
-            t = t.cuda(non_blocking=True)
     else:
         arr = np.asarray(getattr(x, "values", x))
         if arr.dtype != np.float64 and arr.dtype != np.float32:
             arr = arr.astype(np.float64)
-        t = torch.from_numpy(np.ascontiguousarray(arr)).cuda(non_blocking=True)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    if not t.is_cuda:
+        if t.is_contiguous() and t.numel() * t.element_size() >= (64 << 20) and not t.is_pinned():
+            t = _pageable_to_device(torch, t)
+        else:
+            t = t.cuda(non_blocking=True)
     if t.dtype != torch.float64:
         t = t.to(torch.float64)
     return t.contiguous()

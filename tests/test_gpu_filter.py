@@ -382,9 +382,17 @@ def test_reference_kat_532_on_the_product(mb, filt):
     """The reference's own numeric known-answer (test/test_meld.py:43-81), run against the PRODUCT: dense graph
     (thresh=0 -> graphtools TraditionalGraph), exact solver, sum of the 'treat' densities == 532."""
     cheby, og, omeld = _oracle()
-    np.random.seed(42)
+    np.random.seed(42)  # the reference's recipe, legacy global-seed RNG on purpose (test/test_meld.py:46-57)
+
+    def norm(x):
+        x = x.copy()
+        x = x - np.min(x)
+        x = x / np.max(x)
+        return x
+
     data = np.random.normal(0, 2, (1000, 2))
-    sample_labels = np.random.choice(["treat", "ctrl"], size=data.shape[0])
+    sample_labels = np.random.binomial(1, norm(data[:, 0]), 1000)
+    sample_labels = np.array(["treat" if val else "ctrl" for val in sample_labels])
     op = mb.MELD(knn=20, decay=10, thresh=0, anisotropy=0, filter=filt, solver="exact", sample_normalize=False, verbose=0)
     dens = op.fit_transform(data, sample_labels)
     assert list(dens.columns) == ["ctrl", "treat"]
