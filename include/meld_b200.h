@@ -223,6 +223,12 @@ int meld_b200_cheby_filter_dist(meld_b200_graph_t *slice, meld_b200_dist_t *d, d
                                 const double *coeffs_host, int n_coeffs, const double *S, int p, double *R,
                                 void *stream);
 
+/* meld_b200_estimate_lmax on a row-partitioned operator: every rank holds its rows (`slice`); per Lanczos step the
+ * ranks exchange their rows of the new vector by peer stores and two scalars (w.Lw, |w|^2) through rank-ordered
+ * slots in peer memory, so all ranks compute bit-identical coefficients and stop at the same step.           */
+int meld_b200_estimate_lmax_dist(meld_b200_graph_t *slice, meld_b200_dist_t *d, int max_iters, double rel_tol,
+                                 void *stream, double *lmax_host, int *iters_host);
+
 /* Frees the library-owned build arena (several GB after a large build; it is re-grown on the next build).  */
 int meld_b200_release_workspace(void);
 

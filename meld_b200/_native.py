@@ -59,6 +59,7 @@ SIGNATURES = {
     "meld_b200_dist_error": (C.c_int, [_vp, _pint]),
     "meld_b200_dist_destroy": (C.c_int, [_vp]),
     "meld_b200_cheby_filter_dist": (C.c_int, [_vp, _vp, _dbl, _pdbl, _i32, _vp, _i32, _vp, _vp]),
+    "meld_b200_estimate_lmax_dist": (C.c_int, [_vp, _vp, _i32, _dbl, _vp, _pdbl, _pint]),
     "meld_b200_release_workspace": (C.c_int, []),
     "meld_b200_indicator_matrix": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     "meld_b200_l1_normalize_rows": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),

@@ -116,6 +116,11 @@ struct StepArgs {
   int *err_flag;                        // set when a flag wait times out
   int n_peers, world, rank;
   int store_r;                          // last term: T_new / peer_tnew receive the finished R rows instead of T_k
+  int peer_store;                       // 0: T_new stays local (distributed Lanczos: only the scalar is published)
+  double *peer_scal[kMaxPeers];         // peers' scalar slots (4 x 8 doubles, ring indexed by epoch & 3)
+  double *my_scal;                      // this rank's scalar slots
+  const double *scal_partials;          // per-CTA partial sums whose total the last CTA publishes (or nullptr)
+  int n_scal_partials;
   unsigned long long wait_epoch;        // > 0: wait until every peer's flag >= wait_epoch before gathering
   unsigned long long post_epoch;        // > 0: value published to the peers when this launch's stores are done
 };
@@ -856,9 +861,27 @@ __device__ __forceinline__ void peer_post(const StepArgs &a) {
     if (prev == gridDim.x - 1) {
       *a.done_ctr = 0;  // the next launch starts after this one has ended
       __threadfence_system();
+      if (a.scal_partials != nullptr) {
+        // this rank's partial sum (CTA partials added in a fixed order) goes into slot [epoch & 3][rank] of every
+        // rank; all ranks then add the slots in rank order and obtain the same global sum bit for bit
+        double sum = 0.0;
+        for (int i = 0; i < a.n_scal_partials; ++i) sum += __ldcg(a.scal_partials + i);
+        const int slot = (int)(a.post_epoch & 3ull) * 8 + a.rank;
+        a.my_scal[slot] = sum;
+        for (int w = 0; w < a.n_peers; ++w) a.peer_scal[w][slot] = sum;
+        __threadfence_system();
+      }
       for (int w = 0; w < a.n_peers; ++w) st_release_sys(a.peer_flags[w], a.post_epoch);
     }
   }
+}
+
+// global sum published in phase `epoch`: the ranks' slots in rank order (call after peer_wait(epoch))
+__device__ __forceinline__ double peer_scalar_sum(const double *my_scal, int world, unsigned long long epoch) {
+  double s = 0.0;
+  const int base = (int)(epoch & 3ull) * 8;
+  for (int r = 0; r < world; ++r) s += __ldcg(my_scal + base + r);
+  return s;
 }
 
 template <int P, int TB, int HINT, int LAYOUT, bool DOT, bool PEER>
@@ -989,7 +1012,7 @@ __global__ void __launch_bounds__(TB, 1) cheby_flat2_kernel(const StepArgs a, co
       }
       if (a.Tnew) a.Tnew[li] = outv;  // gathered by the next step: keep cacheable
       if constexpr (PEER) {
-        if (a.Tnew) {
+        if (a.Tnew && a.peer_store) {
 #pragma unroll 1
           for (int w = 0; w < a.n_peers; ++w) a.peer_tnew[w][li] = outv;
         }
@@ -1076,9 +1099,9 @@ static FlatKernel pick_flat2_peer_h(int P) {
 static FlatKernel pick_flat2_peer(int P, int hint) {
   return hint >= 2 ? pick_flat2_peer_h<2>(P) : pick_flat2_peer_h<1>(P);
 }
-static FlatKernel pick_flat2_dot(int hint) {
+static FlatKernel pick_flat2_dot(int hint, bool peer) {
   (void)hint;
-  return cheby_flat2_kernel<1, 1024, 1, 1, true, false>;
+  return peer ? cheby_flat2_kernel<1, 1024, 1, 1, true, true> : cheby_flat2_kernel<1, 1024, 1, 1, true, false>;
 }
 
 // Measured on the 500k-cell graph of config 4 (tools/r02_probe.py, profiles/r02_probe_spmm_variants.txt): the cache
@@ -1139,7 +1162,8 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
   const bool g8 = (t.flat_group > 0 ? t.flat_group : G) == 8 || (t.flat_group <= 0 && G == 16);
   if ((g->x_mode == 2 && t.flat_gen == 1 && g8) || want_peer || want_dot) {  // second-generation flat kernel (8 lanes per row)
     const int hint = auto_hint(P, t.flat_hint), layout = auto_layout(P, t.flat_layout);
-    FlatKernel fk = want_peer ? pick_flat2_peer(P, hint) : (want_dot ? pick_flat2_dot(hint) : pick_flat2(P, hint, layout));
+    FlatKernel fk = want_dot ? pick_flat2_dot(hint, want_peer)
+                             : (want_peer ? pick_flat2_peer(P, hint) : pick_flat2(P, hint, layout));
     MELD_REQUIRE(fk != nullptr, "cheby_step: p=%d outside 1..8", P);
     MELD_REQUIRE(!want_dot || P == 1, "cheby_step: the fused dot product needs p = 1");
     a.row_ptr = g->row_ptr.p;
@@ -1152,6 +1176,7 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
     const int64_t groups = ceil_div(g->n_rows, 4);
     if ((int64_t)grid * 32 > groups) grid = (int)ceil_div(groups, 32);
     if (grid < 1) grid = 1;
+    if (a.scal_partials != nullptr) a.n_scal_partials = grid;  // one partial per CTA of this launch
     fk<<<grid, 1024, 0, stream>>>(a, g->n_rows);
     MELD_LAUNCH_CHECK();
     if (grid_out) *grid_out = grid;
@@ -1317,6 +1342,50 @@ __global__ void __launch_bounds__(kRedThreads) lanczos_axpy_kernel(const double 
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) pb_next[blockIdx.x] = s;
+}
+
+// Row-partitioned Lanczos step 2 (see meld_b200_estimate_lmax_dist): the dot product w_j . (L w_j) and |w_j|^2 are
+// the rank-ordered sums of the slots the ranks published in phases `dot_epoch` / `norm_epoch`; this rank updates
+// its rows of w_{j+1} (over w_{j-1}) in its own and in every peer's vector, and its last CTA publishes |w_{j+1}|^2
+// of its rows.  pb0: partials of the full |w_0|^2 (j == 0: every rank generated the whole start vector).
+__global__ void __launch_bounds__(kRedThreads) lanczos_axpy_peer_kernel(const StepArgs a, const double *__restrict__ y_loc,
+                                                                        const double *__restrict__ w_cur, double *w_prev,
+                                                                        int64_t row0, int64_t nloc,
+                                                                        unsigned long long dot_epoch,
+                                                                        unsigned long long norm_epoch, const double *pb0,
+                                                                        int j, double *alpha_arr, double *beta_arr,
+                                                                        double *pb_out) {
+  __shared__ double sh[33];
+  peer_wait(a.my_flags, a.world, a.rank, a.wait_epoch, a.err_flag);
+  const double dot = peer_scalar_sum(a.my_scal, a.world, dot_epoch);
+  const double b2 = j == 0 ? sum_partials(pb0, sh) : peer_scalar_sum(a.my_scal, a.world, norm_epoch);
+  const double beta = sqrt(b2);
+  const double beta_prev = j > 0 ? __ldcg(beta_arr + j - 1) : 1.0;
+  const double alpha = b2 > 0.0 ? dot / b2 : 0.0;
+  const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+  const double ratio = (j > 0 && beta_prev > 0.0) ? beta / beta_prev : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    alpha_arr[j] = alpha;
+    beta_arr[j] = beta;
+  }
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t gi = row0 + i;
+    const double x = (y_loc[i] - alpha * w_cur[gi]) * inv - ratio * w_prev[gi];
+    w_prev[gi] = x;
+    for (int w = 0; w < a.n_peers; ++w) a.peer_tnew[w][i] = x;  // peers' copies of this rank's rows
+    s = fma(x, x, s);
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) pb_out[blockIdx.x] = s;
+  peer_post(a);
+}
+
+// beta_arr[k] = |w_k| from the slots of phase `norm_epoch` (waits until every rank has published)
+__global__ void __launch_bounds__(32) lanczos_tail_peer_kernel(const StepArgs a, unsigned long long norm_epoch, int k,
+                                                               double *beta_arr) {
+  peer_wait(a.my_flags, a.world, a.rank, a.wait_epoch, a.err_flag);
+  if (threadIdx.x == 0) beta_arr[k] = sqrt(peer_scalar_sum(a.my_scal, a.world, norm_epoch));
 }
 
 // beta_arr[k] = |w_k| for the newest vector (its partials are complete once the axpy of step k-1 has run)
@@ -1576,6 +1645,13 @@ static void fill_peer_args(StepArgs &a, const meld_b200_dist *d, int which_buf, 
     a.peer_flags[a.n_peers] = d->flags(w) + d->rank;
     ++a.n_peers;
   }
+  a.peer_store = 1;
+  {
+    int k = 0;
+    for (int w = 0; w < d->world; ++w)
+      if (w != d->rank) a.peer_scal[k++] = d->scal(w);
+  }
+  a.my_scal = d->scal(d->rank);
   a.my_flags = d->flags(d->rank);
   a.done_ctr = d->ctr();
   a.err_flag = d->err();
@@ -1693,6 +1769,8 @@ int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeff
   return 0;
 }
 
+static int lanczos_check(std::vector<double> &alpha, std::vector<double> &beta, int &k, double rel_tol, double &theta);
+
 int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol, void *stream_, double *lmax_host,
                             int *iters_host) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1721,7 +1799,7 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
   MELD_CUDA(cudaMemsetAsync(pa, 0, (4 * kRedBlocks + 2 * ((size_t)max_iters + 2)) * sizeof(double), stream));
   lanczos_init_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(wa, n, pb);  // w_0, |w_0|^2 -> pb[0]
   MELD_LAUNCH_CHECK();
-  std::vector<double> alpha((size_t)max_iters + 2), beta((size_t)max_iters + 2), dd, ee, zl;
+  std::vector<double> alpha((size_t)max_iters + 2), beta((size_t)max_iters + 2);
   double theta = 0.0;
   int k = 0, next_check = max_iters < 8 ? max_iters : 8;
   bool done = false;
@@ -1748,47 +1826,137 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
     MELD_CUDA(cudaMemcpyAsync(alpha.data(), d_alpha, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(beta.data(), d_beta, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));
-    // T_k: diagonal alpha_0..alpha_{k-1}, off-diagonal beta_1..beta_{k-1}; beta_k couples to the next vector.
-    // An exactly invariant Krylov space (beta_j ~ 0) ends the recurrence early.
-    int kk = k;
-    double scale = 0.0;
-    for (int j = 0; j < k; ++j) scale = fmax(scale, fabs(alpha[(size_t)j]));
-    for (int j = 1; j <= k; ++j) {
-      if (!(beta[(size_t)j] > 1e-13 * fmax(scale, 1e-300))) {
-        kk = j;
-        done = true;
-        break;
-      }
+    const int rc = lanczos_check(alpha, beta, k, rel_tol, theta);
+    if (rc < 0) return rc;
+    done = rc == 1;
+    next_check = k + 4 < max_iters ? k + 4 : max_iters;
+  }
+  *lmax_host = 1.01 * theta;
+  if (iters_host) *iters_host = k;
+  return 0;
+}
+
+// Shared by both Lanczos drivers: Ritz analysis of T_k (alpha_0..alpha_{k-1}, beta_1..beta_{k-1}; beta_k couples to
+// the next vector).  Returns < 0 on error, 1 when converged (k may shrink to an invariant subspace), else 0.
+static int lanczos_check(std::vector<double> &alpha, std::vector<double> &beta, int &k, double rel_tol, double &theta) {
+  int kk = k;
+  bool done = false;
+  double scale = 0.0;
+  for (int j = 0; j < k; ++j) scale = fmax(scale, fabs(alpha[(size_t)j]));
+  for (int j = 1; j <= k; ++j) {
+    if (!(beta[(size_t)j] > 1e-13 * fmax(scale, 1e-300))) {
+      kk = j;
+      done = true;
+      break;
     }
-    for (int j = 0; j < kk; ++j)
-      if (!isfinite(alpha[(size_t)j])) {
-        set_error("estimate_lmax: non-finite Lanczos coefficient at step %d", j);
-        return MELD_B200_ERR_INTERNAL;
-      }
-    dd.assign(alpha.begin(), alpha.begin() + kk);
-    ee.assign((size_t)kk, 0.0);
-    for (int j = 0; j + 1 < kk; ++j) ee[(size_t)j] = beta[(size_t)j + 1];
-    zl.assign((size_t)kk, 0.0);
-    if (!tridiag_ql_last_row(dd, ee, zl, kk)) {
-      set_error("estimate_lmax: tridiagonal QL iteration did not converge");
+  }
+  for (int j = 0; j < kk; ++j)
+    if (!isfinite(alpha[(size_t)j])) {
+      set_error("estimate_lmax: non-finite Lanczos coefficient at step %d", j);
       return MELD_B200_ERR_INTERNAL;
     }
-    int top = 0;
-    for (int j = 1; j < kk; ++j)
-      if (dd[(size_t)j] > dd[(size_t)top]) top = j;
-    theta = dd[(size_t)top];
-    const double resid = kk < k ? 0.0 : fabs(beta[(size_t)k] * zl[(size_t)top]);
-    double second = -INFINITY;
-    for (int j = 0; j < kk; ++j)
-      if (j != top && dd[(size_t)j] > second) second = dd[(size_t)j];
-    const double gap = theta - second;  // Ritz estimate of the spectral gap below lambda_max
-    double err = resid;
-    if (kk >= 2 && gap > 0.0 && resid <= 0.5 * gap) err = fmin(resid, resid * resid / gap);
-    if (getenv("MELD_B200_LANCZOS_DEBUG"))
-      fprintf(stderr, "[meld_b200 lanczos] k=%d theta=%.15g resid/theta=%.3e ritz gap/theta=%.3e bound/theta=%.3e\n", k,
-              theta, resid / fabs(theta), gap / fabs(theta), err / fabs(theta));
-    if (err <= rel_tol * fabs(theta)) done = true;
-    if (done) k = kk;
+  std::vector<double> dd(alpha.begin(), alpha.begin() + kk), ee((size_t)kk, 0.0), zl((size_t)kk, 0.0);
+  for (int j = 0; j + 1 < kk; ++j) ee[(size_t)j] = beta[(size_t)j + 1];
+  if (!tridiag_ql_last_row(dd, ee, zl, kk)) {
+    set_error("estimate_lmax: tridiagonal QL iteration did not converge");
+    return MELD_B200_ERR_INTERNAL;
+  }
+  int top = 0;
+  for (int j = 1; j < kk; ++j)
+    if (dd[(size_t)j] > dd[(size_t)top]) top = j;
+  theta = dd[(size_t)top];
+  const double resid = kk < k ? 0.0 : fabs(beta[(size_t)k] * zl[(size_t)top]);
+  double second = -INFINITY;
+  for (int j = 0; j < kk; ++j)
+    if (j != top && dd[(size_t)j] > second) second = dd[(size_t)j];
+  const double gap = theta - second;  // Ritz estimate of the spectral gap below lambda_max
+  double err = resid;
+  if (kk >= 2 && gap > 0.0 && resid <= 0.5 * gap) err = fmin(resid, resid * resid / gap);
+  if (getenv("MELD_B200_LANCZOS_DEBUG"))
+    fprintf(stderr, "[meld_b200 lanczos] k=%d theta=%.15g resid/theta=%.3e ritz gap/theta=%.3e bound/theta=%.3e\n", k,
+            theta, resid / fabs(theta), gap / fabs(theta), err / fabs(theta));
+  if (err <= rel_tol * fabs(theta)) done = true;
+  if (done) k = kk;
+  return done ? 1 : 0;
+}
+
+int meld_b200_estimate_lmax_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, int max_iters, double rel_tol,
+                                 void *stream_, double *lmax_host, int *iters_host) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(gs && d && lmax_host, "estimate_lmax_dist: NULL argument");
+  MELD_REQUIRE(d->connected, "estimate_lmax_dist: the peer buffers are not connected");
+  MELD_REQUIRE(gs->n_cols == d->n, "estimate_lmax_dist: graph has %lld columns, context %lld", (long long)gs->n_cols,
+               (long long)d->n);
+  const int64_t n = gs->n_cols, nloc = gs->n_rows, row0 = gs->row0;
+  if (max_iters <= 0) max_iters = 160;
+  if (max_iters > n) max_iters = (int)n;
+  if (rel_tol <= 0) rel_tol = 1e-5;
+  const size_t lenl = ((size_t)nloc + 2 + 3) & ~(size_t)3;
+  const size_t need = lenl + 3 * kRedBlocks + 2 * ((size_t)max_iters + 2);
+  MELD_CHECK(ensure_work(gs, need));
+  double *y = gs->work.p, *pa = y + lenl, *pb0 = pa + kRedBlocks, *pbn = pb0 + kRedBlocks;
+  double *d_alpha = pbn + kRedBlocks, *d_beta = d_alpha + max_iters + 2;
+  MELD_CUDA(cudaMemsetAsync(pa, 0, (3 * kRedBlocks + 2 * ((size_t)max_iters + 2)) * sizeof(double), stream));
+  int ci = 0, oi = 1;
+  MELD_CUDA(cudaMemsetAsync(d->buf(d->rank, oi), 0, (size_t)n * sizeof(double), stream));  // w_{-1} = 0
+  lanczos_init_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(d->buf(d->rank, ci), n, pb0);  // every rank: whole w_0
+  MELD_LAUNCH_CHECK();
+  std::vector<double> alpha((size_t)max_iters + 2), beta((size_t)max_iters + 2);
+  double theta = 0.0;
+  int k = 0, next_check = max_iters < 8 ? max_iters : 8;
+  bool done = false;
+  unsigned long long norm_epoch = 0;
+  while (!done && k < max_iters) {
+    for (int j = k; j < next_check; ++j) {
+      StepArgs a{};  // phase A: y = L[rows] w_j, this rank's part of w_j . y published
+      a.Tcur = d->buf(d->rank, ci);
+      a.Tnew = y;
+      a.alpha = 1.0;
+      a.dot_partials = pa;
+      fill_peer_args(a, d, oi, row0, 1);
+      a.peer_store = 0;
+      a.scal_partials = pa;
+      a.wait_epoch = d->epoch;  // the peers' rows of w_j have arrived
+      a.post_epoch = ++d->epoch;
+      const unsigned long long dot_epoch = a.post_epoch;
+      if (nloc > 0) {
+        MELD_CHECK(launch_step(gs, a, 1, 0, stream));
+      } else {
+        a.n_scal_partials = 1;  // pa[0] = 0: an empty rank publishes a zero
+        dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, 1, nullptr);
+        MELD_LAUNCH_CHECK();
+      }
+      StepArgs b{};  // phase B: w_{j+1} rows into every rank's vector, |w_{j+1}|^2 of these rows published
+      fill_peer_args(b, d, oi, row0, 1);
+      b.scal_partials = pbn;
+      b.n_scal_partials = kRedBlocks;
+      b.wait_epoch = d->epoch;
+      b.post_epoch = ++d->epoch;
+      // few blocks for few rows (unwritten partial slots stay zero): a waiting grid should not cover the whole GPU
+      int agrid = (int)ceil_div(nloc > 0 ? nloc : 1, 4 * kRedThreads);
+      if (agrid > kRedBlocks) agrid = kRedBlocks;
+      lanczos_axpy_peer_kernel<<<agrid, kRedThreads, 0, stream>>>(b, y, d->buf(d->rank, ci), d->buf(d->rank, oi), row0,
+                                                                       nloc, dot_epoch, norm_epoch, pb0, j, d_alpha,
+                                                                       d_beta, pbn);
+      MELD_LAUNCH_CHECK();
+      norm_epoch = b.post_epoch;
+      const int t = ci;
+      ci = oi;
+      oi = t;
+    }
+    k = next_check;
+    StepArgs t{};
+    fill_peer_args(t, d, oi, row0, 1);
+    t.wait_epoch = d->epoch;
+    lanczos_tail_peer_kernel<<<1, 32, 0, stream>>>(t, norm_epoch, k, d_beta);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaMemcpyAsync(alpha.data(), d_alpha, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaMemcpyAsync(beta.data(), d_beta, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));
+    const int rc = lanczos_check(alpha, beta, k, rel_tol, theta);  // identical on every rank: same sums, same order
+    if (rc < 0) return rc;
+    done = rc == 1;
     next_check = k + 4 < max_iters ? k + 4 : max_iters;
   }
   *lmax_host = 1.01 * theta;

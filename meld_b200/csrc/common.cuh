@@ -227,7 +227,10 @@ struct meld_b200_dist {
   char *peer_base[8] = {nullptr};    // mapped blocks of all ranks ([rank] = base)
   unsigned long long epoch = 0;      // last phase published (identical on every rank: same call sequence)
   bool connected = false;
-  static constexpr size_t kFlagsOff = 0, kErrOff = 512, kCtrOff = 576, kBufOff = 1024;
+  // [0, 64) flag words, one per rank | 512 error word | 576 done counter | [640, 896) 4 x 8 scalar slots (the
+  // rank-ordered partial sums of the distributed Lanczos, ring indexed by epoch) | 1024.. the two signal buffers
+  static constexpr size_t kFlagsOff = 0, kErrOff = 512, kCtrOff = 576, kScalOff = 640, kBufOff = 1024;
+  double *scal(int r) const { return reinterpret_cast<double *>(peer_base[r] + kScalOff); }
   unsigned long long *flags(int r) const { return reinterpret_cast<unsigned long long *>(peer_base[r] + kFlagsOff); }
   int *err() const { return reinterpret_cast<int *>(base + kErrOff); }
   unsigned int *ctr() const { return reinterpret_cast<unsigned int *>(base + kCtrOff); }

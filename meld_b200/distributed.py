@@ -211,6 +211,22 @@ class ShardedFilter:
             "cheby_step",
         )
 
+    def estimate_lmax(self, max_iters=0, rel_tol=0.0):
+        """1.01 x lambda_max by the row-partitioned Lanczos (p2p mode; every rank returns the same value bit for bit).
+        NCCL mode: the full graph's own (replicated) estimate."""
+        if self.mode != "p2p":
+            return self.graph.estimate_lmax(max_iters, rel_tol)
+        from . import _native as nv
+
+        lmax, iters = C.c_double(), C.c_int()
+        nv.check(
+            nv.lib().meld_b200_estimate_lmax_dist(self.slice._h, self.ctx._h, int(max_iters), float(rel_tol),
+                                                  nv.current_stream_ptr(), C.byref(lmax), C.byref(iters)),
+            "estimate_lmax_dist",
+        )
+        self.lmax_iters = iters.value
+        return lmax.value
+
     # ---- p2p ---------------------------------------------------------------------------------------------
     def _apply_p2p(self, lmax, coeffs, S):
         import torch

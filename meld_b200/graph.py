@@ -203,38 +203,68 @@ class DeviceGraph:
         decay = 0.0 if decay is None else decay
         bounds = cls.shard_bounds(N, world)
         lap("input to device")
-        counts, cand, d2, eps, perm = cls.candidates(X, bounds[rank], bounds[rank + 1], knn, decay, thresh,
-                                                     bandwidth_scale)
+        dev = X.device
+        lib = nv.lib()
+        a, b = bounds[rank], bounds[rank + 1]
+        # ---- stage 1 on this rank's query rows
+        h = C.c_void_p()
+        nloc = total = 0
+        has_perm = 0
+        if b > a:
+            nv.check(lib.meld_b200_knn_candidates(nv.ptr(X), N, d, int(knn), float(decay), float(thresh),
+                                                  float(bandwidth_scale), int(a), int(b), 0, nv.current_stream_ptr(),
+                                                  C.byref(h)), "knn_candidates")
+            c_n, c_t, c_p, c_m = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+            nv.check(lib.meld_b200_cands_info(h, C.byref(c_n), C.byref(c_t), C.byref(c_p), C.byref(c_m)), "cands_info")
+            nloc, total, has_perm = c_n.value, c_t.value, c_p.value
         lap("stage 1 (local rows)")
-        sizes = torch.tensor([counts.shape[0], cand.shape[0]], dtype=torch.int64, device=X.device)
-        all_sizes = torch.empty(2 * world, dtype=torch.int64, device=X.device)
-        dist.all_gather_into_tensor(all_sizes, sizes, group=group)
-        all_sizes = all_sizes.cpu().view(world, 2)
+        try:
+            # ---- one exchange: every rank's [d2 | eps | counts | cand] block, padded to the longest, all-gathered
+            sizes = torch.tensor([nloc, total, has_perm], dtype=torch.int64, device=dev)
+            all_sizes = torch.empty(3 * world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+            all_sizes = all_sizes.cpu().view(world, 3)
+            rows, tots = all_sizes[:, 0].tolist(), all_sizes[:, 1].tolist()
+            any_perm = bool(all_sizes[:, 2].max().item())
+            blk = max(12 * t + 16 * r for r, t in zip(rows, tots))
+            blk = (blk + 15) // 16 * 16
 
-        def gather_var(local, lens):
-            longest = int(max(lens))
-            pad = torch.zeros(longest, dtype=local.dtype, device=local.device)
-            pad[: local.shape[0]] = local
-            out = torch.empty(world * longest, dtype=local.dtype, device=local.device)
-            dist.all_gather_into_tensor(out, pad, group=group)
-            return torch.cat([out[r * longest: r * longest + int(lens[r])] for r in range(world)])
+            def views(buf, r, t):  # typed views of one rank's block
+                o = 0
+                v_d2 = buf[o:o + 8 * t].view(torch.float64)
+                o += 8 * t
+                v_eps = buf[o:o + 8 * r].view(torch.float64)
+                o += 8 * r
+                v_cnt = buf[o:o + 8 * r].view(torch.int64)
+                o += 8 * r
+                v_cand = buf[o:o + 4 * t].view(torch.int32)
+                return v_d2, v_eps, v_cnt, v_cand
 
-        rows, tots = all_sizes[:, 0].tolist(), all_sizes[:, 1].tolist()
-        counts = gather_var(counts, rows)
-        eps = gather_var(eps, rows)
-        cand = gather_var(cand, tots)
-        d2 = gather_var(d2, tots)
-        # whether the native build re-ordered the cells is the library's decision (tuning): ask the ranks
-        has = torch.tensor([1 if perm is not None else 0], dtype=torch.int64, device=X.device)
-        dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
-        if int(has.item()):
-            if perm is None:  # a rank with an empty row range did not compute the order
-                perm = torch.empty(N, dtype=torch.int32, device=X.device)
-            src = next(r for r in range(world) if rows[r] > 0)
-            dist.broadcast(perm, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
-        lap("all-gather")
+            recv = torch.empty(world * blk, dtype=torch.uint8, device=dev)
+            mine = recv[rank * blk:(rank + 1) * blk]  # in-place all-gather: this rank's block sits in its slot
+            perm = torch.empty(N, dtype=torch.int32, device=dev) if any_perm else None
+            if nloc > 0:
+                v_d2, v_eps, v_cnt, v_cand = views(mine, nloc, total)
+                nv.check(lib.meld_b200_cands_export(h, nv.ptr(v_cnt), nv.ptr(v_cand), nv.ptr(v_d2), nv.ptr(v_eps),
+                                                    nv.ptr(perm) if has_perm else C.c_void_p(0),
+                                                    nv.current_stream_ptr()), "cands_export")
+            if world > 1:
+                dist.all_gather_into_tensor(recv, mine, group=group)
+            parts = [views(recv[r * blk:(r + 1) * blk], rows[r], tots[r]) for r in range(world)]
+            d2 = torch.cat([p_[0] for p_ in parts])
+            eps = torch.cat([p_[1] for p_ in parts])
+            counts = torch.cat([p_[2] for p_ in parts])
+            cand = torch.cat([p_[3] for p_ in parts])
+            if any_perm and world > 1:  # every rank with rows derived the same order; take the first one's
+                src = next(r for r in range(world) if rows[r] > 0)
+                dist.broadcast(perm, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+            lap("all-gather")
+        finally:
+            if h.value:
+                torch.cuda.current_stream().synchronize()
+                lib.meld_b200_cands_destroy(h)
         g = cls.from_candidates(N, counts, cand, d2, eps, perm, knn, decay, thresh, anisotropy, bandwidth_scale,
-                                device=X.device)
+                                device=dev)
         lap("stage 2 (replicated)")
         return g
 

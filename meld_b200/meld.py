@@ -422,6 +422,10 @@ class MELD(object):
                                                 int(bool(self.sample_normalize)), nv.ptr(S), nv.current_stream_ptr()),
             "indicator_matrix",
         )
+        if self._sharded is not None and self.solver == "chebyshev" and self.graph._lmax is None:
+            # row-partitioned Lanczos on the ranks' slices (identical result on every rank)
+            self.graph._lmax = self._sharded.estimate_lmax()
+            self.graph.lmax_iters = getattr(self._sharded, "lmax_iters", None)
         events = self.profile_events
         if events is not None and self.solver == "chebyshev":
             self.graph.estimate_lmax()  # keep the Lanczos launches out of the filter bracket

@@ -428,3 +428,77 @@ def test_decay_none_binary_knn_kernel(mb):
     dens = op.transform(labels)
     normwise, ok = density_parity(dens.values, ref.values, RTOL)
     assert ok and normwise < TIGHT
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_row_partitioned_lanczos_ranks_in_one_process(mb, world):
+    """meld_b200_estimate_lmax_dist with every rank in this process (one host thread + stream per rank, contexts
+    connected by pointer): all ranks return the SAME value bit for bit, equal to the single-GPU Lanczos to rounding,
+    and a filter call afterwards still works (the epochs carry over)."""
+    import ctypes as C
+    import threading
+    import torch
+    from meld_b200 import _native as nv
+    from meld_b200.distributed import chunk_partition
+
+    lib = nv.lib()
+    X, _ = mb.synthetic.make_blobs(5000, 20, 5, 3, 6.0, seed=8)
+    graph = mb.DeviceGraph.from_data(X, knn=7)
+    ref = graph.estimate_lmax()
+    N = graph.N
+    chunk, bounds = chunk_partition(N, world)
+    slices = [graph.row_slice(bounds[r], bounds[r + 1]) for r in range(world)]
+    ctxs = []
+    for r in range(world):
+        h = C.c_void_p()
+        nv.check(lib.meld_b200_dist_create(r, world, N, 8, nv.current_stream_ptr(), C.byref(h)), "dist_create")
+        ctxs.append(h)
+    arr = (C.c_void_p * world)(*[h.value for h in ctxs])
+    for h in ctxs:
+        nv.check(lib.meld_b200_dist_connect_local(h, arr, world), "dist_connect_local")
+    torch.cuda.synchronize()
+    dev = torch.cuda.current_device()
+    out, iters, errs = [None] * world, [None] * world, []
+
+    def run(r):
+        try:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                lm, it = C.c_double(), C.c_int()
+                nv.check(lib.meld_b200_estimate_lmax_dist(slices[r]._h, ctxs[r], 0, 0.0, nv.current_stream_ptr(),
+                                                          C.byref(lm), C.byref(it)), "estimate_lmax_dist")
+                out[r], iters[r] = lm.value, it.value
+        except Exception as exc:  # noqa: BLE001
+            errs.append(exc)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errs, errs
+    torch.cuda.synchronize()
+    for r in range(world):
+        e = C.c_int(0)
+        nv.check(lib.meld_b200_dist_error(ctxs[r], C.byref(e)), "dist_error")
+        assert e.value == 0
+    assert all(o == out[0] for o in out) and all(i == iters[0] for i in iters), (out, iters)
+    assert abs(out[0] - ref) <= 1e-9 * ref and iters[0] == graph.lmax_iters, (out[0], ref, iters[0], graph.lmax_iters)
+    # a filter on the same contexts afterwards
+    p, m = 3, 12
+    S = torch.from_numpy(np.random.default_rng(3).normal(size=(N, p))).cuda()
+    c = np.ascontiguousarray(mb.filter.cheby_coefficients(mb.filter.filter_kernel("heat", 40), ref, m))
+    want = mb.filter.cheby_apply(graph, ref, c, S)
+    cptr = c.ctypes.data_as(C.POINTER(C.c_double))
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    outs = [torch.empty_like(S) for _ in range(world)]
+    torch.cuda.synchronize()
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            nv.check(lib.meld_b200_cheby_filter_dist(slices[r]._h, ctxs[r], float(ref), cptr, len(c), nv.ptr(S), p,
+                                                     nv.ptr(outs[r]), nv.current_stream_ptr()), "cheby_filter_dist")
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert _close(outs[r], want)
+    for h in ctxs:
+        lib.meld_b200_dist_destroy(h)
