@@ -584,6 +584,7 @@ def run_b200(args):
             "config": {
                 "workload": workload_name(args, cfg, n),
                 "parallelism": par, "dist_mode": dist_mode if strong else None, "dist_note": dist_note,
+                "halo_fraction_rank0": (getattr(op._sharded, "halo_fraction", None) if strong and op._sharded else None),
                 "nnz_L": int(nnz), "nnz_per_row": nnz / n, "lmax": lmax, "lmax_iters": lmax_iters,
                 "candidate_cap": stats["candidate_cap"],
                 "max_candidates": stats["max_candidates"], "search_passes": stats["search_passes"],

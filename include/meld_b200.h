@@ -214,6 +214,14 @@ int meld_b200_dist_connect(meld_b200_dist_t *d, const void *all_blobs_host);
  * the process that exported it) are connected by pointer; the ranks' call sequences then run on different
  * streams of that device and meet through the same flag protocol.                                          */
 int meld_b200_dist_connect_local(meld_b200_dist_t *d, meld_b200_dist_t *const *all, int count);
+/* Halo of a row slice.  Per term a rank's rows of T_k only have to reach the peers whose own rows reference them
+ * as columns.  meld_b200_graph_mark_columns sets ref[c] = 1 (device bytes, n_cols long, caller-zeroed) for every
+ * column the slice references; the caller exchanges the row ranges (all-to-all of bytes: rank w's marks of rank
+ * r's rows go to rank r), and meld_b200_graph_set_halo turns recv[w * chunk + i] (w = 0..world-1) into the
+ * per-row peer mask the step kernel tests before each peer store.  Without a halo every row goes to every peer. */
+int meld_b200_graph_mark_columns(const meld_b200_graph_t *slice, uint8_t *ref, void *stream);
+int meld_b200_graph_set_halo(meld_b200_graph_t *slice, const uint8_t *recv, int64_t chunk, int world, int rank,
+                             void *stream);
 /* 1 when a flag wait timed out (a peer died or left the call sequence); synchronises the device.           */
 int meld_b200_dist_error(const meld_b200_dist_t *d, int *err_host);
 int meld_b200_dist_destroy(meld_b200_dist_t *d);

@@ -56,6 +56,8 @@ SIGNATURES = {
     "meld_b200_dist_export": (C.c_int, [_vp, _vp]),
     "meld_b200_dist_connect": (C.c_int, [_vp, _vp]),
     "meld_b200_dist_connect_local": (C.c_int, [_vp, C.POINTER(_vp), _i32]),
+    "meld_b200_graph_mark_columns": (C.c_int, [_vp, _vp, _vp]),
+    "meld_b200_graph_set_halo": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "meld_b200_dist_error": (C.c_int, [_vp, _pint]),
     "meld_b200_dist_destroy": (C.c_int, [_vp]),
     "meld_b200_cheby_filter_dist": (C.c_int, [_vp, _vp, _dbl, _pdbl, _i32, _vp, _i32, _vp, _vp]),

@@ -117,6 +117,7 @@ struct StepArgs {
   int n_peers, world, rank;
   int store_r;                          // last term: T_new / peer_tnew receive the finished R rows instead of T_k
   int peer_store;                       // 0: T_new stays local (distributed Lanczos: only the scalar is published)
+  const uint8_t *halo;                  // per local row: which peers reference it (nullptr: all of them)
   double *peer_scal[kMaxPeers];         // peers' scalar slots (4 x 8 doubles, ring indexed by epoch & 3)
   double *my_scal;                      // this rank's scalar slots
   const double *scal_partials;          // per-CTA partial sums whose total the last CTA publishes (or nullptr)
@@ -1013,8 +1014,11 @@ __global__ void __launch_bounds__(TB, 1) cheby_flat2_kernel(const StepArgs a, co
       if (a.Tnew) a.Tnew[li] = outv;  // gathered by the next step: keep cacheable
       if constexpr (PEER) {
         if (a.Tnew && a.peer_store) {
+          // only the peers whose rows reference this row as a column need it (the finished R goes to everyone)
+          const unsigned hm = (a.halo != nullptr && !a.store_r) ? (unsigned)__ldg(a.halo + r) : 0xffu;
 #pragma unroll 1
-          for (int w = 0; w < a.n_peers; ++w) a.peer_tnew[w][li] = outv;
+          for (int w = 0; w < a.n_peers; ++w)
+            if ((hm >> w) & 1u) a.peer_tnew[w][li] = outv;
         }
       }
     }
@@ -1373,7 +1377,9 @@ __global__ void __launch_bounds__(kRedThreads) lanczos_axpy_peer_kernel(const St
     const int64_t gi = row0 + i;
     const double x = (y_loc[i] - alpha * w_cur[gi]) * inv - ratio * w_prev[gi];
     w_prev[gi] = x;
-    for (int w = 0; w < a.n_peers; ++w) a.peer_tnew[w][i] = x;  // peers' copies of this rank's rows
+    const unsigned hm = a.halo != nullptr ? (unsigned)__ldg(a.halo + i) : 0xffu;
+    for (int w = 0; w < a.n_peers; ++w)
+      if ((hm >> w) & 1u) a.peer_tnew[w][i] = x;  // peers' copies of this rank's rows (those that gather them)
     s = fma(x, x, s);
   }
   s = block_sum(s, sh);
@@ -1689,6 +1695,7 @@ int meld_b200_cheby_filter_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, doub
     a.Told = k >= 2 ? d->buf(d->rank, oi) + (size_t)row0 * p : nullptr;
     a.Tnew = d->buf(d->rank, oi) + (size_t)row0 * p;  // T_k over T_{k-2}; at k = m the finished rows of R
     fill_peer_args(a, d, oi, row0, p);
+    a.halo = gs->halo.p;
     a.store_r = k == m;
     a.R = Rloc;
     a.alpha = (k == 1 ? 1.0 : 2.0) / a1;
@@ -1929,6 +1936,7 @@ int meld_b200_estimate_lmax_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, int
       }
       StepArgs b{};  // phase B: w_{j+1} rows into every rank's vector, |w_{j+1}|^2 of these rows published
       fill_peer_args(b, d, oi, row0, 1);
+      b.halo = gs->halo.p;
       b.scal_partials = pbn;
       b.n_scal_partials = kRedBlocks;
       b.wait_epoch = d->epoch;

@@ -200,6 +200,9 @@ struct meld_b200_graph {
   int64_t dict_total = 0, direct_blocks = 0;  // statistics
   // Cell order used internally (graph row a = caller's cell perm[a]); null = identity.
   meld::DevBuf<int32_t> perm{true};
+  // Row slices of a partitioned operator: bit k of halo[i] = the k-th peer (ranks in order, this one skipped)
+  // references local row i as a column of its own rows, i.e. needs this row of every exchanged vector.
+  meld::DevBuf<uint8_t> halo{true};
   // Chebyshev / Lanczos workspace, grown on demand.
   meld::DevBuf<double> work{true};
   // Un-symmetrised kNN kernel kept for export (compact CSR, slot order), optional.

@@ -20,9 +20,53 @@ __global__ void slice_row_ptr_kernel(const int32_t *__restrict__ row_ptr, int64_
   if (i <= n_rows) out[i] = row_ptr[row_begin + i] - row_ptr[row_begin];
 }
 
+__global__ void mark_columns_kernel(const int32_t *__restrict__ col, int64_t nnz, uint8_t *__restrict__ ref) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+    ref[col[e]] = 1;
+}
+
+// recv[w * chunk + i] = 1 when rank w references this rank's row i; bit k of mask[i] <- the k-th peer (rank skipped)
+__global__ void halo_mask_kernel(const uint8_t *__restrict__ recv, int64_t chunk, int64_t nloc, int world, int rank,
+                                 uint8_t *__restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned m = 0;
+    int k = 0;
+    for (int w = 0; w < world; ++w) {
+      if (w == rank) continue;
+      if (recv[(int64_t)w * chunk + i]) m |= 1u << k;
+      ++k;
+    }
+    mask[i] = (uint8_t)m;
+  }
+}
+
 }  // namespace meld
 
 extern "C" {
+
+int meld_b200_graph_mark_columns(const meld_b200_graph_t *g, uint8_t *ref, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(g && ref, "graph_mark_columns: NULL argument");
+  if (g->nnz > 0) {
+    mark_columns_kernel<<<sm_count() * 4, 256, 0, stream>>>(g->col.p, g->nnz, ref);
+    MELD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int meld_b200_graph_set_halo(meld_b200_graph_t *g, const uint8_t *recv, int64_t chunk, int world, int rank, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(g && recv && world >= 1 && world <= 8 && rank >= 0 && rank < world && chunk >= g->n_rows,
+               "graph_set_halo: bad argument");
+  MELD_CHECK(g->halo.alloc((size_t)(g->n_rows > 0 ? g->n_rows : 1)));
+  if (g->n_rows > 0) {
+    halo_mask_kernel<<<sm_count() * 2, 256, 0, stream>>>(recv, chunk, g->n_rows, world, rank, g->halo.p);
+    MELD_LAUNCH_CHECK();
+  }
+  return 0;
+}
 
 int meld_b200_graph_row_slice(const meld_b200_graph_t *g, int64_t row_begin, int64_t row_end, void *stream_,
                               meld_b200_graph_t **out) {

@@ -187,12 +187,37 @@ class ShardedFilter:
         self.chunk, self.bounds = chunk_partition(self.N, self.world)
         self.row_range = (self.bounds[self.rank], self.bounds[self.rank + 1])
         self._nccl_bufs = {}
+        self.halo_fraction = 1.0
         self._attach()
 
     def _attach(self):
         """Native state: this rank's row slice and (p2p) the peer-memory context."""
         self.slice = self.graph.row_slice(*self.row_range)
         self.ctx = shared_context(self.N, self.p_max, self.group) if self.mode == "p2p" else None
+        if self.mode == "p2p" and self.world > 1:
+            self._exchange_halo()
+
+    def _exchange_halo(self):
+        """Which of this rank's rows does each peer gather?  One all-to-all of byte marks (plumbing, once per graph);
+        afterwards a row of T_k is only stored into the peers that reference it."""
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as nv
+
+        lib = nv.lib()
+        dev = self.graph.device
+        ref = torch.zeros(self.world * self.chunk, dtype=torch.uint8, device=dev)
+        nv.check(lib.meld_b200_graph_mark_columns(self.slice._h, nv.ptr(ref), nv.current_stream_ptr()), "graph_mark_columns")
+        recv = torch.empty_like(ref)
+        dist.all_to_all_single(recv, ref, group=self.group)  # recv[w * chunk + i] = rank w's mark of my row i
+        nv.check(lib.meld_b200_graph_set_halo(self.slice._h, nv.ptr(recv), self.chunk, self.world, self.rank,
+                                              nv.current_stream_ptr()), "graph_set_halo")
+        peers = [w for w in range(self.world) if w != self.rank]
+        a, b = self.row_range
+        # fraction of (row, peer) pairs that actually travel per term (1.0 = plain all-gather)
+        self.halo_fraction = float(recv.view(self.world, self.chunk)[peers, : max(b - a, 1)].float().mean()) if b > a else 0.0
+        torch.cuda.current_stream().synchronize()  # recv / ref die here
 
     # ---- the two native operations of the NCCL path (overridden by the CPU / gloo test) -----------------
     def _permute(self, src, p, to_internal, dst):

@@ -330,8 +330,8 @@ def test_row_slices_and_single_rank_dist_filter(mb):
         sf.close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_peer_store_filter_ranks_in_one_process(mb, world):
+@pytest.mark.parametrize("world,halo", [(2, False), (3, False), (3, True)])
+def test_peer_store_filter_ranks_in_one_process(mb, world, halo):
     """The flag protocol of meld_b200_cheby_filter_dist with every rank in this process: one context per rank on
     the same device (connected by pointer), each rank's call sequence on its own stream.  The grids are small,
     so all ranks' kernels are co-resident and really wait on each other's flags.  Result = full filter."""
@@ -350,6 +350,20 @@ def test_peer_store_filter_ranks_in_one_process(mb, world):
     ref = mb.filter.cheby_apply(graph, lmax, c, S)
     chunk, bounds = chunk_partition(N, world)
     slices = [graph.row_slice(bounds[r], bounds[r + 1]) for r in range(world)]
+    if halo:  # rows only go to the peers that reference them (what ShardedFilter._exchange_halo sets up over NCCL)
+        refs = []
+        for r in range(world):
+            ref = torch.zeros(world * chunk, dtype=torch.uint8, device="cuda")
+            nv.check(lib.meld_b200_graph_mark_columns(slices[r]._h, nv.ptr(ref), nv.current_stream_ptr()), "mark")
+            refs.append(ref)
+        sent = 0
+        for r in range(world):
+            recv = torch.cat([refs[w][r * chunk:(r + 1) * chunk] for w in range(world)])  # the all-to-all
+            nv.check(lib.meld_b200_graph_set_halo(slices[r]._h, nv.ptr(recv), chunk, world, r, nv.current_stream_ptr()),
+                     "set_halo")
+            torch.cuda.synchronize()
+            sent += int(sum(int(refs[w][r * chunk:(r + 1) * chunk].sum()) for w in range(world) if w != r))
+        assert sent < (world - 1) * N  # clustered cell order: most rows are not needed by most peers
     ctxs = []
     for r in range(world):
         h = C.c_void_p()

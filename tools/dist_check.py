@@ -86,7 +86,7 @@ def main():
             torch.cuda.synchronize()
             best = min(best, maxr(e0.elapsed_time(e1)))
         say(mode=mode, world=world, rel_err_vs_full=err, flag_timeout=bad, filter_ms=round(best, 3),
-            us_per_term=round(1e3 * best / m, 2))
+            us_per_term=round(1e3 * best / m, 2), halo_fraction_rank0=round(sf.halo_fraction, 4))
         sf.close()
     # single-GPU filter time for the ratio
     best = 1e9
