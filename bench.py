@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c4", help="synthetic config of meld_b200.synthetic (c1..c5)")
     ap.add_argument("--cells", type=int, default=None, help="override the number of cells")
+    ap.add_argument("--n-pca", default="default", help="'none' disables the PCA of config 2 (distance GEMM over 2000 dims)")
     ap.add_argument("--cpu-cells", type=int, default=10000,
                     help="cells of the sample the CPU path's per-row stages (affinities .. filter) are timed on")
     ap.add_argument("--cpu-queries", type=int, default=1024,
@@ -193,13 +194,17 @@ def make_inputs(args, seed_offset=0):
 
     cfg = synthetic.CONFIGS[args.config]
     n = args.cells or cfg["N"]
-    X, labels, kw = synthetic.make_config(args.config, seed=int(args.config[1:]) + seed_offset, N=n)
+    base_seed = int("".join(ch for ch in args.config if ch.isdigit()))
+    X, labels, kw = synthetic.make_config(args.config, seed=base_seed + seed_offset, N=n)
+    if args.n_pca == "none":
+        kw = dict(kw, n_pca=None)
     return X, labels, kw, cfg
 
 
 def workload_name(args, cfg, n):
-    return "{}: {} cells x {} dims, {} samples, {}".format(
-        args.config, n, cfg["D"], cfg["n_samples"], ", ".join("{}={}".format(k, v) for k, v in cfg["meld"].items()) or "defaults")
+    return "{}: {} cells x {} dims, {} samples, {}{}".format(
+        args.config, n, cfg["D"], cfg["n_samples"], ", ".join("{}={}".format(k, v) for k, v in cfg["meld"].items()) or "defaults",
+        ", n_pca=None" if args.n_pca == "none" else "")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -223,9 +228,9 @@ class CpuPath:
         self.X, self.labels, kw = synthetic.make_config(args.config, N=self.n)
         self.kw = kw
         self.graph_kw = {k: kw[k] for k in ("knn", "decay", "thresh", "anisotropy") if k in kw}
-        self.filter_kw = {k: v for k, v in kw.items() if k not in self.graph_kw}
+        self.filter_kw = {k: v for k, v in kw.items() if k not in self.graph_kw and k != "n_pca"}
         self.knn = self.graph_kw.get("knn", 5)
-        self.n_pca = None if self.cfg["D"] <= 100 else 100
+        self.n_pca = None if (self.cfg["D"] <= 100 or args.n_pca == "none") else 100
         self.sample = min(args.cpu_cells, self.n)
         self.queries = min(args.cpu_queries, self.n)
         t0 = time.perf_counter()
@@ -346,7 +351,7 @@ def parity_block(args, op, out_dev, labels, kw, cfg):
     }
     ns = min(20000, cfg["N"] if args.cells is None else args.cells)
     Xs, ys, kws = synthetic.make_config(args.config, N=ns)
-    n_pca = None if cfg["D"] <= 100 else 100
+    n_pca = None if (cfg["D"] <= 100 or args.n_pca == "none") else 100
     ref_s, g, lmax = omeld.fit_transform(Xs, ys, n_pca=n_pca, random_state=0, n_jobs=os.cpu_count(), **kws)
     ops = meld_b200.MELD(verbose=0, n_pca=n_pca, random_state=0, **kws)
     ops.fit(Xs)

@@ -19,6 +19,9 @@ CONFIGS = {
     "c3": dict(N=90_000, D=100, n_blobs=20, n_samples=4, tau=10.0, meld=dict()),
     "c4": dict(N=500_000, D=100, n_blobs=20, n_samples=4, tau=10.0, meld=dict(knn=15, chebyshev_order=64)),
     "c5": dict(N=2_000_000, D=50, n_blobs=20, n_samples=6, tau=10.0, meld=dict(knn=10)),
+    # adversarial for the pruned search: ONE isotropic Gaussian blob in 100 dimensions -- no cluster structure to prune
+    # by and distance concentration (SURVEY finding 9: ~170+ kept neighbours per row)
+    "c4iso": dict(N=500_000, D=100, n_blobs=1, n_samples=4, tau=1e12, meld=dict(knn=15, chebyshev_order=64)),
 }
 
 
@@ -60,7 +63,7 @@ def make_config(name, seed=None, N=None, dtype=np.float64):
     """Inputs + MELD kwargs for a BASELINE.json config (``c1`` .. ``c5``); ``N`` overrides the size."""
     cfg = CONFIGS[name]
     if seed is None:
-        seed = int(name[1:])
+        seed = int("".join(ch for ch in name if ch.isdigit()))
     if cfg.get("kind") == "readme":
         X, y = make_readme_toy(seed)
         return X, y, dict(cfg["meld"])

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+NP=${1:-2}
+( timeout 300 python -m pytest tests/test_gpu_filter.py -m gpu -q -k "peer or lanczos" ) > gpurun_out/c7_pytest.log 2>&1
+( time timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29520 tools/dist_check.py --config c4 --reps 3 ) > gpurun_out/c7_dist_check_np$NP.log 2>&1
+( time timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $NP --steps 5 --warmup 3 --no-parity ) > gpurun_out/c7_bench_c4_np$NP.log 2>&1
+tail -2 gpurun_out/c7_pytest.log
+grep "^{" gpurun_out/c7_dist_check_np$NP.log | tail -9
+grep '^{"metric' gpurun_out/c7_bench_c4_np$NP.log | cut -c1-330
