@@ -132,6 +132,32 @@ def main():
         inrange = int(((ci.long() >= lo) & (ci.long() < hi)).sum())
         print(json.dumps(dict(stat="columns inside the CTA's own row range", frac=round(inrange / graph.nnz, 4))), flush=True)
         del L
+    if "prune" in what:
+        # cell-order / pruning knobs of the candidate search: ms of a whole build and of its two GEMM passes
+        Xd = torch.from_numpy(X).cuda()
+        base = dict(clusters=64, kmeans_iters=1, cluster_cells=1024, prune_window=2, tl_chunks=2, tc_multicast=2)
+        trials = [dict(), dict(clusters=96), dict(clusters=128), dict(clusters=32), dict(kmeans_iters=2),
+                  dict(clusters=128, kmeans_iters=2), dict(prune_window=1), dict(prune_window=3), dict(tl_chunks=1),
+                  dict(tl_chunks=3), dict(tl_chunks=4), dict(tc_multicast=1), dict(tc_multicast=4)]
+        for tr in trials:
+            nv.set_tuning(**dict(base, **tr))
+            ts = []
+            for rep in range(4):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                gg = meld_b200.DeviceGraph.from_data(Xd, knn=kw.get("knn", 5))
+                e1.record()
+                torch.cuda.synchronize()
+                if rep:
+                    ts.append(e0.elapsed_time(e1))
+                bt, st = gg.build_times(), gg.build_stats()
+                gg.close()
+            print(json.dumps(dict(prune=tr, build_ms=round(float(np.median(ts)), 3), pass1_ms=round(bt["pass1_ms"], 3),
+                                  pass2_ms=round(bt["pass2_ms"], 3), candidates=st["candidate_cap"],
+                                  tile_pairs_kept=round(bt["flops_per_pass"] / max(bt["flops_unpruned_pass"], 1), 4))),
+                  flush=True)
+        nv.set_tuning(**base)
     if "sweep" in what:
         Xs, ys, kws = synthetic.make_config("c3", N=26827)  # the notebook's dataset size (MELD_Quickstart)
         g3 = meld_b200.DeviceGraph.from_data(Xs, knn=7)
