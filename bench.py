@@ -323,7 +323,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
-def parity_block(args, op, out_dev, labels, kw, cfg):
+def parity_block(args, op, out_dev, labels, kw, cfg, L):
     """Does the bench's own output agree with the reference's CPU arithmetic?  (i) FULL size: the oracle's Chebyshev
     filter (scipy matvecs) on the GPU-built graph copied to the host vs the densities of the last timed step
     (BASELINE.md 3.5); (ii) a 20k-cell sample of the same generator through the whole oracle vs the whole engine
@@ -334,9 +334,7 @@ def parity_block(args, op, out_dev, labels, kw, cfg):
 
     res = {}
     filter_kw = {k: v for k, v in kw.items() if k in ("beta", "offset", "order", "filter", "chebyshev_order")}
-    t0 = time.perf_counter()
-    L = op.graph.to_scipy_L()
-    t1 = time.perf_counter()
+    t0 = t1 = time.perf_counter()  # L was exported (or gathered from the ranks' row slices) by the caller
     ref = omeld.transform(L, op.graph.lmax, labels, **filter_kw)
     t2 = time.perf_counter()
     got = out_dev.cpu().numpy()
@@ -422,8 +420,8 @@ def run_b200(args):
             opc = make_op()
             opc.fit(X_dev)
             a = opc.transform_device(codes_dev, p)
-            opr = meld_b200.MELD(verbose=0, **kw)
-            opr.fit(opc.graph)
+            opr = meld_b200.MELD(verbose=0, distributed=True, dist_mode="replicated", **kw)  # whole graph + filter per rank
+            opr.fit(X_dev)
             b = opr.transform_device(codes_dev, p)
             torch.cuda.synchronize()
             if opc._sharded.ctx.error() != 0 or float((a - b).abs().max()) > 1e-9 * float(b.abs().max()):
@@ -482,6 +480,11 @@ def run_b200(args):
     ms_total = e0.elapsed_time(e1)
     step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     nnz = op.graph.nnz
+    rows_only = strong and op._sharded is not None and op.graph.n_rows != op.graph.n_cols  # this rank holds a row slice
+    if rows_only:
+        tn = torch.tensor([nnz], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tn)
+        nnz = int(tn)
     lmax = op.graph.lmax
     lmax_iters = op.graph.lmax_iters
     stats = op.graph.build_stats()
@@ -503,10 +506,12 @@ def run_b200(args):
     gc.disable()  # a generation-2 collection in the middle of a 60 ms step is measurement noise, not the engine
     t_e2e = time.perf_counter()
     f0.record()
+    e2e_host = []
     for _ in range(args.steps):
         t_s = time.perf_counter()
         op_e2e, dens = step_e2e(X_pin_np)
         e2e_steps.append(1e3 * (time.perf_counter() - t_s))  # the DataFrame is on the host when the call returns
+        e2e_host.append({k: round(1e3 * v, 2) for k, v in op_e2e.timings_.items()})
     f1.record()
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - t_e2e))
@@ -565,16 +570,23 @@ def run_b200(args):
                     "what": "{} independent replicas (one {}-cell dataset per GPU), no data-path collective".format(world, n)}
         del Xr_dev
 
+    L_full = None
+    if not args.no_parity:  # collective when no rank holds the whole graph
+        L_full = op._sharded.gather_scipy_L() if rows_only else (op.graph.to_scipy_L() if rank == 0 else None)
     if rank == 0:
         pk, pk_kind = peaks()
         if world == 1:
             par = "1 GPU"
         elif strong:
-            par = ("ONE dataset on {w} GPUs: candidate search / exact distances / eps sharded by query rows, NCCL "
-                   "all-gather of the candidate lists, Laplacian assembly + lmax replicated, Chebyshev recurrence "
-                   "row-partitioned x{w} with one exchange of the T_k slices per term ({how})").format(
-                w=world, how={"p2p": "P2P stores over NVLink from inside the SpMM kernel + flag words in peer memory",
-                              "nccl": "NCCL all-gather per term", "replicated": "none: filter replicated"}[dist_mode])
+            build = ("every rank assembles ONLY its rows of L (NCCL all-gathers of eps and of the kernel row sums, 8 N "
+                     "bytes each, + all-to-all-v of the mirrored entries)" if rows_only else
+                     "NCCL all-gather of the candidate lists, Laplacian assembly replicated")
+            par = ("ONE dataset on {w} GPUs, rows of the internal cell order partitioned x{w}: candidate search / exact "
+                   "distances / eps by query rows; {build}; Lanczos and Chebyshev recurrence row-partitioned with one "
+                   "exchange of the vector slices per term ({how})").format(
+                w=world, build=build,
+                how={"p2p": "P2P stores over NVLink from inside the SpMM kernel, halo rows only, flag words in peer memory",
+                     "nccl": "NCCL all-gather per term", "replicated": "none: filter replicated"}[dist_mode])
         else:
             par = ("{} independent replicas (one {}-cell dataset per GPU, different seeds), no data-path collective; "
                    "value = cells of all ranks / max-over-ranks time").format(world, n)
@@ -583,6 +595,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "step_ms": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms),
+                        "all": [round(v, 2) for v in step_ms],
                         "fit_median": float(np.median([a.elapsed_time(b) for a, b in fit_marks])) if fit_marks else None,
                         "filter_median": float(np.median(filt_ms)) if filt_ms else None,
                         "per_rank_min_median_max_filter": [[round(float(v), 3) for v in row] for row in per_rank]},
@@ -599,7 +612,9 @@ def run_b200(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(max(jobs, world if strong else 1) * (Xh.nbytes + 4 * n)),
                     "d2h_bytes_per_step": int(max(jobs, world if strong else 1) * 8 * n * p), "ms_per_step": e2e_ms / args.steps,
-                    "step_ms": {"min": min(e2e_steps), "median": float(np.median(e2e_steps)), "max": max(e2e_steps)},
+                    "step_ms": {"min": min(e2e_steps), "median": float(np.median(e2e_steps)), "max": max(e2e_steps),
+                                "all": [round(v, 2) for v in e2e_steps]},
+                    "host_timings_ms_slowest_step": e2e_host[int(np.argmax(e2e_steps))],
                     "input": "pinned host numpy array",
                     "pageable_input_step_ms": ({"min": min(pageable_steps), "median": float(np.median(pageable_steps)),
                                                 "max": max(pageable_steps)} if pageable_steps else None),
@@ -640,7 +655,7 @@ def run_b200(args):
             line["replicas"] = replicas
         cpu_filter_s = None
         if not args.no_parity:
-            line["parity"], cpu_filter_s = parity_block(args, op, out, labels, kw, cfg)
+            line["parity"], cpu_filter_s = parity_block(args, op, out, labels, kw, cfg, L_full)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             path = CpuPath(args, cores)

@@ -105,6 +105,32 @@ int meld_b200_graph_from_candidates(int64_t n, const int64_t *counts, const int3
                                     double thresh, double anisotropy, double bandwidth_scale, int flags, void *stream,
                                     meld_b200_graph_t **graph_out);
 
+/* ---- sharded stage 2: every rank assembles ONLY its rows of L (nothing O(nnz) is replicated or exchanged) -------
+ * Given a rank's stage-1 result `c` (rows [row_begin, row_end)), eps of ALL rows (the caller all-gathers the ranks'
+ * eps, 8 n bytes) and the ranks' row bounds (world + 1 values, host):
+ *   stage2_begin     kernel values of the local rows; entries whose reverse edge is below threshold must also appear
+ *                    in row j: local j are appended here, remote j become 16-byte records {int32 j, int32 i, f64 v}.
+ *                    Returns the number of records per owner rank (host, `world` values).
+ *   stage2_records   writes the records, grouped by owner rank in rank order, into the caller's device buffer
+ *   (caller)         all-to-all-v of the records (rank w receives the records of its rows)
+ *   stage2_assemble  counts, row pointers, fill, rows sorted by column; writes the local row sums q (row_end -
+ *                    row_begin doubles) into the caller's device buffer
+ *   (caller)         all-gather of q (8 n bytes)
+ *   stage2_finish    anisotropy + Laplacian of the local rows with the global q -> a graph handle holding rows
+ *                    [row_begin, row_end) of the n-column operator (like meld_b200_graph_row_slice), with the cell
+ *                    order of `c`.
+ * The handle borrows `c` (destroy the stage-2 handle first); `c`'s candidate arrays are consumed.                  */
+typedef struct meld_b200_stage2 meld_b200_stage2_t;
+int meld_b200_stage2_begin(meld_b200_cands_t *c, const double *eps_full, const int64_t *bounds_host, int world,
+                           int knn, double decay, double thresh, double anisotropy, double bandwidth_scale,
+                           void *stream, meld_b200_stage2_t **out, int64_t *send_counts_host);
+int meld_b200_stage2_records(meld_b200_stage2_t *st, void *records_out, void *stream);
+int meld_b200_stage2_assemble(meld_b200_stage2_t *st, const void *recv_records, int64_t n_recv, void *stream,
+                              double *q_local_out);
+int meld_b200_stage2_finish(meld_b200_stage2_t *st, const double *q_full, void *stream,
+                            meld_b200_graph_t **graph_out);
+int meld_b200_stage2_destroy(meld_b200_stage2_t *st);
+
 /* Test hook: run only the reduced-precision candidate search of knn_graph_build and return the
  * per-row pass-2 key (float, s-space) and candidate count; used to cross-check the tcgen05 search
  * against the SIMT one.  Synchronous.                                            */

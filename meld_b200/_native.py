@@ -35,6 +35,11 @@ SIGNATURES = {
     "meld_b200_cands_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "meld_b200_cands_destroy": (C.c_int, [_vp]),
     "meld_b200_graph_from_candidates": (C.c_int, [_i64, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _vp, C.POINTER(_vp)]),
+    "meld_b200_stage2_begin": (C.c_int, [_vp, _vp, _pi64, _i32, _i32, _dbl, _dbl, _dbl, _dbl, _vp, C.POINTER(_vp), _pi64]),
+    "meld_b200_stage2_records": (C.c_int, [_vp, _vp, _vp]),
+    "meld_b200_stage2_assemble": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "meld_b200_stage2_finish": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "meld_b200_stage2_destroy": (C.c_int, [_vp]),
     "meld_b200_debug_candidate_search": (C.c_int, [_vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _i32, _vp, _vp, _vp, _pi64]),
     "meld_b200_graph_from_csr": (C.c_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "meld_b200_graph_info": (C.c_int, [_vp, _pi64, _pi64, _pi64, _pi64]),

@@ -1271,18 +1271,25 @@ static int ensure_work(meld_b200_graph *g, size_t count) {
   return g->work.alloc(count);
 }
 
-// rows of an (n, p) array through a permutation: out[a] = in[perm[a]] (gather) or out[perm[a]] = in[a]
+// Internal row width of a p-column signal.  A gathered row costs one L1TEX data-pipe wavefront per load instruction
+// per lane, and only 32-byte aligned rows can be read with 256-bit loads: p = 3 (three 8-byte loads), 5, 7 (five /
+// seven) and 6 (three 16-byte loads) are padded with zero columns to 4 / 8 doubles -> one / two wavefronts per row.
+static inline int padded_width(int p) { return p <= 2 ? p : (p <= 4 ? 4 : 8); }
+
+// rows of an (n, p) array through a permutation.  The CALLER's array has p columns, the internal (graph-order) one pw
+// >= p (zero padded): gather: internal[a] = caller[perm[a]]; scatter: caller[perm[a]] = internal[a].
 __global__ void permute_rows_kernel(const double *__restrict__ in, const int32_t *__restrict__ perm, int64_t n, int p,
-                                    int scatter, double *__restrict__ out) {
-  const int64_t total = n * p;
+                                    int pw, int scatter, double *__restrict__ out) {
+  const int64_t total = n * pw;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = t / p;
-    const int j = (int)(t - i * p);
+    const int64_t i = t / pw;
+    const int j = (int)(t - i * pw);
     const int64_t o = perm ? (int64_t)perm[i] : i;
-    if (scatter)
-      out[o * p + j] = in[t];
-    else
-      out[t] = in[o * p + j];
+    if (scatter) {
+      if (j < p) out[o * p + j] = in[t];
+    } else {
+      out[t] = j < p ? in[o * p + j] : 0.0;
+    }
   }
 }
 
@@ -1499,7 +1506,7 @@ __global__ void l1_normalize_rows_kernel(const double *__restrict__ in, int64_t 
 template <int FC>
 __global__ void __launch_bounds__(256) combine_basis_kernel(const double *__restrict__ T, size_t slot_stride,
                                                            int n_terms, const double *__restrict__ C, int f0, int nf,
-                                                           const int32_t *__restrict__ perm, int64_t n, int p,
+                                                           const int32_t *__restrict__ perm, int64_t n, int p, int pw,
                                                            double *__restrict__ R) {
   extern __shared__ double cs[];  // FC x n_terms
   for (int t = threadIdx.x; t < FC * n_terms; t += blockDim.x) {
@@ -1507,8 +1514,11 @@ __global__ void __launch_bounds__(256) combine_basis_kernel(const double *__rest
     cs[t] = f < nf ? C[(size_t)(f0 + f) * n_terms + k] : 0.0;
   }
   __syncthreads();
-  const int64_t total = n * p;
+  const int64_t total = n * pw, out_total = n * p;  // the basis is stored pw wide (zero-padded), the output p wide
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / pw;
+    const int j = (int)(e - i * pw);
+    if (j >= p) continue;
     double acc[FC];
 #pragma unroll
     for (int f = 0; f < FC; ++f) acc[f] = 0.0;
@@ -1517,27 +1527,25 @@ __global__ void __launch_bounds__(256) combine_basis_kernel(const double *__rest
 #pragma unroll
       for (int f = 0; f < FC; ++f) acc[f] = __dadd_rn(acc[f], __dmul_rn(cs[f * n_terms + k], t));
     }
-    const int64_t i = e / p;
-    const int j = (int)(e - i * p);
     const int64_t o = perm ? (int64_t)perm[i] : i;
 #pragma unroll
     for (int f = 0; f < FC; ++f)
-      if (f < nf) R[(size_t)(f0 + f) * total + o * p + j] = acc[f];
+      if (f < nf) R[(size_t)(f0 + f) * out_total + o * p + j] = acc[f];
   }
 }
 
 // Last phase of a row-partitioned filter: wait until every peer has stored its rows of R into this rank's
 // buffer, bring the rows back into the caller's cell order, then tell the peers this rank's buffers are free.
 __global__ void __launch_bounds__(256) dist_unpermute_kernel(const StepArgs a, const double *__restrict__ X,
-                                                            const int32_t *__restrict__ perm, int64_t n, int p,
+                                                            const int32_t *__restrict__ perm, int64_t n, int p, int pw,
                                                             double *__restrict__ out) {
   peer_wait(a.my_flags, a.world, a.rank, a.wait_epoch, a.err_flag);
-  const int64_t total = n * p;
+  const int64_t total = n * pw;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = t / p;
-    const int j = (int)(t - i * p);
+    const int64_t i = t / pw;
+    const int j = (int)(t - i * pw);
     const int64_t o = perm ? (int64_t)perm[i] : i;
-    out[o * p + j] = __ldcg(X + t);  // written by peers over NVLink: read through L2
+    if (j < p) out[o * p + j] = __ldcg(X + t);  // written by peers over NVLink: read through L2
   }
   peer_post(a);
 }
@@ -1584,7 +1592,7 @@ int meld_b200_graph_permute_signal(const meld_b200_graph_t *g, const double *in,
   meld::use_stream(stream);
   MELD_REQUIRE(g && in && out && p >= 1 && in != out, "graph_permute_signal: bad argument");
   const int64_t n = g->n_cols;
-  permute_rows_kernel<<<grid_for(n * p, 256), 256, 0, stream>>>(in, g->perm.p, n, p, to_internal ? 0 : 1, out);
+  permute_rows_kernel<<<grid_for(n * p, 256), 256, 0, stream>>>(in, g->perm.p, n, p, p, to_internal ? 0 : 1, out);
   MELD_LAUNCH_CHECK();
   return 0;
 }
@@ -1600,13 +1608,15 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
   MELD_REQUIRE(g->row0 == 0 && g->n_rows == g->n_cols, "cheby_filter: needs the full operator (use cheby_step)");
   MELD_REQUIRE(S != R, "cheby_filter: R may not alias S");
   const int64_t n = g->n_rows;
+  // the staged kernels (x_mode 0 / 1) bulk-copy unpadded row slices; the flat kernels run on the padded width
+  const int pw = g->x_mode == 2 ? padded_width(p) : p;
   // four padded work arrays (S and R in graph order, two recurrence buffers): even length + 2 so
   // the kernel's 16-byte aligned bulk copies of row slices stay inside the allocation
-  const size_t len = ((size_t)n * p + 2 + 3) & ~(size_t)3;  // multiple of 32 bytes: 256-bit gathers on the direct path
+  const size_t len = ((size_t)n * pw + 2 + 3) & ~(size_t)3;  // multiple of 32 bytes: 256-bit gathers on the direct path
   MELD_CHECK(ensure_work(g, 4 * len));
   double *Sp = g->work.p, *Rp = Sp + len, *Ta = Rp + len, *Tb = Ta + len;
-  const int pgrid = grid_for(n * p, 256);
-  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, g->perm.p, n, p, /*scatter=*/0, Sp);  // S into graph order
+  const int pgrid = grid_for(n * pw, 256);
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, g->perm.p, n, p, pw, /*scatter=*/0, Sp);  // S into graph order
   MELD_LAUNCH_CHECK();
   const double a1 = lmax / 2.0, a2 = lmax / 2.0;
   // k = 1: T1 = (L S - a2 S)/a1 ; R = c0/2 S + c1 T1
@@ -1621,7 +1631,7 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
   a.c = coeffs_host[1];
   a.c_cur = 0.5 * coeffs_host[0];
   a.r_acc = 0;
-  MELD_CHECK(launch_step(g, a, p, 1, stream));
+  MELD_CHECK(launch_step(g, a, pw, 1, stream));
   // k = 2 still reads T0 = S, so T2 goes to the second buffer; from k = 3 on T_k overwrites T_{k-2}.
   const double *cur = Ta, *old = Sp;
   for (int k = 2; k < n_coeffs; ++k) {
@@ -1634,11 +1644,11 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
     a.c = coeffs_host[k];
     a.c_cur = 0.0;
     a.r_acc = 1;
-    MELD_CHECK(launch_step(g, a, p, 1, stream));
+    MELD_CHECK(launch_step(g, a, pw, 1, stream));
     old = cur;
     cur = nxt;
   }
-  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(Rp, g->perm.p, n, p, /*scatter=*/1, R);  // back to caller order
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(Rp, g->perm.p, n, p, pw, /*scatter=*/1, R);  // back to caller order
   MELD_LAUNCH_CHECK();
   return 0;
 }
@@ -1678,23 +1688,25 @@ int meld_b200_cheby_filter_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, doub
                (long long)d->n);
   MELD_REQUIRE(S != R, "cheby_filter_dist: R may not alias S");
   const int64_t n = gs->n_cols, nloc = gs->n_rows, row0 = gs->row0;
-  const size_t lenl = ((size_t)nloc * p + 2 + 3) & ~(size_t)3;
+  const int pw = padded_width(p);  // <= 8 <= the buffers' width
+  MELD_REQUIRE(pw <= d->p_max || pw == p, "cheby_filter_dist: padded width %d exceeds the context's %d", pw, d->p_max);
+  const size_t lenl = ((size_t)nloc * pw + 2 + 3) & ~(size_t)3;
   MELD_CHECK(ensure_work(gs, lenl));
   double *Rloc = gs->work.p;
-  const int pgrid = grid_for(n * p, 256);
+  const int pgrid = grid_for(n * pw, 256);
   // T_0 = S in graph order, every rank the whole signal (replicated, 8 n p bytes).  The peers finished storing
   // into this rank's buffers before the previous call returned here (its last phase waited for them).
   int ci = 0, oi = 1;
-  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, gs->perm.p, n, p, /*scatter=*/0, d->buf(d->rank, ci));
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, gs->perm.p, n, p, pw, /*scatter=*/0, d->buf(d->rank, ci));
   MELD_LAUNCH_CHECK();
   const double a1 = lmax / 2.0, a2 = lmax / 2.0;
   const int m = n_coeffs - 1;
   for (int k = 1; k <= m; ++k) {
     StepArgs a{};
     a.Tcur = d->buf(d->rank, ci);
-    a.Told = k >= 2 ? d->buf(d->rank, oi) + (size_t)row0 * p : nullptr;
-    a.Tnew = d->buf(d->rank, oi) + (size_t)row0 * p;  // T_k over T_{k-2}; at k = m the finished rows of R
-    fill_peer_args(a, d, oi, row0, p);
+    a.Told = k >= 2 ? d->buf(d->rank, oi) + (size_t)row0 * pw : nullptr;
+    a.Tnew = d->buf(d->rank, oi) + (size_t)row0 * pw;  // T_k over T_{k-2}; at k = m the finished rows of R
+    fill_peer_args(a, d, oi, row0, pw);
     a.halo = gs->halo.p;
     a.store_r = k == m;
     a.R = Rloc;
@@ -1707,9 +1719,9 @@ int meld_b200_cheby_filter_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, doub
     a.wait_epoch = d->epoch;  // the peers' stores of term k-1 (or their release of the buffers) are visible
     a.post_epoch = ++d->epoch;
     if (nloc > 0) {
-      MELD_CHECK(launch_step(gs, a, p, 0, stream));
+      MELD_CHECK(launch_step(gs, a, pw, 0, stream));
     } else {  // a rank without rows still takes part in every phase
-      dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, p, nullptr);
+      dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, p, p, nullptr);
       MELD_LAUNCH_CHECK();
     }
     const int t = ci;
@@ -1720,7 +1732,7 @@ int meld_b200_cheby_filter_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, doub
   fill_peer_args(a, d, 0, 0, p);
   a.wait_epoch = d->epoch;
   a.post_epoch = ++d->epoch;
-  dist_unpermute_kernel<<<pgrid, 256, 0, stream>>>(a, d->buf(d->rank, ci), gs->perm.p, n, p, R);
+  dist_unpermute_kernel<<<pgrid, 256, 0, stream>>>(a, d->buf(d->rank, ci), gs->perm.p, n, p, pw, R);
   MELD_LAUNCH_CHECK();
   return 0;
 }
@@ -1737,7 +1749,8 @@ int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeff
   MELD_REQUIRE(g->row0 == 0 && g->n_rows == g->n_cols, "cheby_sweep: needs the full operator");
   const int64_t n = g->n_rows;
   // the whole basis T_0 .. T_m is kept (n_coeffs slots of the padded signal) + the coefficient table
-  const size_t len = ((size_t)n * p + 2 + 3) & ~(size_t)3;
+  const int pw = g->x_mode == 2 ? padded_width(p) : p;
+  const size_t len = ((size_t)n * pw + 2 + 3) & ~(size_t)3;
   const size_t ctab = ((size_t)n_filters * n_coeffs + 3) & ~(size_t)3;
   MELD_CHECK(ensure_work(g, (size_t)n_coeffs * len + ctab));
   double *T = g->work.p, *Cd = T + (size_t)n_coeffs * len;
@@ -1750,8 +1763,8 @@ int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeff
     MELD_CUDA(cudaMemcpyAsync(Cd, ch.data(), ch.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     MELD_CUDA(cudaStreamSynchronize(stream));  // ch is a local
   }
-  const int pgrid = grid_for(n * p, 256);
-  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, g->perm.p, n, p, /*scatter=*/0, T);  // T_0 = S in graph order
+  const int pgrid = grid_for(n * pw, 256);
+  permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, g->perm.p, n, p, pw, /*scatter=*/0, T);  // T_0 = S in graph order
   MELD_LAUNCH_CHECK();
   const double a1 = lmax / 2.0, a2 = lmax / 2.0;
   for (int k = 1; k < n_coeffs; ++k) {
@@ -1763,14 +1776,14 @@ int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeff
     a.alpha = (k == 1 ? 1.0 : 2.0) / a1;
     a.shift = a2;
     a.gamma = k >= 2 ? 1.0 : 0.0;
-    MELD_CHECK(launch_step(g, a, p, 1, stream));
+    MELD_CHECK(launch_step(g, a, pw, 1, stream));
   }
   constexpr int FC = 16;
   const size_t smem = (size_t)FC * n_coeffs * sizeof(double);
   MELD_CUDA(cudaFuncSetAttribute(combine_basis_kernel<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int f0 = 0; f0 < n_filters; f0 += FC) {
     const int nf = n_filters - f0 < FC ? n_filters - f0 : FC;
-    combine_basis_kernel<FC><<<pgrid, 256, smem, stream>>>(T, len, n_coeffs, Cd, f0, nf, g->perm.p, n, p, R);
+    combine_basis_kernel<FC><<<pgrid, 256, smem, stream>>>(T, len, n_coeffs, Cd, f0, nf, g->perm.p, n, p, pw, R);
     MELD_LAUNCH_CHECK();
   }
   return 0;
@@ -1931,7 +1944,7 @@ int meld_b200_estimate_lmax_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, int
         MELD_CHECK(launch_step(gs, a, 1, 0, stream));
       } else {
         a.n_scal_partials = 1;  // pa[0] = 0: an empty rank publishes a zero
-        dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, 1, nullptr);
+        dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, 1, 1, nullptr);
         MELD_LAUNCH_CHECK();
       }
       StepArgs b{};  // phase B: w_{j+1} rows into every rank's vector, |w_{j+1}|^2 of these rows published

@@ -699,6 +699,12 @@ struct StageTimer {
   }
 };
 
+static int grid_for_rows(int64_t n) {
+  int64_t b = ceil_div(n > 0 ? n : 1, 256);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(b < cap ? b : (cap > 0 ? cap : 1184));
+}
+
 static int warp_grid(int64_t n_rows, int threads) {
   const int64_t warps_per_block = threads / 32;
   int64_t b = ceil_div(n_rows, warps_per_block);
@@ -1234,7 +1240,415 @@ struct meld_b200_cands {
   meld::DevBuf<int32_t> perm{true};  // n, or empty (identity)
   int32_t max_per_row = 0;
   int passes = 0;
+  double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // as meld_b200_graph::times, for the local rows
 };
+
+// ---- sharded stage 2: a rank assembles ONLY its rows of L ---------------------------------------------------------
+// Inputs per rank: its stage-1 result (candidates + exact d^2 of rows [row0, row0 + nloc)), eps of ALL rows
+// (all-gathered, 8 N bytes).  K_ij and K_ji follow from d_ij, eps_i, eps_j, so kernel values are row-local.  An entry
+// (i, j) whose reverse edge is below threshold has to appear in row j as well: j local -> appended here, j remote -> a
+// 16-byte record (j, i, v) for j's owner (all-to-all-v by the caller).  Anisotropy needs the row sums q of all rows
+// (all-gathered, 8 N bytes).  Nothing O(nnz) is replicated or exchanged.
+struct MirrorRec {
+  int32_t j, i;
+  double v;
+};
+
+namespace meld {
+
+__global__ void kernel_values_local_kernel(int64_t nloc, int64_t row0, int32_t *__restrict__ cand,
+                                           const int64_t *__restrict__ cptr, double *__restrict__ d2buf,
+                                           const double *__restrict__ eps_full, double decay, double thresh,
+                                           int32_t *__restrict__ kept, int32_t *__restrict__ extra) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < nloc; i += nwarps) {
+    const int c = (int)(cptr[i + 1] - cptr[i]);
+    int32_t *ci = cand + cptr[i];
+    double *di = d2buf + cptr[i];
+    const int32_t ig = (int32_t)(row0 + i);
+    const double ei = eps_full[ig];
+    int nk = 0;
+    for (int t = lane; t < c; t += 32) {
+      const int32_t j = ci[t];
+      const double dist = sqrt(di[t]);
+      const double kij = alpha_decay(dist, ei, decay);
+      if (kij >= thresh) {
+        double kji = (j == ig) ? kij : alpha_decay(dist, eps_full[j], decay);
+        if (kji < thresh) kji = 0.0;
+        di[t] = (kij + kji) / 2;
+        if (kji == 0.0) {
+          ci[t] = ~j;  // mirrored entry needed in row j
+          if (j >= row0 && j < row0 + nloc) atomicAdd(extra + (j - row0), 1);
+        }
+        ++nk;
+      } else {
+        ci[t] = INT32_MIN;  // dead slot
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) nk += __shfl_xor_sync(0xffffffffu, nk, o);
+    if (lane == 0) kept[i] = nk;
+  }
+}
+
+__device__ __forceinline__ int owner_of(const int64_t *bounds, int world, int64_t j) {
+  int w = 0;
+  while (w + 1 < world && j >= bounds[w + 1]) ++w;
+  return w;
+}
+
+// flagged slots whose row j lives on another rank: counted per owner (fill == 0) or written as records into the
+// owner's region of the send buffer (fill == 1; cursor[w] starts at the region's offset)
+__global__ void mirror_records_kernel(int64_t nloc, int64_t row0, const int32_t *__restrict__ cand,
+                                      const int64_t *__restrict__ cptr, const double *__restrict__ vbuf,
+                                      const int64_t *__restrict__ bounds, int world, int fill,
+                                      unsigned long long *__restrict__ cursor, MirrorRec *__restrict__ out) {
+  __shared__ int64_t sb[9];
+  if (threadIdx.x <= world) sb[threadIdx.x] = bounds[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < nloc; i += nwarps) {
+    const int c = (int)(cptr[i + 1] - cptr[i]);
+    const int32_t *ci = cand + cptr[i];
+    const double *vi = vbuf + cptr[i];
+    for (int t = lane; t < c; t += 32) {
+      const int32_t j = ci[t];
+      if (j < 0 && j != INT32_MIN) {
+        const int32_t jj = ~j;
+        if (jj < row0 || jj >= row0 + nloc) {
+          const int w = owner_of(sb, world, jj);
+          const unsigned long long pos = atomicAdd(cursor + w, 1ull);
+          if (fill) {
+            MirrorRec r;
+            r.j = jj;
+            r.i = (int32_t)(row0 + i);
+            r.v = vi[t];
+            out[pos] = r;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void count_received_kernel(const MirrorRec *__restrict__ rec, int64_t n_rec, int64_t row0, int64_t nloc,
+                                      int32_t *__restrict__ extra, int *__restrict__ err) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_rec; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = rec[t].j - row0;
+    if (j < 0 || j >= nloc) {
+      atomicExch(err, 1);
+      continue;
+    }
+    atomicAdd(extra + j, 1);
+  }
+}
+
+// fill_sym_kernel for a row slice: columns are global, mirrored entries are only appended for local rows j
+__global__ void fill_sym_local_kernel(int64_t nloc, int64_t row0, const int32_t *__restrict__ cand,
+                                      const int64_t *__restrict__ cptr, const double *__restrict__ vbuf,
+                                      const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ kept,
+                                      int32_t *__restrict__ cursor, int32_t *__restrict__ col, double *__restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < nloc; i += nwarps) {
+    const int c = (int)(cptr[i + 1] - cptr[i]);
+    const int32_t *ci = cand + cptr[i];
+    const double *vi = vbuf + cptr[i];
+    int base = row_ptr[i];
+    for (int t0 = 0; t0 < c; t0 += 32) {
+      const int t = t0 + lane;
+      int32_t j = INT32_MIN;
+      double v = 0.0;
+      if (t < c) {
+        j = ci[t];
+        v = vi[t];
+      }
+      const bool live = j != INT32_MIN;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        const bool flagged = j < 0;
+        const int32_t jj = flagged ? ~j : j;
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        col[pos] = jj;
+        val[pos] = v;
+        if (flagged && jj >= row0 && jj < row0 + nloc) {
+          const int64_t jl = jj - row0;
+          const int p2 = row_ptr[jl] + kept[jl] + atomicAdd(cursor + jl, 1);
+          col[p2] = (int32_t)(row0 + i);
+          val[p2] = v;
+        }
+      }
+      base += __popc(m);
+    }
+  }
+}
+
+__global__ void append_received_kernel(const MirrorRec *__restrict__ rec, int64_t n_rec, int64_t row0,
+                                       const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ kept,
+                                       int32_t *__restrict__ cursor, int32_t *__restrict__ col, double *__restrict__ val) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_rec; t += (int64_t)gridDim.x * blockDim.x) {
+    const MirrorRec r = rec[t];
+    const int64_t jl = r.j - row0;
+    const int p2 = row_ptr[jl] + kept[jl] + atomicAdd(cursor + jl, 1);
+    col[p2] = r.i;
+    val[p2] = r.v;
+  }
+}
+
+// laplacian_kernel for a row slice (q holds the row sums of ALL rows)
+__global__ void laplacian_local_kernel(int64_t nloc, int64_t row0, const int32_t *__restrict__ row_ptr,
+                                       const int32_t *__restrict__ col, double *__restrict__ val,
+                                       const double *__restrict__ q, double anisotropy) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < nloc; i += nwarps) {
+    const int32_t ig = (int32_t)(row0 + i);
+    const double qi = q[ig];
+    double dw = 0.0;
+    int diag = -1;
+    for (int e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
+      const int32_t j = col[e];
+      if (j == ig) {
+        diag = e;
+        continue;
+      }
+      double w = val[e];
+      if (anisotropy != 0.0) {
+        const double qq = qi * q[j];
+        w = (anisotropy == 1.0 ? 1.0 / qq : pow(qq, -anisotropy)) * w;
+      }
+      val[e] = -w;
+      dw += w;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      dw += __shfl_xor_sync(0xffffffffu, dw, o);
+      diag = max(diag, __shfl_xor_sync(0xffffffffu, diag, o));
+    }
+    if (lane == 0 && diag >= 0) val[diag] = dw;
+  }
+}
+
+}  // namespace meld
+
+// State of a sharded stage 2 between its three calls (the caller runs the collectives in between).
+struct meld_b200_stage2 {
+  meld_b200_cands *cands = nullptr;  // borrowed; its candidate / distance arrays are rewritten in place
+  BuildParams bp;
+  int64_t n = 0, row0 = 0, nloc = 0;
+  int world = 1;
+  int64_t bounds[9] = {0};
+  meld::DevBuf<int64_t> d_bounds{true};
+  meld::DevBuf<int32_t> kept{true}, extra{true};
+  meld::DevBuf<unsigned long long> cursor{true};
+  int64_t send_counts[8] = {0}, n_send = 0;
+  meld_b200_graph *g = nullptr;  // under construction
+  ~meld_b200_stage2() { delete g; }
+};
+
+extern "C" {
+
+int meld_b200_stage2_begin(meld_b200_cands_t *c, const double *eps_full, const int64_t *bounds_host, int world, int knn,
+                           double decay, double thresh, double anisotropy, double bandwidth_scale, void *stream_,
+                           meld_b200_stage2_t **out, int64_t *send_counts_host) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(c && eps_full && bounds_host && out && send_counts_host, "stage2_begin: NULL argument");
+  MELD_REQUIRE(world >= 1 && world <= 8, "stage2_begin: world=%d", world);
+  *out = nullptr;
+  meld_b200_stage2 *st = new (std::nothrow) meld_b200_stage2();
+  if (!st) {
+    set_error("stage2_begin: host allocation failed");
+    return MELD_B200_ERR_NOMEM;
+  }
+  struct Guard {
+    meld_b200_stage2 *s;
+    ~Guard() { delete s; }
+  } guard{st};
+  st->cands = c;
+  st->n = c->n;
+  st->row0 = c->row_begin;
+  st->nloc = c->row_end - c->row_begin;
+  st->world = world;
+  for (int w = 0; w <= world; ++w) st->bounds[w] = bounds_host[w];
+  MELD_REQUIRE(st->bounds[0] == 0 && st->bounds[world] == c->n, "stage2_begin: bounds do not cover [0, n)");
+  MELD_CHECK(parse_build_params("stage2_begin", c->n, 1, knn, decay, thresh, anisotropy, bandwidth_scale, 0, &st->bp));
+  const int64_t nloc = st->nloc;
+  MELD_CHECK(st->d_bounds.alloc(9));
+  MELD_CUDA(cudaMemcpyAsync(st->d_bounds.p, st->bounds, 9 * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  MELD_CHECK(st->kept.alloc((size_t)nloc + 1));
+  MELD_CHECK(st->extra.alloc((size_t)nloc + 1));
+  MELD_CHECK(st->cursor.alloc(8));
+  MELD_CUDA(cudaMemsetAsync(st->extra.p, 0, ((size_t)nloc + 1) * sizeof(int32_t), stream));
+  MELD_CUDA(cudaMemsetAsync(st->cursor.p, 0, 8 * sizeof(unsigned long long), stream));
+  kernel_values_local_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(nloc, st->row0, c->cand.p, c->cptr.p, c->d2.p,
+                                                                      eps_full, st->bp.decay, st->bp.thresh_eff,
+                                                                      st->kept.p, st->extra.p);
+  MELD_LAUNCH_CHECK();
+  mirror_records_kernel<<<warp_grid(nloc, 256), 256, 0, stream>>>(nloc, st->row0, c->cand.p, c->cptr.p, c->d2.p,
+                                                                 st->d_bounds.p, world, 0, st->cursor.p, nullptr);
+  MELD_LAUNCH_CHECK();
+  unsigned long long h_cnt[8] = {0};
+  MELD_CUDA(cudaMemcpyAsync(h_cnt, st->cursor.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  MELD_CUDA(cudaStreamSynchronize(stream));
+  st->n_send = 0;
+  for (int w = 0; w < world; ++w) {
+    st->send_counts[w] = (int64_t)h_cnt[w];
+    st->n_send += (int64_t)h_cnt[w];
+    send_counts_host[w] = (int64_t)h_cnt[w];
+  }
+  guard.s = nullptr;
+  *out = st;
+  return 0;
+}
+
+int meld_b200_stage2_records(meld_b200_stage2_t *st, void *records_out, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(st && st->cands && (st->n_send == 0 || records_out), "stage2_records: NULL argument");
+  if (st->n_send == 0) return 0;
+  unsigned long long off[8] = {0};
+  int64_t run = 0;
+  for (int w = 0; w < st->world; ++w) {
+    off[w] = (unsigned long long)run;
+    run += st->send_counts[w];
+  }
+  MELD_CUDA(cudaMemcpyAsync(st->cursor.p, off, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  MELD_CUDA(cudaStreamSynchronize(stream));  // off is a local
+  meld_b200_cands *c = st->cands;
+  mirror_records_kernel<<<warp_grid(st->nloc, 256), 256, 0, stream>>>(st->nloc, st->row0, c->cand.p, c->cptr.p, c->d2.p,
+                                                                     st->d_bounds.p, st->world, 1, st->cursor.p,
+                                                                     static_cast<MirrorRec *>(records_out));
+  MELD_LAUNCH_CHECK();
+  return 0;
+}
+
+int meld_b200_stage2_assemble(meld_b200_stage2_t *st, const void *recv_records, int64_t n_recv, void *stream_,
+                              double *q_local_out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(st && st->cands && q_local_out && (n_recv == 0 || recv_records), "stage2_assemble: NULL argument");
+  const MirrorRec *rec = static_cast<const MirrorRec *>(recv_records);
+  meld_b200_cands *c = st->cands;
+  const int64_t nloc = st->nloc, row0 = st->row0;
+  DevBuf<int> err{true};
+  MELD_CHECK(err.alloc(1));
+  MELD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
+  if (n_recv > 0) {
+    count_received_kernel<<<grid_for_rows(n_recv), 256, 0, stream>>>(rec, n_recv, row0, nloc, st->extra.p, err.p);
+    MELD_LAUNCH_CHECK();
+  }
+  DevBuf<int32_t> tot{true}, cur32{true}, max_extra{true};
+  MELD_CHECK(tot.alloc((size_t)nloc + 1));
+  add_counts_kernel<<<(unsigned)ceil_div(nloc + 1, 256), 256, 0, stream>>>(st->kept.p, st->extra.p, nloc, tot.p);
+  MELD_LAUNCH_CHECK();
+  meld_b200_graph *g = new (std::nothrow) meld_b200_graph();
+  if (!g) {
+    set_error("stage2_assemble: host allocation failed");
+    return MELD_B200_ERR_NOMEM;
+  }
+  delete st->g;
+  st->g = g;
+  g->n_rows = nloc;
+  g->n_cols = st->n;
+  g->row0 = row0;
+  MELD_CHECK(g->row_ptr.alloc((size_t)nloc + 1 + kCsrPad));
+  MELD_CUDA(cudaMemsetAsync(g->row_ptr.p + nloc + 1, 0, kCsrPad * sizeof(int32_t), stream));
+  int32_t h_nnz = 0, h_max_extra = 0;
+  int h_err = 0;
+  {
+    size_t tmp_bytes = 0;
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, tot.p, g->row_ptr.p, (int)(nloc + 1), stream));
+    DevBuf<unsigned char> tmp{true};
+    MELD_CHECK(tmp.alloc(tmp_bytes));
+    MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, tot.p, g->row_ptr.p, (int)(nloc + 1), stream));
+    MELD_CHECK(max_extra.alloc(1));
+    MELD_CUDA(cudaMemsetAsync(max_extra.p, 0, sizeof(int32_t), stream));
+    max_int_kernel<<<296, 256, 0, stream>>>(st->extra.p, nloc, max_extra.p);
+    MELD_LAUNCH_CHECK();
+    MELD_CUDA(cudaMemcpyAsync(&h_max_extra, max_extra.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaMemcpyAsync(&h_nnz, g->row_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MELD_CUDA(cudaStreamSynchronize(stream));
+  }
+  MELD_REQUIRE(h_err == 0, "stage2_assemble: a received mirror record does not belong to this rank's rows");
+  MELD_REQUIRE(h_nnz >= 0, "stage2_assemble: nnz overflows int32");
+  g->nnz = h_nnz;
+  {
+    DevBuf<int32_t> ucol{true};
+    DevBuf<double> uval{true};
+    MELD_CHECK(ucol.alloc((size_t)g->nnz + 1));
+    MELD_CHECK(uval.alloc((size_t)g->nnz + 1));
+    MELD_CHECK(cur32.alloc((size_t)nloc + 1));
+    MELD_CUDA(cudaMemsetAsync(cur32.p, 0, ((size_t)nloc + 1) * sizeof(int32_t), stream));
+    fill_sym_local_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(nloc, row0, c->cand.p, c->cptr.p, c->d2.p,
+                                                                   g->row_ptr.p, st->kept.p, cur32.p, ucol.p, uval.p);
+    MELD_LAUNCH_CHECK();
+    if (n_recv > 0) {
+      append_received_kernel<<<grid_for_rows(n_recv), 256, 0, stream>>>(rec, n_recv, row0, g->row_ptr.p, st->kept.p,
+                                                                       cur32.p, ucol.p, uval.p);
+      MELD_LAUNCH_CHECK();
+    }
+    MELD_CHECK(g->col.alloc((size_t)g->nnz + kCsrPad));
+    MELD_CHECK(g->val.alloc((size_t)g->nnz + kCsrPad));
+    MELD_CUDA(cudaMemsetAsync(g->col.p + g->nnz, 0, kCsrPad * sizeof(int32_t), stream));
+    MELD_CUDA(cudaMemsetAsync(g->val.p + g->nnz, 0, kCsrPad * sizeof(double), stream));
+    if (h_max_extra <= 2048 && tuning().merge_rows) {
+      merge_rows_kernel<<<warp_grid(nloc, 256), 256, 0, stream>>>(nloc, g->row_ptr.p, st->kept.p, ucol.p, uval.p,
+                                                                   g->col.p, g->val.p);
+      MELD_LAUNCH_CHECK();
+    } else {
+      size_t tmp_bytes = 0;
+      MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p, (int)g->nnz,
+                                                    (int)nloc, g->row_ptr.p, g->row_ptr.p + 1, stream));
+      DevBuf<unsigned char> tmp{true};
+      MELD_CHECK(tmp.alloc(tmp_bytes));
+      MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp.p, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p, (int)g->nnz,
+                                                    (int)nloc, g->row_ptr.p, g->row_ptr.p + 1, stream));
+    }
+    row_sum_kernel<<<warp_grid(nloc, 256), 256, 0, stream>>>(nloc, g->row_ptr.p, g->val.p, q_local_out);
+    MELD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int meld_b200_stage2_finish(meld_b200_stage2_t *st, const double *q_full, void *stream_, meld_b200_graph_t **graph_out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  meld::use_stream(stream);
+  MELD_REQUIRE(st && st->g && q_full && graph_out, "stage2_finish: NULL argument (stage2_assemble first)");
+  meld_b200_graph *g = st->g;
+  laplacian_local_kernel<<<warp_grid(st->nloc, 256), 256, 0, stream>>>(st->nloc, st->row0, g->row_ptr.p, g->col.p,
+                                                                      g->val.p, q_full, st->bp.anisotropy);
+  MELD_LAUNCH_CHECK();
+  MELD_CHECK(graph_finalize(g, stream));
+  if (st->cands->perm.p) {
+    MELD_CHECK(g->perm.alloc((size_t)st->n));
+    MELD_CUDA(cudaMemcpyAsync(g->perm.p, st->cands->perm.p, (size_t)st->n * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                              stream));
+  }
+  g->stats[0] = st->cands->passes;
+  g->stats[1] = st->cands->max_per_row;
+  g->stats[2] = st->cands->total;
+  for (int i = 0; i < 8; ++i) g->times[i] = st->cands->times[i];
+  st->g = nullptr;
+  *graph_out = g;
+  return 0;
+}
+
+int meld_b200_stage2_destroy(meld_b200_stage2_t *st) {
+  if (st) {
+    cudaDeviceSynchronize();
+    meld::use_stream(nullptr);
+  }
+  delete st;
+  return 0;
+}
+
+}  // extern "C"
 
 extern "C" {
 
@@ -1358,6 +1772,11 @@ int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, dou
   c->total = cs.total;
   c->max_per_row = cs.max_per_row;
   c->passes = cs.passes;
+  c->times[0] = cs.pass1_ms;
+  c->times[1] = cs.pass2_ms;
+  c->times[2] = cs.gemm_flops_per_pass;
+  c->times[3] = cs.gemm_flops_pass1;
+  c->times[4] = cs.tile_frac > 0 ? cs.gemm_flops_per_pass / cs.tile_frac : cs.gemm_flops_per_pass;
   // the handle keeps its own copies (the search's buffers live in the build arena)
   MELD_CHECK(c->cptr.alloc(cs.cptr.n));
   MELD_CHECK(c->cand.alloc(cs.cand.n));
@@ -1489,8 +1908,8 @@ int meld_b200_graph_build_times(const meld_b200_graph_t *g, double *times8_host)
 int meld_b200_graph_permutation(const meld_b200_graph_t *g, int32_t *perm_out, int *is_identity_host, void *stream_) {
   MELD_REQUIRE(g && is_identity_host, "graph_permutation: NULL argument");
   *is_identity_host = g->perm.p ? 0 : 1;
-  if (g->perm.p && perm_out)
-    MELD_CUDA(cudaMemcpyAsync(perm_out, g->perm.p, (size_t)g->n_rows * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+  if (g->perm.p && perm_out)  // n_cols entries: a row slice keeps the whole operator's cell order
+    MELD_CUDA(cudaMemcpyAsync(perm_out, g->perm.p, (size_t)g->n_cols * sizeof(int32_t), cudaMemcpyDeviceToDevice,
                               (cudaStream_t)stream_));
   return 0;
 }

@@ -173,7 +173,10 @@ class ShardedFilter:
     order and gets the same (N, p) result.  ``graph`` is the FULL DeviceGraph (every rank holds one after a
     sharded build); its rows are sliced here."""
 
-    def __init__(self, graph, group=None, mode="p2p", p_max=8):
+    def __init__(self, graph, group=None, mode="p2p", p_max=8, row_slice=None, bounds=None):
+        """``graph``: the FULL DeviceGraph (its rows are sliced here in equal chunks), or -- p2p mode only -- pass the
+        rank's ready ``row_slice`` with the ranks' row ``bounds`` (what ``DeviceGraph.from_data_sharded_rows`` returns):
+        then no rank ever holds the whole graph."""
         import torch.distributed as dist
 
         if mode not in ("p2p", "nccl"):
@@ -183,11 +186,25 @@ class ShardedFilter:
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         else:
             self.rank, self.world = 0, 1
+        self._nccl_bufs = {}
+        self.halo_fraction = 1.0
+        self._own_slice = row_slice is None
+        if row_slice is not None:
+            if mode != "p2p":
+                raise ValueError("a ready row slice needs mode='p2p' (the NCCL all-gather wants equal chunks)")
+            self.N = row_slice.n_cols
+            self.bounds = list(bounds)
+            self.chunk = max(self.bounds[r + 1] - self.bounds[r] for r in range(self.world))
+            self.row_range = (self.bounds[self.rank], self.bounds[self.rank + 1])
+            assert self.row_range == (row_slice.row0, row_slice.row0 + row_slice.n_rows)
+            self.slice = row_slice
+            self.ctx = shared_context(self.N, self.p_max, self.group)
+            if self.world > 1:
+                self._exchange_halo()
+            return
         self.N = graph.N
         self.chunk, self.bounds = chunk_partition(self.N, self.world)
         self.row_range = (self.bounds[self.rank], self.bounds[self.rank + 1])
-        self._nccl_bufs = {}
-        self.halo_fraction = 1.0
         self._attach()
 
     def _attach(self):
@@ -206,17 +223,21 @@ class ShardedFilter:
         from . import _native as nv
 
         lib = nv.lib()
-        dev = self.graph.device
-        ref = torch.zeros(self.world * self.chunk, dtype=torch.uint8, device=dev)
+        dev = self.slice.device
+        a, b = self.row_range
+        nloc = b - a
+        rows = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
+        ref = torch.zeros(max(self.N, 1), dtype=torch.uint8, device=dev)  # my marks of ALL columns, in row order
         nv.check(lib.meld_b200_graph_mark_columns(self.slice._h, nv.ptr(ref), nv.current_stream_ptr()), "graph_mark_columns")
-        recv = torch.empty_like(ref)
-        dist.all_to_all_single(recv, ref, group=self.group)  # recv[w * chunk + i] = rank w's mark of my row i
-        nv.check(lib.meld_b200_graph_set_halo(self.slice._h, nv.ptr(recv), self.chunk, self.world, self.rank,
+        recv = torch.empty(max(self.world * nloc, 1), dtype=torch.uint8, device=dev)
+        # rank w's marks of MY rows arrive at recv[w * nloc : (w + 1) * nloc]
+        dist.all_to_all_single(recv[: self.world * nloc], ref[: self.N], output_split_sizes=[nloc] * self.world,
+                               input_split_sizes=rows, group=self.group)
+        nv.check(lib.meld_b200_graph_set_halo(self.slice._h, nv.ptr(recv), max(nloc, 1), self.world, self.rank,
                                               nv.current_stream_ptr()), "graph_set_halo")
         peers = [w for w in range(self.world) if w != self.rank]
-        a, b = self.row_range
         # fraction of (row, peer) pairs that actually travel per term (1.0 = plain all-gather)
-        self.halo_fraction = float(recv.view(self.world, self.chunk)[peers, : max(b - a, 1)].float().mean()) if b > a else 0.0
+        self.halo_fraction = float(recv[: self.world * nloc].view(self.world, nloc)[peers].float().mean()) if nloc else 0.0
         torch.cuda.current_stream().synchronize()  # recv / ref die here
 
     # ---- the two native operations of the NCCL path (overridden by the CPU / gloo test) -----------------
@@ -322,4 +343,28 @@ class ShardedFilter:
         return R
 
     def close(self):
-        self.slice.close()  # the peer context is shared (shared_context) and lives until the process ends
+        if self._own_slice:
+            self.slice.close()  # the peer context is shared (shared_context) and lives until the process ends
+
+    def gather_scipy_L(self):
+        """COLLECTIVE: the whole Laplacian in the caller's cell order as a scipy CSR matrix on rank 0 (None elsewhere)
+        -- parity checks and debugging only; the data path never assembles it."""
+        import torch.distributed as dist
+        from scipy import sparse
+
+        local = self.slice.to_scipy_L()  # rows [a, b) in the internal order, global columns
+        if self.world == 1:
+            parts = [local]
+        else:
+            parts = [None] * self.world if self.rank == 0 else None
+            dist.gather_object((local.indptr, local.indices, local.data), parts, dst=0, group=self.group)
+            if self.rank != 0:
+                return None
+            parts = [sparse.csr_matrix((d, i, p), shape=(len(p) - 1, self.N)) for p, i, d in parts]
+        M = sparse.vstack(parts).tocsr()
+        perm = self.slice.permutation()
+        if perm is not None:
+            coo = M.tocoo()
+            M = sparse.csr_matrix((coo.data, (perm[coo.row], perm[coo.col])), shape=M.shape)
+        M.sort_indices()
+        return M

@@ -269,6 +269,80 @@ class DeviceGraph:
         return g
 
     @classmethod
+    def from_data_sharded_rows(cls, data_nu, knn=5, decay=40.0, thresh=1e-4, anisotropy=1.0, bandwidth_scale=1.0,
+                               group=None):
+        """Fully row-partitioned build: every rank ends with ONLY its rows of L (a slice handle, internal cell order) --
+        nothing O(nnz) is replicated or exchanged.  Stage 1 as in :meth:`from_data_sharded`; then an
+        all-gather of eps (8 N bytes), an all-to-all-v of the mirrored entries (~10 x 16 bytes per row) and an
+        all-gather of the kernel row sums (8 N bytes) around the three ``meld_b200_stage2_*`` calls.  Returns
+        ``(slice_graph, bounds)``; every rank passes the same data."""
+        torch = nv.require_cuda()
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        X = _as_device_f64(torch, data_nu)
+        N, d = X.shape
+        knn = _clamp_knn(knn, N)
+        decay = 0.0 if decay is None else decay
+        bounds = cls.shard_bounds(N, world)
+        if any(bounds[r + 1] <= bounds[r] for r in range(world)):
+            raise ValueError("{} cells are too few for {} row-partitioned ranks (512-row tiles)".format(N, world))
+        dev, lib = X.device, nv.lib()
+        a, b = bounds[rank], bounds[rank + 1]
+        nloc = b - a
+        rows = [bounds[r + 1] - bounds[r] for r in range(world)]
+        rows_max = max(rows)
+        h, st = C.c_void_p(), C.c_void_p()
+        nv.check(lib.meld_b200_knn_candidates(nv.ptr(X), N, d, int(knn), float(decay), float(thresh),
+                                              float(bandwidth_scale), int(a), int(b), 0, nv.current_stream_ptr(),
+                                              C.byref(h)), "knn_candidates")
+        try:
+            c_n, c_t, c_p, c_m = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+            nv.check(lib.meld_b200_cands_info(h, C.byref(c_n), C.byref(c_t), C.byref(c_p), C.byref(c_m)), "cands_info")
+
+            def allgather_rows(local):  # (rows_max,) padded slices -> the N-vector in row order
+                out = torch.empty(world * rows_max, dtype=local.dtype, device=dev)
+                dist.all_gather_into_tensor(out, local, group=group)
+                if all(r == rows_max for r in rows):
+                    return out
+                return torch.cat([out[r * rows_max: r * rows_max + rows[r]] for r in range(world)])
+
+            eps_loc = torch.zeros(rows_max, dtype=torch.float64, device=dev)
+            nv.check(lib.meld_b200_cands_export(h, C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), nv.ptr(eps_loc),
+                                                C.c_void_p(0), nv.current_stream_ptr()), "cands_export")
+            eps_full = allgather_rows(eps_loc)
+            hb = (C.c_int64 * (world + 1))(*bounds)
+            hc = (C.c_int64 * world)()
+            nv.check(lib.meld_b200_stage2_begin(h, nv.ptr(eps_full), hb, world, int(knn), float(decay), float(thresh),
+                                                float(anisotropy), float(bandwidth_scale), nv.current_stream_ptr(),
+                                                C.byref(st), hc), "stage2_begin")
+            send_counts = [int(v) for v in hc]
+            sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc, group=group)
+            recv_counts = rc.cpu().tolist()
+            send = torch.empty(max(sum(send_counts), 1) * 16, dtype=torch.uint8, device=dev)
+            nv.check(lib.meld_b200_stage2_records(st, nv.ptr(send), nv.current_stream_ptr()), "stage2_records")
+            recv = torch.empty(max(sum(recv_counts), 1) * 16, dtype=torch.uint8, device=dev)
+            dist.all_to_all_single(recv[: sum(recv_counts) * 16], send[: sum(send_counts) * 16],
+                                   output_split_sizes=[16 * v for v in recv_counts],
+                                   input_split_sizes=[16 * v for v in send_counts], group=group)
+            q_loc = torch.zeros(rows_max, dtype=torch.float64, device=dev)
+            nv.check(lib.meld_b200_stage2_assemble(st, nv.ptr(recv), int(sum(recv_counts)), nv.current_stream_ptr(),
+                                                   nv.ptr(q_loc)), "stage2_assemble")
+            q_full = allgather_rows(q_loc)
+            out = C.c_void_p()
+            nv.check(lib.meld_b200_stage2_finish(st, nv.ptr(q_full), nv.current_stream_ptr(), C.byref(out)),
+                     "stage2_finish")
+            torch.cuda.current_stream().synchronize()
+        finally:
+            if st.value:
+                lib.meld_b200_stage2_destroy(st)
+            lib.meld_b200_cands_destroy(h)
+        params = dict(knn=knn, decay=decay, thresh=thresh, anisotropy=anisotropy, bandwidth_scale=bandwidth_scale)
+        return cls(out.value, params, device=dev), bounds
+
+    @classmethod
     def from_scipy(cls, L, row0=0, n_cols=None, params=None):
         """Adopt a Laplacian (or a row slice of one) built elsewhere, e.g. by the test oracle."""
         torch = nv.require_cuda()
@@ -355,6 +429,9 @@ class DeviceGraph:
             (data[:nnz].cpu().numpy(), indices[:nnz].cpu().numpy(), indptr.cpu().numpy()),
             shape=(self.n_rows, self.n_cols),
         )
+        if self.n_rows != self.n_cols:  # a row slice: rows [row0, row0 + n_rows) in the INTERNAL cell order
+            M.sort_indices()
+            return M
         perm = self.permutation()
         if perm is not None:  # rows / columns back to the caller's cell order
             coo = M.tocoo()
@@ -366,7 +443,7 @@ class DeviceGraph:
         """Internal cell order: graph row a is the caller's cell ``perm[a]`` (None = identity)."""
         torch = nv.require_cuda()
         ident = C.c_int(1)
-        perm = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
+        perm = torch.empty(self.n_cols, dtype=torch.int32, device=self.device)
         nv.check(nv.lib().meld_b200_graph_permutation(self._h, nv.ptr(perm), C.byref(ident), nv.current_stream_ptr()),
                  "graph_permutation")
         if ident.value:

@@ -104,6 +104,10 @@ class MELD(object):
         # "nccl" = row-partitioned with an NCCL all-gather per term, "replicated" = every rank filters alone
         self.dist_mode = kwargs.pop("dist_mode", "p2p")
         _check_in(["p2p", "nccl", "replicated"], dist_mode=self.dist_mode)
+        # how a distributed estimator assembles the graph: "rows" = every rank only its rows (nothing O(nnz) replicated;
+        # needs dist_mode="p2p"), "replicated" = candidate lists all-gathered, every rank assembles the whole graph
+        self.dist_build = kwargs.pop("dist_build", "rows" if self.dist_mode == "p2p" else "replicated")
+        _check_in(["rows", "replicated"], dist_build=self.dist_build)
         self._sharded = None
         self.anisotropy = anisotropy
         self.n_landmark = n_landmark
@@ -260,7 +264,7 @@ class MELD(object):
         extra.pop("use_pygsp", None)
         self._check_supported(extra)
         build_key = (self.knn, self.decay, self.thresh, self.anisotropy, self.n_pca, self.random_state, self.distributed,
-                     self.dist_mode, tuple(sorted(extra.items())))
+                     self.dist_mode, self.dist_build, tuple(sorted(extra.items())))
         if (self.graph is not None and self.X is not None and getattr(self, "_build_key", None) == build_key
                 and _same_data(torch, X, self.X)):
             return self  # same data AND same effective build parameters: keep the graph
@@ -272,26 +276,34 @@ class MELD(object):
         data_nu = self._reduce_data(X)
         self._log("Calculating graph and diffusion operator...")
         t1 = time.perf_counter()
+        slice_bounds = None
         if self.thresh == 0 and self.decay is not None:
             # graphtools.api.Graph: thresh == 0 with a decay selects the dense "exact" graph (TraditionalGraph)
             self.graph = DeviceGraph.from_data_dense(data_nu, knn=self.knn, decay=self.decay, anisotropy=self.anisotropy,
                                                      bandwidth_scale=extra.get("bandwidth_scale", 1.0))
         else:
             build = DeviceGraph.from_data
-            if self.distributed:  # candidate search sharded over the ranks of torch.distributed (same data everywhere)
+            rows_only = self.distributed and self.dist_mode == "p2p" and self.dist_build == "rows"
+            if rows_only:  # every rank assembles only its rows of L
+                build = DeviceGraph.from_data_sharded_rows
+            elif self.distributed:  # candidate search sharded over the ranks (same data everywhere), full graph on each
                 build = DeviceGraph.from_data_sharded
-            self.graph = build(
+            built = build(
                 data_nu, knn=self.knn, decay=0.0 if self.decay is None else self.decay, thresh=self.thresh,
                 anisotropy=self.anisotropy,
                 bandwidth_scale=extra.get("bandwidth_scale", 1.0),
             )
+            self.graph, slice_bounds = built if rows_only else (built, None)
         if self._sharded is not None:
             self._sharded.close()
             self._sharded = None
-        if self.distributed and self.dist_mode != "replicated":
+        if self.distributed and self.dist_mode != "replicated" and not (self.thresh == 0 and self.decay is not None):
             from .distributed import ShardedFilter
 
-            self._sharded = ShardedFilter(self.graph, mode=self.dist_mode)
+            if slice_bounds is not None:
+                self._sharded = ShardedFilter(None, mode="p2p", row_slice=self.graph, bounds=slice_bounds)
+            else:
+                self._sharded = ShardedFilter(self.graph, mode=self.dist_mode)
         self.timings_["graph"] = time.perf_counter() - t1
         self._log("Calculated graph and diffusion operator in {:.2f} seconds.".format(time.perf_counter() - t0))
         self.X = X

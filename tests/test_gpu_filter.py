@@ -353,9 +353,9 @@ def test_peer_store_filter_ranks_in_one_process(mb, world, halo):
     if halo:  # rows only go to the peers that reference them (what ShardedFilter._exchange_halo sets up over NCCL)
         refs = []
         for r in range(world):
-            ref = torch.zeros(world * chunk, dtype=torch.uint8, device="cuda")
-            nv.check(lib.meld_b200_graph_mark_columns(slices[r]._h, nv.ptr(ref), nv.current_stream_ptr()), "mark")
-            refs.append(ref)
+            marks = torch.zeros(world * chunk, dtype=torch.uint8, device="cuda")
+            nv.check(lib.meld_b200_graph_mark_columns(slices[r]._h, nv.ptr(marks), nv.current_stream_ptr()), "mark")
+            refs.append(marks)
         sent = 0
         for r in range(world):
             recv = torch.cat([refs[w][r * chunk:(r + 1) * chunk] for w in range(world)])  # the all-to-all

@@ -223,3 +223,89 @@ def test_device_pca_matches_sklearn(mb):
     dens = op.transform(labels)
     normwise, ok = density_parity(dens.values, ref.values, 1e-5)
     assert ok and normwise < 1e-7, normwise
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_partitioned_stage2_matches_single_call(mb, world):
+    """The fully sharded build (meld_b200_stage2_*: every rank assembles only its rows of L), all ranks driven on one
+    GPU with the collectives done by hand: eps all-gather = concatenation, all-to-all-v of the mirror records =
+    re-grouping the send buffers, row-sum all-gather = concatenation.  The stacked slices equal the single-call
+    Laplacian bit for bit."""
+    import ctypes as C
+    import torch
+    from scipy import sparse
+    from meld_b200 import _native as nv
+    from meld_b200.graph import DeviceGraph, _as_device_f64
+
+    lib = nv.lib()
+    X, _ = mb.synthetic.make_blobs(6000, 30, 6, 3, 8.0, seed=5)  # >= 4096 cells: the internal cell order is active
+    kw = dict(knn=9, decay=40.0, thresh=1e-4)
+    full = DeviceGraph.from_data(X, anisotropy=1.0, **kw)
+    ref = full.to_scipy_L()
+    Xd = _as_device_f64(torch, X)
+    N = X.shape[0]
+    bounds = DeviceGraph.shard_bounds(N, world)
+    sp = nv.current_stream_ptr
+    hs, eps = [], []
+    for r in range(world):
+        h = C.c_void_p()
+        nv.check(lib.meld_b200_knn_candidates(nv.ptr(Xd), N, X.shape[1], 9, 40.0, 1e-4, 1.0, bounds[r], bounds[r + 1], 0,
+                                              sp(), C.byref(h)), "knn_candidates")
+        e = torch.zeros(bounds[r + 1] - bounds[r], dtype=torch.float64, device="cuda")
+        nv.check(lib.meld_b200_cands_export(h, None, None, None, nv.ptr(e), None, sp()), "cands_export")
+        hs.append(h)
+        eps.append(e)
+    eps_full = torch.cat(eps)
+    hb = (C.c_int64 * (world + 1))(*bounds)
+    sts, counts, sends = [], [], []
+    for r in range(world):
+        st, hc = C.c_void_p(), (C.c_int64 * world)()
+        nv.check(lib.meld_b200_stage2_begin(hs[r], nv.ptr(eps_full), hb, world, 9, 40.0, 1e-4, 1.0, 1.0, sp(), C.byref(st),
+                                            hc), "stage2_begin")
+        cnt = [int(v) for v in hc]
+        assert cnt[r] == 0  # a rank never sends records to itself
+        buf = torch.empty(max(sum(cnt), 1) * 16, dtype=torch.uint8, device="cuda")
+        nv.check(lib.meld_b200_stage2_records(st, nv.ptr(buf), sp()), "stage2_records")
+        sts.append(st)
+        counts.append(cnt)
+        sends.append(buf)
+    assert sum(sum(c) for c in counts) > 0  # rows of different ranks do mirror into each other
+    qs = []
+    for r in range(world):  # the all-to-all-v: what every source grouped for destination r
+        parts = []
+        for s_ in range(world):
+            off = 16 * sum(counts[s_][:r])
+            parts.append(sends[s_][off: off + 16 * counts[s_][r]])
+        recv = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device="cuda")
+        n_recv = recv.numel() // 16
+        if n_recv == 0:
+            recv = torch.empty(16, dtype=torch.uint8, device="cuda")
+        q = torch.zeros(bounds[r + 1] - bounds[r], dtype=torch.float64, device="cuda")
+        nv.check(lib.meld_b200_stage2_assemble(sts[r], nv.ptr(recv), n_recv, sp(), nv.ptr(q)), "stage2_assemble")
+        torch.cuda.synchronize()
+        qs.append(q)
+    q_full = torch.cat(qs)
+    slices = []
+    for r in range(world):
+        out = C.c_void_p()
+        nv.check(lib.meld_b200_stage2_finish(sts[r], nv.ptr(q_full), sp(), C.byref(out)), "stage2_finish")
+        slices.append(DeviceGraph(out.value, device=Xd.device))
+    torch.cuda.synchronize()
+    for r in range(world):
+        lib.meld_b200_stage2_destroy(sts[r])
+        lib.meld_b200_cands_destroy(hs[r])
+    assert [(g.row0, g.n_rows, g.n_cols) for g in slices] == [(bounds[r], bounds[r + 1] - bounds[r], N) for r in range(world)]
+    M = sparse.vstack([g.to_scipy_L() for g in slices]).tocsr()
+    perm = slices[0].permutation()
+    coo = M.tocoo()
+    M = sparse.csr_matrix((coo.data, (perm[coo.row], perm[coo.col])), shape=M.shape)
+    M.sort_indices()
+    assert _same_pattern(M, ref)
+    assert np.array_equal(M.data, ref.data)
+    # the slices drive the row-partitioned filter like slices cut from a full graph
+    lmax = full.estimate_lmax()
+    for g, r in zip(slices, range(world)):
+        cut = full.row_slice(bounds[r], bounds[r + 1]).to_scipy_L()
+        mine = g.to_scipy_L()
+        assert _same_pattern(mine, cut) and np.array_equal(mine.data, cut.data)
+    assert lmax > 0

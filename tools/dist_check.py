@@ -88,6 +88,20 @@ def main():
         say(mode=mode, world=world, rel_err_vs_full=err, flag_timeout=bad, filter_ms=round(best, 3),
             us_per_term=round(1e3 * best / m, 2), halo_fraction_rank0=round(sf.halo_fraction, 4))
         sf.close()
+    # fully row-partitioned build: gather the slices and compare with the single-GPU Laplacian
+    gs, bounds = meld_b200.DeviceGraph.from_data_sharded_rows(Xd, knn=kw.get("knn", 5))
+    sfr = ShardedFilter(None, mode="p2p", row_slice=gs, bounds=bounds)
+    Lg = sfr.gather_scipy_L()
+    if rank == 0:
+        Ls = ref_op.graph.to_scipy_L()
+        same = Lg.nnz == Ls.nnz and np.array_equal(Lg.indptr, Ls.indptr) and np.array_equal(Lg.indices, Ls.indices)
+        say(check="row-partitioned build vs single-GPU L", pattern_equal=bool(same),
+            max_abs_diff=float(np.abs(Lg.data - Ls.data).max()) if same else None, halo_fraction_rank0=round(sfr.halo_fraction, 4))
+    lm = sfr.estimate_lmax()
+    outr = sfr.apply(lm, coeffs, S)
+    torch.cuda.synchronize()
+    say(check="row-partitioned build + lanczos + filter vs single GPU", lmax_rel=abs(lm - lmax) / lmax,
+        rel=float((outr - full).abs().max() / full.abs().max()), flag_timeout=sfr.ctx.error())
     # single-GPU filter time for the ratio
     best = 1e9
     for _ in range(args.reps):
@@ -100,9 +114,10 @@ def main():
         best = min(best, e0.elapsed_time(e1))
     say(mode="single GPU (replicated)", filter_ms=round(best, 3), us_per_term=round(1e3 * best / m, 2))
     # whole fit_transform, distributed vs single
-    for mode in ("p2p", "nccl", "replicated"):
+    for mode in ("p2p rows", "p2p", "nccl", "replicated"):
         def step():
-            op = meld_b200.MELD(verbose=0, distributed=True, dist_mode=mode, **kw)
+            dm, db = (mode.split()[0], "rows") if mode.endswith("rows") else (mode, "replicated")
+            op = meld_b200.MELD(verbose=0, distributed=True, dist_mode=dm, dist_build=db, **kw)
             op.fit(Xd)
             return op.transform_device(codes, p)
         for _ in range(2):
