@@ -84,6 +84,7 @@ struct Tuning {
   int prune = 1;          // candidate search skips (row tile, column tile) pairs that bounding balls prove too far apart
   int clusters = 64;      // k-means clusters of the internal cell order (0: Morton order only)
   int kmeans_iters = 1;   // Lloyd iterations after seeding
+  int km_var_pct = 99;    // k-means / projection features: leading ones up to this % of the total variance (0: up to 128)
   int reorder_min_n = 4096;  // cells are re-ordered (clusters + Morton curve) from this size on
   int merge_rows = 1;     // graph assembly places mirrored entries by rank instead of a segmented sort of every row
   int prune_proj = 1;     // tile pruning also uses the projection bound between k-means clusters

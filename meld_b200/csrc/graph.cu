@@ -392,6 +392,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "prune")) t.prune = value;
   else if (!strcmp(key, "clusters")) t.clusters = value;
   else if (!strcmp(key, "kmeans_iters")) t.kmeans_iters = value;
+  else if (!strcmp(key, "km_var_pct")) t.km_var_pct = value;
   else if (!strcmp(key, "reorder_min_n")) t.reorder_min_n = value;
   else if (!strcmp(key, "prune_window")) t.prune_window = value;
   else if (!strcmp(key, "cluster_cells")) t.cluster_cells = value;

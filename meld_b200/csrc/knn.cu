@@ -744,9 +744,27 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
   std::vector<int> order((size_t)d);
   for (int64_t k = 0; k < d; ++k) order[(size_t)k] = (int)k;
   const int ndim = d < 4 ? (int)d : 4;
-  const int nd = d < kKmDims ? (int)d : kKmDims;  // features of the k-means step
+  int nd = d < kKmDims ? (int)d : kKmDims;  // features of the k-means step
   std::partial_sort(order.begin(), order.begin() + nd, order.end(),
                     [&](int a, int b) { return h_var[a] > h_var[b] || (h_var[a] == h_var[b] && a < b); });
+  // Clustering (and the projection bound that rides on it) only needs the features that carry the variance: keep the
+  // leading ones up to km_var_pct % of the total, in steps of 32.  PCA-like data (config 4: 99.8 % in 32 of 100
+  // features) runs the assignment and the tile projections over a quarter of the columns; a flat spectrum keeps all
+  // 128.  Any subset is valid: a bound on the distance within a feature subset bounds the full distance.
+  if (tuning().km_var_pct > 0 && tuning().km_var_pct < 100 && nd > 32) {
+    double tot = 0.0, cum = 0.0;
+    for (int64_t k = 0; k < d; ++k) tot += h_var[(size_t)k];
+    int keep = nd;
+    for (int k = 0; k < nd; ++k) {
+      cum += h_var[(size_t)order[(size_t)k]];
+      if (cum >= 0.01 * tuning().km_var_pct * tot) {
+        keep = k + 1;
+        break;
+      }
+    }
+    keep = (keep + 31) / 32 * 32;
+    if (keep < nd) nd = keep;
+  }
   MortonDims md;
   md.ndim = ndim;
   for (int k = 0; k < 4; ++k) {

@@ -405,11 +405,13 @@ class MELD(object):
         dev = self.graph.device
         d_codes = torch.from_numpy(codes).to(dev, non_blocking=True)
         densities = self.transform_device(d_codes, len(samples))
-        # pinned staging (torch's caching host allocator): a pageable 16 MB read-back costs ~3x as long
-        staged = torch.empty(densities.shape, dtype=densities.dtype, device="cpu", pin_memory=True)
+        # Read-back through ONE persistent pinned staging buffer per size (a pageable 16 MB read-back costs ~3x as long;
+        # a fresh pinned allocation per call costs a cudaHostAlloc of milliseconds, because the DataFrame returned last
+        # time still owns the previous block), then a multi-threaded host copy into the array the DataFrame keeps.
+        staged = _pinned_staging(torch, densities)
         staged.copy_(densities, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        host = staged.numpy()
+        host = torch.empty(densities.shape, dtype=densities.dtype).copy_(staged).numpy()
         self.timings_["transform"] = time.perf_counter() - t0
         self.sample_densities = pd.DataFrame(host, index=self._labels_index, columns=self.samples)
         return self.sample_densities
@@ -561,6 +563,19 @@ class MELD(object):
                 worker.join()
         self.timings_["fit_and_join"] = time.perf_counter() - t_fit
         return self.transform(sample_labels, _codes=pre.get("codes"))
+
+
+_STAGING = {}
+
+
+def _pinned_staging(torch, like):
+    key = (tuple(like.shape), like.dtype)
+    buf = _STAGING.get(key)
+    if buf is None:
+        if len(_STAGING) >= 4:
+            _STAGING.clear()
+        buf = _STAGING[key] = torch.empty(like.shape, dtype=like.dtype, device="cpu", pin_memory=True)
+    return buf
 
 
 _HASH_MULT = np.random.default_rng(0x5EED).integers(1, 2**63 - 1, size=64, dtype=np.int64).astype(np.uint64) | np.uint64(1)

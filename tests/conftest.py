@@ -1,6 +1,11 @@
 import os
 import sys
 
+# Tests that drive several "ranks" of the peer-store protocol inside ONE process let a kernel of rank A spin on a flag
+# that a later kernel of rank B sets.  With CUDA's lazy module loading the first launch of a not-yet-loaded kernel can
+# wait for the device to drain, i.e. for A's spin to time out.  Real multi-process runs are not affected.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import numpy as np
 import pytest
 

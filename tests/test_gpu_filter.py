@@ -35,6 +35,19 @@ def _close(a, b, rtol=1e-12):
     return float((a - b).abs().max()) <= rtol * float(b.abs().max())
 
 
+def _load_dist_kernels(mb, graph, p):
+    """Launch every kernel of the peer-store path once with a single rank (see conftest: lazy module loading)."""
+    import torch
+    from meld_b200.distributed import ShardedFilter
+
+    sf = ShardedFilter(graph, mode="p2p")
+    lm = sf.estimate_lmax()
+    S = torch.zeros((graph.N, p), dtype=torch.float64, device="cuda")
+    sf.apply(lm, np.array([1.0, 0.5, 0.25]), S)
+    torch.cuda.synchronize()
+    sf.close()
+
+
 def _oracle():
     from oracle import cheby, graph, meld as omeld
 
@@ -349,6 +362,7 @@ def test_peer_store_filter_ranks_in_one_process(mb, world, halo):
     c = np.ascontiguousarray(mb.filter.cheby_coefficients(mb.filter.filter_kernel("heat", 40), lmax, m))
     ref = mb.filter.cheby_apply(graph, lmax, c, S)
     chunk, bounds = chunk_partition(N, world)
+    _load_dist_kernels(mb, graph, p)
     slices = [graph.row_slice(bounds[r], bounds[r + 1]) for r in range(world)]
     if halo:  # rows only go to the peers that reference them (what ShardedFilter._exchange_halo sets up over NCCL)
         refs = []
@@ -461,6 +475,7 @@ def test_row_partitioned_lanczos_ranks_in_one_process(mb, world):
     ref = graph.estimate_lmax()
     N = graph.N
     chunk, bounds = chunk_partition(N, world)
+    _load_dist_kernels(mb, graph, 3)
     slices = [graph.row_slice(bounds[r], bounds[r + 1]) for r in range(world)]
     ctxs = []
     for r in range(world):

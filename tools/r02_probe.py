@@ -136,9 +136,13 @@ def main():
         # cell-order / pruning knobs of the candidate search: ms of a whole build and of its two GEMM passes
         Xd = torch.from_numpy(X).cuda()
         base = dict(clusters=64, kmeans_iters=1, cluster_cells=1024, prune_window=2, tl_chunks=2, tc_multicast=2)
-        trials = [dict(), dict(clusters=96), dict(clusters=128), dict(clusters=32), dict(kmeans_iters=2),
-                  dict(clusters=128, kmeans_iters=2), dict(prune_window=1), dict(prune_window=3), dict(tl_chunks=1),
-                  dict(tl_chunks=3), dict(tl_chunks=4), dict(tc_multicast=1), dict(tc_multicast=4)]
+        base["km_var_pct"] = 99
+        trials = [dict(), dict(km_var_pct=0), dict(km_var_pct=95), dict(km_var_pct=90), dict(kmeans_iters=0),
+                  dict(clusters=96), dict(clusters=128), dict(clusters=32), dict(kmeans_iters=2),
+                  dict(prune_window=1), dict(prune_window=3), dict(tl_chunks=1),
+                  dict(tl_chunks=4), dict(tc_multicast=1), dict(tc_multicast=4)]
+        if os.environ.get("PROBE_PRUNE_SHORT"):
+            trials = trials[:5]
         for tr in trials:
             nv.set_tuning(**dict(base, **tr))
             ts = []
