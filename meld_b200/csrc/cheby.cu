@@ -855,9 +855,11 @@ __device__ __forceinline__ void peer_wait(const unsigned long long *my_flags, in
 // peers (fence + counter: all CTAs' stores are ordered before the flag stores).
 __device__ __forceinline__ void peer_post(const StepArgs &a) {
   if (a.post_epoch == 0) return;
-  __threadfence_system();
+  // CTA barrier, then ONE system-scope fence per CTA (cumulative over the stores the barrier made visible to this
+  // thread -- the pattern of a cooperative grid barrier); 1024 fences per CTA each wait for the NVLink acknowledgements
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int prev = atomicAdd(a.done_ctr, 1u);
     if (prev == gridDim.x - 1) {
       *a.done_ctr = 0;  // the next launch starts after this one has ended
@@ -1271,10 +1273,16 @@ static int ensure_work(meld_b200_graph *g, size_t count) {
   return g->work.alloc(count);
 }
 
-// Internal row width of a p-column signal.  A gathered row costs one L1TEX data-pipe wavefront per load instruction
-// per lane, and only 32-byte aligned rows can be read with 256-bit loads: p = 3 (three 8-byte loads), 5, 7 (five /
-// seven) and 6 (three 16-byte loads) are padded with zero columns to 4 / 8 doubles -> one / two wavefronts per row.
-static inline int padded_width(int p) { return p <= 2 ? p : (p <= 4 ? 4 : 8); }
+// Internal row width of a p-column signal.  Only 32-byte aligned rows can be gathered with 256-bit loads, so padding
+// p = 3 / 5 / 6 / 7 with zero columns to 4 / 8 doubles turns three to seven narrow loads per gathered row into one or
+// two wide ones.  MEASURED (round 2, bench.py): it is SLOWER -- config 5 (2M cells, p = 6 -> 8) 796 -> 894 us per
+// launch, config 2 (50k cells, p = 3 -> 4) 5.0 -> 6.0 ms per filter: the gather cost follows the 32-byte sectors a row
+// occupies (two for 48 as for 64 bytes), not the number of load instructions, and the padded columns add a third to
+// the epilogue's vector traffic.  Off by default (tuning key pad_width = 1 enables it for experiments).
+static inline int padded_width(int p) {
+  if (!tuning().pad_width) return p;
+  return p <= 2 ? p : (p <= 4 ? 4 : 8);
+}
 
 // rows of an (n, p) array through a permutation.  The CALLER's array has p columns, the internal (graph-order) one pw
 // >= p (zero padded): gather: internal[a] = caller[perm[a]]; scatter: caller[perm[a]] = internal[a].

@@ -74,6 +74,7 @@ struct Tuning {
                           // (measured: 154 us either way at p = 4 -- L1-tag bound; Lanczos p = 1 gains 15 %)
   int flat_sched = 1;     // flat kernel: 1 = every CTA owns a contiguous, nonzero-balanced row range; 0 = round-robin
   int flat_group = 0;     // lanes per row of the flat kernel (0 = like the staged kernel)
+  int pad_width = 0;      // 1: signals of 3 / 5..7 columns run zero-padded to 4 / 8 (measured slower, see cheby.cu)
   int flat_gen = 1;       // 1: second-generation flat kernel (cheby_flat2_kernel), 0: the round-1 flat kernels
   int flat_hint = -1;     // cheby_flat2_kernel HINT (0..3, see cheby.cu); -1: chosen from the signal width
   int flat_layout = -1;   // cheby_flat2_kernel LAYOUT (0: 4 consecutive entries per lane, 1: lane-consecutive); -1: auto

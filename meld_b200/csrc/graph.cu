@@ -406,6 +406,7 @@ int meld_b200_set_tuning(const char *key, int value) {
   else if (!strcmp(key, "flat_sched")) t.flat_sched = value;
   else if (!strcmp(key, "flat_pipe")) t.flat_pipe = value;
   else if (!strcmp(key, "flat_gen")) t.flat_gen = value;
+  else if (!strcmp(key, "pad_width")) t.pad_width = value;
   else if (!strcmp(key, "flat_hint")) t.flat_hint = value;
   else if (!strcmp(key, "flat_layout")) t.flat_layout = value;
   else if (!strcmp(key, "tl_interleave")) t.tl_interleave = value;

@@ -329,12 +329,43 @@ __global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t row_
 }
 
 // ---- 2. exact float64 distances of the candidates, eps_i ----------------------------------------
-// One warp per row.  Candidates of row i are cand[cptr[i] .. cptr[i+1]); d2buf (same indexing) receives
-// the exact squared distances.
-__global__ void refine_dist_kernel(const double *__restrict__ X, int64_t row_begin, int64_t n, int64_t d,
-                                   const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr, int k1,
-                                   double bandwidth_scale,
-                                   double *__restrict__ d2buf, double *__restrict__ eps, int *__restrict__ err_flag) {
+// One warp per row.  Candidates of row i are cand[cptr[i] .. cptr[i+1]) (columns ascending); d2buf (same indexing)
+// receives the exact squared distances.  d_ij = d_ji bit for bit (the differences only change sign), and gathering a
+// candidate's 8 d bytes is what this stage costs (35.6 M rows of 800 bytes at config 4), so a pair that is in both
+// rows' lists is computed ONCE: pass 1 computes the slots with j >= i (and every slot whose row j is not local),
+// pass 2 fills the slots with j < i from row j's list (a binary search over ~70 sorted columns instead of a 800-byte
+// gather), computes the few whose mirror does not exist, and then selects eps_i.
+__device__ __forceinline__ double exact_d2(const double *__restrict__ xi, const double *__restrict__ xj, int64_t d,
+                                           bool vec4) {
+  double acc = 0.0;
+  if (vec4) {
+    // rows are 32-byte aligned (d % 4 == 0): one 256-bit load per four features and lane instead of four
+    // 8-byte ones -- the scalar loop is bound by L1 tag lookups (32 distinct lines per warp instruction)
+    for (int64_t k = 0; k < d; k += 4) {  // same sequential, unfused order as the scalar loop
+      double a0, a1, a2, a3, b0, b1, b2, b3;
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(xi + k));
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3) : "l"(xj + k));
+      double diff = __dsub_rn(a0, b0);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(a1, b1);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(a2, b2);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(a3, b3);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+    }
+  } else {
+    for (int64_t k = 0; k < d; ++k) {  // sequential, unfused: the ball tree's rdist order
+      const double diff = __dsub_rn(xi[k], xj[k]);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+    }
+  }
+  return acc;
+}
+
+__global__ void refine_upper_kernel(const double *__restrict__ X, int64_t row_begin, int64_t n, int64_t d,
+                                    const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr,
+                                    double *__restrict__ d2buf) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -344,38 +375,47 @@ __global__ void refine_dist_kernel(const double *__restrict__ X, int64_t row_beg
     const int c = (int)(cptr[i + 1] - cptr[i]);
     const int32_t *ci = cand + cptr[i];
     double *di = d2buf + cptr[i];
-    const double *xi = X + (row_begin + i) * d;
-    if (vec4) {
-      // rows are 32-byte aligned (d % 4 == 0): one 256-bit load per four features and lane instead of four
-      // 8-byte ones -- the scalar loop is bound by L1 tag lookups (32 distinct lines per warp instruction)
-      for (int t = lane; t < c; t += 32) {
-        const double *xj = X + (int64_t)ci[t] * d;
-        double acc = 0.0;
-        for (int64_t k = 0; k < d; k += 4) {  // same sequential, unfused order as below
-          double a0, a1, a2, a3, b0, b1, b2, b3;
-          asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(xi + k));
-          asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3) : "l"(xj + k));
-          double diff = __dsub_rn(a0, b0);
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-          diff = __dsub_rn(a1, b1);
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-          diff = __dsub_rn(a2, b2);
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-          diff = __dsub_rn(a3, b3);
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-        }
-        di[t] = acc;
+    const int64_t ig = row_begin + i;
+    const double *xi = X + ig * d;
+    for (int t = lane; t < c; t += 32) {
+      const int64_t j = ci[t];
+      if (j >= ig || j < row_begin) di[t] = exact_d2(xi, X + j * d, d, vec4);  // j < i and local: pass 2 looks it up
+    }
+  }
+}
+
+__global__ void refine_lower_kernel(const double *__restrict__ X, int64_t row_begin, int64_t n, int64_t d,
+                                    const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr, int k1,
+                                    double bandwidth_scale,
+                                    double *__restrict__ d2buf, double *__restrict__ eps, int *__restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 31) == 0);
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int c = (int)(cptr[i + 1] - cptr[i]);
+    const int32_t *ci = cand + cptr[i];
+    double *di = d2buf + cptr[i];
+    const int64_t ig = row_begin + i;
+    const double *xi = X + ig * d;
+    for (int t = lane; t < c; t += 32) {
+      const int64_t j = ci[t];
+      if (j >= ig || j < row_begin) continue;  // done in pass 1
+      // row j (local, j < i): is i among its candidates?  Its columns are ascending.
+      const int64_t jl = j - row_begin;
+      const int64_t b0 = cptr[jl];
+      int lo = 0, hi = (int)(cptr[jl + 1] - b0);
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(cand + b0 + mid) < ig)
+          lo = mid + 1;
+        else
+          hi = mid;
       }
-    } else {
-      for (int t = lane; t < c; t += 32) {
-        const double *xj = X + (int64_t)ci[t] * d;
-        double acc = 0.0;
-        for (int64_t k = 0; k < d; ++k) {  // sequential, unfused: the ball tree's rdist order
-          const double diff = __dsub_rn(xi[k], xj[k]);
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-        }
-        di[t] = acc;
-      }
+      if (lo < (int)(cptr[jl + 1] - b0) && (int64_t)__ldg(cand + b0 + lo) == ig)
+        di[t] = __ldcg(d2buf + b0 + lo);  // written by pass 1 (slot (j, i) has i > j)
+      else
+        di[t] = exact_d2(xi, X + j * d, d, vec4);
     }
     __syncwarp();
     if (c < k1) {
@@ -413,6 +453,11 @@ __global__ void refine_dist_kernel(const double *__restrict__ X, int64_t row_beg
     }
   }
 }
+
+// both passes (launch helper)
+static int refine_distances(const double *X, int64_t row_begin, int64_t nloc, int64_t d, const int32_t *cand,
+                            const int64_t *cptr, int k1, double bandwidth_scale, double *d2buf, double *eps, int *err,
+                            cudaStream_t stream);
 
 __device__ __forceinline__ double alpha_decay(double dist, double eps, double decay) {
   // decay == 0 stands for the reference's decay=None: the unweighted kNN kernel (graphtools kNNGraph with
@@ -710,6 +755,17 @@ static int warp_grid(int64_t n_rows, int threads) {
   int64_t b = ceil_div(n_rows, warps_per_block);
   const int64_t cap = (int64_t)sm_count() * 16;
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+static int refine_distances(const double *X, int64_t row_begin, int64_t nloc, int64_t d, const int32_t *cand,
+                            const int64_t *cptr, int k1, double bandwidth_scale, double *d2buf, double *eps, int *err,
+                            cudaStream_t stream) {
+  refine_upper_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(X, row_begin, nloc, d, cand, cptr, d2buf);
+  MELD_LAUNCH_CHECK();
+  refine_lower_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(X, row_begin, nloc, d, cand, cptr, k1, bandwidth_scale,
+                                                               d2buf, eps, err);
+  MELD_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace meld
@@ -1099,9 +1155,8 @@ static int build_stage1(const double *X, int64_t n, int64_t d, const BuildParams
   MELD_CHECK(eps.alloc((size_t)nloc));
   MELD_CHECK(err.alloc(1));
   MELD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
-  refine_dist_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(X, row_begin, nloc, d, cs.cand.p, cs.cptr.p, bp.k1,
-                                                               bp.bandwidth_scale, d2.p, eps.p, err.p);
-  MELD_LAUNCH_CHECK();
+  MELD_CHECK(refine_distances(X, row_begin, nloc, d, cs.cand.p, cs.cptr.p, bp.k1, bp.bandwidth_scale, d2.p, eps.p, err.p,
+                              stream));
   int h_err = 0;
   MELD_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   MELD_CUDA(cudaStreamSynchronize(stream));
@@ -1743,9 +1798,7 @@ int meld_b200_dense_graph_build(const double *X, int64_t n, int64_t d, int knn, 
   MELD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream));
   dense_candidates_kernel<<<sm_count() * 8, 256, 0, stream>>>(n, cptr.p, cand.p);
   MELD_LAUNCH_CHECK();
-  refine_dist_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(X, 0, n, d, cand.p, cptr.p, bp.k1, bp.bandwidth_scale, d2.p,
-                                                           eps.p, err.p);
-  MELD_LAUNCH_CHECK();
+  MELD_CHECK(refine_distances(X, 0, n, d, cand.p, cptr.p, bp.k1, bp.bandwidth_scale, d2.p, eps.p, err.p, stream));
   meld_b200_graph *g = nullptr;
   MELD_CHECK(build_stage2(n, cptr.p, cand.p, d2.p, n * n, eps.p, bp, noperm, stream, &g));
   g->stats[0] = 0;  // no search passes

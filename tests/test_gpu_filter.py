@@ -261,7 +261,7 @@ def test_filter_kernel_variants_agree(mb, tuning):
         nv.set_tuning(**defaults)
 
 
-@pytest.mark.parametrize("p", [2, 4, 8, 11])
+@pytest.mark.parametrize("p", [2, 3, 4, 6, 8, 11])
 def test_flat2_variants_all_widths(mb, p):
     """Second-generation flat kernel (cache-hint / layout variants) at several signal widths vs the oracle."""
     from meld_b200 import _native as nv
@@ -271,14 +271,15 @@ def test_flat2_variants_all_widths(mb, p):
     S = np.random.default_rng(40 + p).normal(size=(g["L"].shape[0], p))
     ref = cheby.cheby_filter(g["L"], g["lmax"], S, "heat", beta=45, chebyshev_order=24)
     try:
-        for hint, layout in [(0, 0), (1, 0), (2, 0), (3, 0), (0, 1), (1, 1), (2, 1), (3, 1), (-1, -1)]:
-            nv.set_tuning(flat_gen=1, flat_hint=hint, flat_layout=layout)
+        for hint, layout, pad in [(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (0, 1, 0), (1, 1, 0), (2, 1, 0), (3, 1, 0),
+                                  (-1, -1, 0), (-1, -1, 1)]:  # pad: odd widths zero-padded to 4 / 8 columns
+            nv.set_tuning(flat_gen=1, flat_hint=hint, flat_layout=layout, pad_width=pad)
             graph = mb.DeviceGraph.from_scipy(g["L"])
             graph.lmax = g["lmax"]
             out = mb.filter.filter(S, graph, "heat", beta=45, solver="chebyshev", chebyshev_order=24)
             assert np.abs(out - ref).max() <= 1e-11 * np.abs(ref).max(), (hint, layout)
     finally:
-        nv.set_tuning(flat_gen=DEFAULT_FLAT_GEN, flat_hint=DEFAULT_FLAT_HINT, flat_layout=DEFAULT_FLAT_LAYOUT)
+        nv.set_tuning(flat_gen=DEFAULT_FLAT_GEN, flat_hint=DEFAULT_FLAT_HINT, flat_layout=DEFAULT_FLAT_LAYOUT, pad_width=0)
 
 
 def test_transform_sweep_matches_looping_the_oracle(mb):
