@@ -330,18 +330,42 @@ __global__ void merge_lists_kernel(const float *__restrict__ lists, int64_t row_
 
 // ---- 2. exact float64 distances of the candidates, eps_i ----------------------------------------
 // One warp per row.  Candidates of row i are cand[cptr[i] .. cptr[i+1]) (columns ascending); d2buf (same indexing)
-// receives the exact squared distances.  d_ij = d_ji bit for bit (the differences only change sign), and gathering a
-// candidate's 8 d bytes is what this stage costs (35.6 M rows of 800 bytes at config 4), so a pair that is in both
-// rows' lists is computed ONCE: pass 1 computes the slots with j >= i (and every slot whose row j is not local),
-// pass 2 fills the slots with j < i from row j's list (a binary search over ~70 sorted columns instead of a 800-byte
-// gather), computes the few whose mirror does not exist, and then selects eps_i.
+// receives the exact squared distances: sqrt(sum_k (x_ik - x_jk)^2) summed sequentially and unfused, the order of
+// scikit-learn's ball tree, so d_ij equals the reference's bit for bit and d_ij = d_ji exactly.
+// (Round 2 tried to compute a pair that is in both rows' lists only once -- pass 1 for j >= i, pass 2 looks the
+// value up in row j's sorted list: 5.3 -> 5.8 ms at config 4.  The stage is bound by the latency chain of a lane's
+// 25 dependent 256-bit gathers, not by bytes; halving the active lanes does not shorten that chain.  Reverted.)
 __device__ __forceinline__ double exact_d2(const double *__restrict__ xi, const double *__restrict__ xj, int64_t d,
                                            bool vec4) {
   double acc = 0.0;
   if (vec4) {
     // rows are 32-byte aligned (d % 4 == 0): one 256-bit load per four features and lane instead of four
-    // 8-byte ones -- the scalar loop is bound by L1 tag lookups (32 distinct lines per warp instruction)
-    for (int64_t k = 0; k < d; k += 4) {  // same sequential, unfused order as the scalar loop
+    // 8-byte ones; two feature quads are requested before either is consumed (more loads in flight per lane)
+    int64_t k = 0;
+    for (; k + 8 <= d; k += 8) {  // same sequential, unfused order as the scalar loop
+      double a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3, e0, e1, e2, e3;
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(xi + k));
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3) : "l"(xj + k));
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(xi + k + 4));
+      asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e0), "=d"(e1), "=d"(e2), "=d"(e3) : "l"(xj + k + 4));
+      double diff = __dsub_rn(a0, b0);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(a1, b1);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(a2, b2);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(a3, b3);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(c0, e0);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(c1, e1);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(c2, e2);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      diff = __dsub_rn(c3, e3);
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+    }
+    for (; k < d; k += 4) {
       double a0, a1, a2, a3, b0, b1, b2, b3;
       asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(xi + k));
       asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(b0), "=d"(b1), "=d"(b2), "=d"(b3) : "l"(xj + k));
@@ -363,9 +387,10 @@ __device__ __forceinline__ double exact_d2(const double *__restrict__ xi, const 
   return acc;
 }
 
-__global__ void refine_upper_kernel(const double *__restrict__ X, int64_t row_begin, int64_t n, int64_t d,
-                                    const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr,
-                                    double *__restrict__ d2buf) {
+__global__ void refine_dist_kernel(const double *__restrict__ X, int64_t row_begin, int64_t n, int64_t d,
+                                   const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr, int k1,
+                                   double bandwidth_scale,
+                                   double *__restrict__ d2buf, double *__restrict__ eps, int *__restrict__ err_flag) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -375,48 +400,8 @@ __global__ void refine_upper_kernel(const double *__restrict__ X, int64_t row_be
     const int c = (int)(cptr[i + 1] - cptr[i]);
     const int32_t *ci = cand + cptr[i];
     double *di = d2buf + cptr[i];
-    const int64_t ig = row_begin + i;
-    const double *xi = X + ig * d;
-    for (int t = lane; t < c; t += 32) {
-      const int64_t j = ci[t];
-      if (j >= ig || j < row_begin) di[t] = exact_d2(xi, X + j * d, d, vec4);  // j < i and local: pass 2 looks it up
-    }
-  }
-}
-
-__global__ void refine_lower_kernel(const double *__restrict__ X, int64_t row_begin, int64_t n, int64_t d,
-                                    const int32_t *__restrict__ cand, const int64_t *__restrict__ cptr, int k1,
-                                    double bandwidth_scale,
-                                    double *__restrict__ d2buf, double *__restrict__ eps, int *__restrict__ err_flag) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const bool vec4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 31) == 0);
-  for (int64_t i = warp; i < n; i += nwarps) {
-    const int c = (int)(cptr[i + 1] - cptr[i]);
-    const int32_t *ci = cand + cptr[i];
-    double *di = d2buf + cptr[i];
-    const int64_t ig = row_begin + i;
-    const double *xi = X + ig * d;
-    for (int t = lane; t < c; t += 32) {
-      const int64_t j = ci[t];
-      if (j >= ig || j < row_begin) continue;  // done in pass 1
-      // row j (local, j < i): is i among its candidates?  Its columns are ascending.
-      const int64_t jl = j - row_begin;
-      const int64_t b0 = cptr[jl];
-      int lo = 0, hi = (int)(cptr[jl + 1] - b0);
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((int64_t)__ldg(cand + b0 + mid) < ig)
-          lo = mid + 1;
-        else
-          hi = mid;
-      }
-      if (lo < (int)(cptr[jl + 1] - b0) && (int64_t)__ldg(cand + b0 + lo) == ig)
-        di[t] = __ldcg(d2buf + b0 + lo);  // written by pass 1 (slot (j, i) has i > j)
-      else
-        di[t] = exact_d2(xi, X + j * d, d, vec4);
-    }
+    const double *xi = X + (row_begin + i) * d;
+    for (int t = lane; t < c; t += 32) di[t] = exact_d2(xi, X + (int64_t)ci[t] * d, d, vec4);
     __syncwarp();
     if (c < k1) {
       if (lane == 0) atomicExch(err_flag, 1);
@@ -454,7 +439,7 @@ __global__ void refine_lower_kernel(const double *__restrict__ X, int64_t row_be
   }
 }
 
-// both passes (launch helper)
+// launch helper
 static int refine_distances(const double *X, int64_t row_begin, int64_t nloc, int64_t d, const int32_t *cand,
                             const int64_t *cptr, int k1, double bandwidth_scale, double *d2buf, double *eps, int *err,
                             cudaStream_t stream);
@@ -760,10 +745,8 @@ static int warp_grid(int64_t n_rows, int threads) {
 static int refine_distances(const double *X, int64_t row_begin, int64_t nloc, int64_t d, const int32_t *cand,
                             const int64_t *cptr, int k1, double bandwidth_scale, double *d2buf, double *eps, int *err,
                             cudaStream_t stream) {
-  refine_upper_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(X, row_begin, nloc, d, cand, cptr, d2buf);
-  MELD_LAUNCH_CHECK();
-  refine_lower_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(X, row_begin, nloc, d, cand, cptr, k1, bandwidth_scale,
-                                                               d2buf, eps, err);
+  refine_dist_kernel<<<warp_grid(nloc, 128), 128, 0, stream>>>(X, row_begin, nloc, d, cand, cptr, k1, bandwidth_scale,
+                                                              d2buf, eps, err);
   MELD_LAUNCH_CHECK();
   return 0;
 }

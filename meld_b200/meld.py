@@ -540,6 +540,9 @@ class MELD(object):
         pre = {}
 
         def _prefetch():
+            # let the caller's thread get into the (GIL-free) native build first: factorising right away competes for
+            # the GIL with the few Python steps in front of it and delays the host-to-device copy by milliseconds
+            time.sleep(0.002)
             t_thr = time.perf_counter()
             try:
                 flat = np.asarray(getattr(sample_labels, "values", sample_labels))
