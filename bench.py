@@ -472,6 +472,7 @@ def run_b200(args):
     barrier()
     events = []
     launches0 = lib.meld_b200_launch_count()
+    syncs0 = lib.meld_b200_sync_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e0.record()
@@ -483,6 +484,7 @@ def run_b200(args):
     barrier()
     gc.enable()
     launches = lib.meld_b200_launch_count() - launches0
+    syncs = lib.meld_b200_sync_count() - syncs0
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     step_ms = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
@@ -632,6 +634,7 @@ def run_b200(args):
                     "host_timings_ms_last_step": {k: round(1e3 * v, 2) for k, v in op_e2e.timings_.items()}},
             "gpu_launches": int(launches),
             "gpu_launches_per_step": int(launches) / max(args.steps, 1),
+            "host_syncs_per_step": int(syncs) / max(args.steps, 1),
             "clocks": clocks,
             "roofline": {
                 "kernel": "Chebyshev SpMM + fused three-term update, one launch per term (cheby_flat kernels; "

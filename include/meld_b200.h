@@ -48,6 +48,8 @@ int meld_b200_version(void);              /* major*10000 + minor*100 + patch    
 const char *meld_b200_last_error(void);   /* thread-local, never NULL            */
 /* Kernels this library has launched so far in this process (its own, not CUB's).  */
 int64_t meld_b200_launch_count(void);
+/* Times this library has made the host wait for a stream so far (cudaStreamSynchronize inside its calls).       */
+int64_t meld_b200_sync_count(void);
 /* sm_count / cc_major / cc_minor of the current device (host pointers).        */
 int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
 

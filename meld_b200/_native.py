@@ -26,6 +26,7 @@ SIGNATURES = {
     "meld_b200_version": (C.c_int, []),
     "meld_b200_last_error": (C.c_char_p, []),
     "meld_b200_launch_count": (C.c_int64, []),
+    "meld_b200_sync_count": (C.c_int64, []),
     "meld_b200_device_info": (C.c_int, [_pint, _pint, _pint]),
     "meld_b200_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "meld_b200_knn_graph_build": (C.c_int, [_vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _vp, C.POINTER(_vp)]),

@@ -1769,7 +1769,7 @@ int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeff
       ch[(size_t)f * n_coeffs] *= 0.5;  // PyGSP uses c_0 / 2
     }
     MELD_CUDA(cudaMemcpyAsync(Cd, ch.data(), ch.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));  // ch is a local
+    MELD_SYNC(stream);  // ch is a local
   }
   const int pgrid = grid_for(n * pw, 256);
   permute_rows_kernel<<<pgrid, 256, 0, stream>>>(S, g->perm.p, n, p, pw, /*scatter=*/0, T);  // T_0 = S in graph order
@@ -1853,7 +1853,7 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaMemcpyAsync(alpha.data(), d_alpha, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(beta.data(), d_beta, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
     const int rc = lanczos_check(alpha, beta, k, rel_tol, theta);
     if (rc < 0) return rc;
     done = rc == 1;
@@ -1982,7 +1982,7 @@ int meld_b200_estimate_lmax_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, int
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaMemcpyAsync(alpha.data(), d_alpha, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(beta.data(), d_beta, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
     const int rc = lanczos_check(alpha, beta, k, rel_tol, theta);  // identical on every rank: same sums, same order
     if (rc < 0) return rc;
     done = rc == 1;
@@ -2006,7 +2006,7 @@ int meld_b200_indicator_matrix(const int32_t *codes, int64_t n, int p, int sampl
   fill_indicator_kernel<<<grid_for(n * p, 256), 256, 0, stream>>>(codes, n, p, sample_normalize, cnt.p, S);
   MELD_LAUNCH_CHECK();
   // cnt goes back to the pool in stream order (cudaFreeAsync on this stream); only plain cudaFree needs the sync
-  if (!use_pool()) MELD_CUDA(cudaStreamSynchronize(stream));
+  if (!use_pool()) MELD_SYNC(stream);
   return 0;
 }
 

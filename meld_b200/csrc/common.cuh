@@ -46,6 +46,14 @@ extern long long g_launches;
     MELD_CUDA(cudaGetLastError());   \
   } while (0)
 
+// Host waits on the stream are counted too (meld_b200_sync_count; bench.py reports them per step).
+extern long long g_syncs;
+#define MELD_SYNC(s)                          \
+  do {                                        \
+    ++meld::g_syncs;                          \
+    MELD_CUDA(cudaStreamSynchronize(s));      \
+  } while (0)
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

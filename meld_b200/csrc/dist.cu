@@ -81,7 +81,7 @@ int meld_b200_graph_row_slice(const meld_b200_graph_t *g, int64_t row_begin, int
   int32_t h_ends[2] = {0, 0};
   MELD_CUDA(cudaMemcpyAsync(&h_ends[0], g->row_ptr.p + row_begin, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   MELD_CUDA(cudaMemcpyAsync(&h_ends[1], g->row_ptr.p + row_end, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  MELD_CUDA(cudaStreamSynchronize(stream));
+  MELD_SYNC(stream);
   const int64_t e0 = h_ends[0], nnz = (int64_t)h_ends[1] - h_ends[0];
   meld_b200_graph *s = new (std::nothrow) meld_b200_graph();
   if (!s) {

@@ -11,6 +11,7 @@ namespace meld {
 
 static thread_local char g_err[1024] = "";
 long long g_launches = 0;
+long long g_syncs = 0;
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -320,7 +321,7 @@ int graph_finalize(meld_b200_graph *g, cudaStream_t stream) {
   MELD_LAUNCH_CHECK();
   unsigned long long h2[2] = {0, 0};
   MELD_CUDA(cudaMemcpyAsync(h2, st2.p, sizeof(h2), cudaMemcpyDeviceToHost, stream));
-  MELD_CUDA(cudaStreamSynchronize(stream));
+  MELD_SYNC(stream);
   g->dict_total = (int64_t)h2[0];
   g->direct_blocks = (int64_t)h2[1];
   g->stats[5] = g->dict_total;
@@ -352,6 +353,8 @@ int meld_b200_release_workspace(void) {
 }
 
 int64_t meld_b200_launch_count(void) { return (int64_t)g_launches; }
+
+int64_t meld_b200_sync_count(void) { return (int64_t)g_syncs; }
 
 const char *meld_b200_last_error(void) { return g_err; }
 

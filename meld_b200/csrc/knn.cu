@@ -778,7 +778,7 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
   std::vector<double> h_mu((size_t)d), h_var((size_t)d);
   MELD_CUDA(cudaMemcpyAsync(h_mu.data(), mu.p, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, stream));
   MELD_CUDA(cudaMemcpyAsync(h_var.data(), var.p, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, stream));
-  MELD_CUDA(cudaStreamSynchronize(stream));
+  MELD_SYNC(stream);
   tm.lap("  order: means + variances");
   std::vector<int> order((size_t)d);
   for (int64_t k = 0; k < d; ++k) order[(size_t)k] = (int)k;
@@ -857,7 +857,7 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
     int32_t h_sel[kKmDims];
     for (int k = 0; k < kKmDims; ++k) h_sel[k] = k < nd ? order[(size_t)k] : 0;
     MELD_CUDA(cudaMemcpyAsync(sel.p, h_sel, sizeof(h_sel), cudaMemcpyHostToDevice, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));  // h_sel is a stack array
+    MELD_SYNC(stream);  // h_sel is a stack array
     tm.lap("  order: morton sort");
     kmeans_seed_kernel<<<C, kKmDims, 0, stream>>>(X, n, d, sel.p, nd, mu.p, perm.p, C, cen.p);
     MELD_LAUNCH_CHECK();
@@ -900,7 +900,7 @@ static int cell_order(const double *X, int64_t n, int64_t d, cudaStream_t stream
   MELD_CHECK(Xp.alloc((size_t)n * d));
   gather_rows_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(X, perm.p, n, d, Xp.p);
   MELD_LAUNCH_CHECK();
-  MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
+  // no host wait: the temporaries are arena bumps or stream-ordered pool frees
   tm.lap("  order: gather rows");
   return 0;
 }
@@ -1025,7 +1025,7 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
     unsigned long long h_steps[4] = {0, 0, 0, 0};
     MELD_CUDA(cudaMemcpyAsync(&h_total, gcount.p, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
     if (prune) MELD_CUDA(cudaMemcpyAsync(h_steps, st.tl_steps.p, sizeof(h_steps), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
     {
       float ms1 = 0.f, ms2 = 0.f;
       cudaEventElapsedTime(&ms1, ev[0], ev[1]);
@@ -1082,7 +1082,7 @@ static int candidate_search(const double *X, int64_t n, int64_t d, int k1, doubl
     max_count_kernel<<<296, 256, 0, stream>>>(out.cptr.p, nloc, mx.p);
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaMemcpyAsync(&out.max_per_row, mx.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
+    MELD_SYNC(stream);  // temporaries die here
   }
   tm.lap("sort pairs -> candidate CSR");
   return 0;
@@ -1142,7 +1142,7 @@ static int build_stage1(const double *X, int64_t n, int64_t d, const BuildParams
                               stream));
   int h_err = 0;
   MELD_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  MELD_CUDA(cudaStreamSynchronize(stream));
+  MELD_SYNC(stream);
   if (h_err) {
     set_error("knn graph build: a row has fewer than knn+1 candidates (candidate search failed)");
     return MELD_B200_ERR_INTERNAL;
@@ -1196,7 +1196,7 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
     MELD_LAUNCH_CHECK();
     MELD_CUDA(cudaMemcpyAsync(&h_max_extra, max_extra.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(&h_nnz, g->row_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
     if (h_nnz < 0) {
       set_error("knn graph build: nnz overflows int32");
       return MELD_B200_ERR_UNSUPPORTED;
@@ -1231,7 +1231,7 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
       MELD_CUDA(cub::DeviceSegmentedSort::SortPairs(tmp.p, tmp_bytes, ucol.p, g->col.p, uval.p, g->val.p,
                                                     (int)g->nnz, (int)n, g->row_ptr.p, g->row_ptr.p + 1, stream));
     }
-    MELD_CUDA(cudaStreamSynchronize(stream));  // temporaries die here
+    // no host wait: ucol / uval / cursor are arena bumps or stream-ordered pool frees
   }
   tm.lap("kernel values, fill, sort");
 
@@ -1248,7 +1248,7 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
     MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, g->knn_cnt.p, rp64.p, (int)(n + 1), stream));
     int64_t h_raw = 0;
     MELD_CUDA(cudaMemcpyAsync(&h_raw, rp64.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
     g->knn_nnz = h_raw;
     MELD_CHECK(g->knn_col.alloc((size_t)h_raw));
     MELD_CHECK(g->knn_val.alloc((size_t)h_raw));
@@ -1257,7 +1257,7 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
     fill_raw_kernel<<<warp_grid(n, 128), 128, 0, stream>>>(n, cand, cptr, kraw.p, g->knn_ptr.p, g->knn_col.p,
                                                            g->knn_val.p);
     MELD_LAUNCH_CHECK();
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
   }
 
   {  // anisotropy + Laplacian
@@ -1267,7 +1267,7 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
     MELD_LAUNCH_CHECK();
     laplacian_kernel<<<warp_grid(n, 256), 256, 0, stream>>>(n, g->row_ptr.p, g->col.p, g->val.p, q.p, bp.anisotropy);
     MELD_LAUNCH_CHECK();
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
   }
   tm.lap("anisotropy + laplacian");
   MELD_CHECK(graph_finalize(g, stream));
@@ -1275,7 +1275,7 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
   if (perm.p) {  // the graph keeps its own copy (perm may live in the build arena)
     MELD_CHECK(g->perm.alloc(perm.n));
     MELD_CUDA(cudaMemcpyAsync(g->perm.p, perm.p, perm.n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
     perm.release();
   }
   g->stats[2] = total;
@@ -1550,7 +1550,7 @@ int meld_b200_stage2_begin(meld_b200_cands_t *c, const double *eps_full, const i
   MELD_LAUNCH_CHECK();
   unsigned long long h_cnt[8] = {0};
   MELD_CUDA(cudaMemcpyAsync(h_cnt, st->cursor.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-  MELD_CUDA(cudaStreamSynchronize(stream));
+  MELD_SYNC(stream);
   st->n_send = 0;
   for (int w = 0; w < world; ++w) {
     st->send_counts[w] = (int64_t)h_cnt[w];
@@ -1574,7 +1574,7 @@ int meld_b200_stage2_records(meld_b200_stage2_t *st, void *records_out, void *st
     run += st->send_counts[w];
   }
   MELD_CUDA(cudaMemcpyAsync(st->cursor.p, off, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-  MELD_CUDA(cudaStreamSynchronize(stream));  // off is a local
+  MELD_SYNC(stream);  // off is a local
   meld_b200_cands *c = st->cands;
   mirror_records_kernel<<<warp_grid(st->nloc, 256), 256, 0, stream>>>(st->nloc, st->row0, c->cand.p, c->cptr.p, c->d2.p,
                                                                      st->d_bounds.p, st->world, 1, st->cursor.p,
@@ -1629,7 +1629,7 @@ int meld_b200_stage2_assemble(meld_b200_stage2_t *st, const void *recv_records, 
     MELD_CUDA(cudaMemcpyAsync(&h_max_extra, max_extra.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(&h_nnz, g->row_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MELD_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
   }
   MELD_REQUIRE(h_err == 0, "stage2_assemble: a received mirror record does not belong to this rank's rows");
   MELD_REQUIRE(h_nnz >= 0, "stage2_assemble: nnz overflows int32");
@@ -1836,7 +1836,7 @@ int meld_b200_knn_candidates(const double *X, int64_t n, int64_t d, int knn, dou
   MELD_CHECK(c->cand.alloc(cs.cand.n));
   MELD_CUDA(cudaMemcpyAsync(c->cptr.p, cs.cptr.p, cs.cptr.n * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
   MELD_CUDA(cudaMemcpyAsync(c->cand.p, cs.cand.p, cs.cand.n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-  MELD_CUDA(cudaStreamSynchronize(stream));
+  MELD_SYNC(stream);
   guard.c = nullptr;
   *cands_out = c;
   return 0;
@@ -1913,7 +1913,7 @@ int meld_b200_graph_from_candidates(int64_t n, const int64_t *counts, const int3
     MELD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt1.p, cptr.p, (int)(n + 1), stream));
     int64_t h_total = 0;
     MELD_CUDA(cudaMemcpyAsync(&h_total, cptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    MELD_CUDA(cudaStreamSynchronize(stream));
+    MELD_SYNC(stream);
     MELD_REQUIRE(h_total == total, "graph_from_candidates: counts sum to %lld, total says %lld", (long long)h_total,
                  (long long)total);
   }
@@ -1948,7 +1948,7 @@ int meld_b200_debug_candidate_search(const double *X, int64_t n, int64_t d, int 
   MELD_CUDA(cudaMemcpyAsync(key2_out, cs.key2.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   row_counts_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(cs.cptr.p, n, cnt_out);
   MELD_LAUNCH_CHECK();
-  MELD_CUDA(cudaStreamSynchronize(stream));
+  MELD_SYNC(stream);
   if (cap_host) *cap_host = cs.total;
   return 0;
 }

@@ -162,3 +162,27 @@ def test_tile_pruning_bounds_are_lower_bounds():
                 lb_proj = -pAB.max() - pBA.max()
                 worst_proj = min(worst_proj, (D - lb_proj).min())
     assert worst_ball >= -1e-9 and worst_proj >= -1e-9, (worst_ball, worst_proj)
+
+
+def test_sampled_bruteforce_rows_equal_the_ball_tree_kernel():
+    """oracle.graph.knn_kernel_rows_bruteforce (the checker of the 500k / 2M-cell GPU tests) reproduces the rows of
+    the ball-tree kernel exactly on a size where both run."""
+    from meld_b200 import synthetic
+
+    X, _ = synthetic.make_blobs(5000, 40, 6, 3, 8.0, seed=3)
+    for knn, decay in ((9, 40.0), (5, 10.0)):
+        K = og.knn_kernel(X, knn=knn, decay=decay)
+        rows = np.random.default_rng(0).choice(X.shape[0], 200, replace=False)
+        for (cols, vals), i in zip(og.knn_kernel_rows_bruteforce(X, rows, knn=knn, decay=decay), rows):
+            a, b = K.indptr[i], K.indptr[i + 1]
+            assert np.array_equal(K.indices[a:b], cols)
+            assert np.abs(K.data[a:b] - vals).max() <= 1e-12
+
+
+def test_decay_none_is_the_binary_knn_kernel():
+    X = np.random.default_rng(5).normal(size=(400, 6))
+    K = og.knn_kernel(X, knn=4, decay=None)
+    assert K.shape == (400, 400) and np.all(K.data == 1.0) and np.all(np.diff(K.indptr) == 5)
+    assert np.all(K.diagonal() == 1.0)
+    g = og.build_graph(X, knn=4, decay=None, n_pca=None)
+    assert abs(g["L"] - g["L"].T).max() == 0.0
