@@ -623,8 +623,11 @@ def run_b200(args):
                 "l2_note": "inputs (X {} MB, L {} MB) exceed the 126 MB L2; no explicit flush".format(
                     Xh.nbytes // 2**20, nnz * 12 // 2**20),
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(max(jobs, world if strong else 1) * (Xh.nbytes + 4 * n)),
-                    "d2h_bytes_per_step": int(max(jobs, world if strong else 1) * 8 * n * p), "ms_per_step": e2e_ms / args.steps,
+            # strong scaling: every rank uploads 1 / world of the matrix (all-gathered over NVLink) + the label codes, and
+            # every rank reads back the whole density matrix; replicas: one matrix in, one density matrix out per rank
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(Xh.nbytes + world * 4 * n) if strong else int(jobs * (Xh.nbytes + 4 * n)),
+                    "d2h_bytes_per_step": int((world if strong else jobs) * 8 * n * p), "ms_per_step": e2e_ms / args.steps,
                     "step_ms": {"min": min(e2e_steps), "median": float(np.median(e2e_steps)), "max": max(e2e_steps),
                                 "all": [round(v, 2) for v in e2e_steps]},
                     "host_timings_ms_slowest_step": e2e_host[int(np.argmax(e2e_steps))],

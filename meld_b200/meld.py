@@ -242,6 +242,37 @@ class MELD(object):
         self._log("Calculated PCA in {:.2f} seconds.".format(self.timings_["pca"]))
         return out
 
+    def _distributed_upload(self, torch, X):
+        """Distributed estimators get the same HOST matrix on every rank; every rank needs all of it on its GPU (the
+        candidate search reads every column).  Instead of N ranks pulling the whole matrix through their PCIe links at
+        once (8 x 800 MB at config 5: 175 ms), every rank uploads its 1 / N of the rows and the pieces are all-gathered
+        over NVLink (plumbing: one NCCL call)."""
+        if not self.distributed or isinstance(X, torch.Tensor):
+            return X
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            return X
+        arr = np.asarray(getattr(X, "values", X))
+        if arr.ndim != 2 or arr.dtype not in (np.float64, np.float32) or arr.nbytes < (64 << 20):
+            return X
+        world, rank = dist.get_world_size(), dist.get_rank()
+        n, d = arr.shape
+        chunk = -(-n // world)
+        lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+        full = torch.empty((world * chunk, d), dtype=torch.from_numpy(arr[:1]).dtype, device="cuda")
+        mine = full[rank * chunk:(rank + 1) * chunk]
+        if hi > lo:
+            src = torch.from_numpy(np.ascontiguousarray(arr[lo:hi]))
+            if src.is_pinned() or src.numel() * src.element_size() < (64 << 20):
+                mine[: hi - lo].copy_(src, non_blocking=True)
+            else:  # pageable: through the pinned staging ring
+                from .graph import _pageable_to_device
+
+                mine[: hi - lo].copy_(_pageable_to_device(torch, src))
+        dist.all_gather_into_tensor(full, mine)
+        return full[:n]
+
     def fit(self, X, **kwargs):
         """Build the kNN alpha-decay graph on ``X`` (array-like (N, D), CUDA tensor, or a prebuilt
         ``DeviceGraph``).  Stands in for the inherited ``GraphEstimator.fit``."""
@@ -273,7 +304,7 @@ class MELD(object):
             raise ValueError("Expected a 2D matrix. Got shape {}".format(shape))
         self._log("Building graph on {} samples and {} features.".format(shape[0], shape[1]))
         t0 = time.perf_counter()
-        data_nu = self._reduce_data(X)
+        data_nu = self._reduce_data(self._distributed_upload(torch, X))
         self._log("Calculating graph and diffusion operator...")
         t1 = time.perf_counter()
         slice_bounds = None
