@@ -380,6 +380,8 @@ class MELD(object):
     def sample_indicators(self):
         """Indicator DataFrame (column-normalised when ``sample_normalize``), built on first use."""
         if getattr(self, "_indicators", None) is None and getattr(self, "_codes", None) is not None:
+            if not isinstance(self._codes, np.ndarray):  # factorised on the device
+                self._codes = self._codes.cpu().numpy()
             p = len(self.samples)
             ind = np.zeros((len(self._codes), p), dtype=int)
             ind[np.arange(len(self._codes)), self._codes] = 1
@@ -434,7 +436,7 @@ class MELD(object):
         _filter.filter_kernel(self.filter, self.beta, self.offset, self.order)
         t0 = time.perf_counter()
         dev = self.graph.device
-        d_codes = torch.from_numpy(codes).to(dev, non_blocking=True)
+        d_codes = codes if isinstance(codes, torch.Tensor) else torch.from_numpy(codes).to(dev, non_blocking=True)
         densities = self.transform_device(d_codes, len(samples))
         # Read-back through ONE persistent pinned staging buffer per size (a pageable 16 MB read-back costs ~3x as long;
         # a fresh pinned allocation per call costs a cudaHostAlloc of milliseconds, because the DataFrame returned last
@@ -578,11 +580,24 @@ class MELD(object):
             try:
                 flat = np.asarray(getattr(sample_labels, "values", sample_labels))
                 if flat.ndim == 1 or (flat.ndim == 2 and flat.shape[1] == 1):
-                    pre["codes"] = self._label_codes(sample_labels)
+                    got = None
+                    if dev_index is not None and not os.environ.get("MELD_B200_HOST_LABELS"):
+                        import torch
+
+                        torch.cuda.set_device(dev_index)
+                        side = torch.cuda.Stream()
+                        with torch.cuda.stream(side):
+                            got = _factorize_device(torch, flat.reshape(-1), torch.device("cuda", dev_index))
+                        side.synchronize()
+                    pre["codes"] = got if got is not None else self._label_codes(sample_labels)
             except Exception:  # noqa: BLE001 - recomputed (and raised) by transform
                 pre.clear()
             self.timings_["labels_thread"] = time.perf_counter() - t_thr
 
+        import torch as _torch
+
+        # None without CUDA: fit raises the engine's "no CPU fallback" error; the labels are still factorised on the host
+        dev_index = _torch.cuda.current_device() if _torch.cuda.is_available() else None
         worker = threading.Thread(target=_prefetch, name="meld_b200-labels", daemon=True)
         if os.environ.get("MELD_B200_NO_LABEL_THREAD"):
             _prefetch()
@@ -613,6 +628,42 @@ def _pinned_staging(torch, like):
 
 
 _HASH_MULT = np.random.default_rng(0x5EED).integers(1, 2**63 - 1, size=64, dtype=np.int64).astype(np.uint64) | np.uint64(1)
+
+
+def _factorize_device(torch, labels, dev):
+    """Label codes on the GPU for fixed-width numpy labels (strings, integers, booleans): the raw bytes go up once
+    (16 MB for 500k '<U8' labels), 64-bit words are hashed, ``torch.unique`` (plumbing) gives the codes, and an exact
+    comparison of every label with its representative rules out hash collisions.  Returns (sorted unique labels --
+    ``np.unique`` order --, int32 CUDA tensor of codes) or None when the labels do not qualify.  Runs on the label
+    thread's own stream beside the graph build: with several ranks on one host the Python-side factorisation (12-80 ms,
+    and every rank waits for the slowest) is what an end-to-end step spends its time on."""
+    if not (isinstance(labels, np.ndarray) and labels.ndim == 1 and labels.dtype.kind in "USiub"
+            and 0 < labels.dtype.itemsize <= 512 and len(labels) > 4096):
+        return None
+    n, w = len(labels), labels.dtype.itemsize
+    raw = np.ascontiguousarray(labels).view(np.uint8).reshape(n, w)
+    w8 = (w + 7) // 8
+    if w8 * 8 != w:
+        pad = np.zeros((n, w8 * 8), dtype=np.uint8)
+        pad[:, :w] = raw
+        raw = pad
+    words = torch.from_numpy(raw.view(np.int64).reshape(n, w8)).to(dev)
+    mult = torch.from_numpy(_HASH_MULT[:w8].view(np.int64).copy()).to(dev)
+    h = (words * mult).sum(dim=1)  # wraps modulo 2^64
+    uniq, inv = torch.unique(h, return_inverse=True)
+    k = int(uniq.numel())
+    if k > 4096:
+        return None
+    first = torch.full((k,), n, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, inv, torch.arange(n, dtype=torch.int64, device=dev), reduce="amin")
+    if not bool(torch.equal(words, words[first][inv])):  # two different labels shared a hash: host path
+        return None
+    reps = labels[first.cpu().numpy()]
+    order = np.argsort(reps, kind="stable")
+    rank = np.empty(k, dtype=np.int32)
+    rank[order] = np.arange(k, dtype=np.int32)
+    codes = torch.from_numpy(rank).to(dev)[inv]
+    return reps[order], codes
 
 
 def _factorize(labels):

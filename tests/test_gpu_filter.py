@@ -532,3 +532,27 @@ def test_row_partitioned_lanczos_ranks_in_one_process(mb, world):
         assert _close(outs[r], want)
     for h in ctxs:
         lib.meld_b200_dist_destroy(h)
+
+
+def test_device_label_factorisation_equals_np_unique(mb, monkeypatch):
+    """fit_transform factorises fixed-width numpy labels on the GPU (hash + unique + exact check); codes and column
+    order equal np.unique's, and the densities equal those of the host-side factorisation bit for bit."""
+    import torch
+    from meld_b200.meld import _factorize_device
+
+    rng = np.random.default_rng(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for labels in (rng.choice(np.array(["sample_%d" % i for i in range(5)]), 30000), rng.integers(-3, 4, 20000),
+                   rng.choice(np.array(["a", "bb", "ccc"]), 9000), rng.integers(0, 2, 5000).astype(bool),
+                   rng.choice(np.array([b"x", b"yy"]), 8000)):
+        samples, codes = _factorize_device(torch, labels, dev)
+        u, inv = np.unique(labels, return_inverse=True)
+        assert np.array_equal(samples, u) and samples.dtype == u.dtype
+        assert np.array_equal(codes.cpu().numpy(), inv)
+    assert _factorize_device(torch, np.array(["a", "b"] * 100), dev) is None  # short inputs stay on the host
+    assert _factorize_device(torch, rng.normal(size=9000), dev) is None  # floats (NaN semantics) stay on the host
+    X, labels = mb.synthetic.make_blobs(8000, 20, 5, 3, 6.0, seed=4)
+    a = mb.MELD(verbose=0, knn=7).fit_transform(X, labels)
+    monkeypatch.setenv("MELD_B200_HOST_LABELS", "1")
+    b = mb.MELD(verbose=0, knn=7).fit_transform(X, labels)
+    assert list(a.columns) == list(b.columns) and np.array_equal(a.values, b.values)
