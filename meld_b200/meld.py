@@ -580,16 +580,7 @@ class MELD(object):
             try:
                 flat = np.asarray(getattr(sample_labels, "values", sample_labels))
                 if flat.ndim == 1 or (flat.ndim == 2 and flat.shape[1] == 1):
-                    got = None
-                    if dev_index is not None and not os.environ.get("MELD_B200_HOST_LABELS"):
-                        import torch
-
-                        torch.cuda.set_device(dev_index)
-                        side = torch.cuda.Stream()
-                        with torch.cuda.stream(side):
-                            got = _factorize_device(torch, flat.reshape(-1), torch.device("cuda", dev_index))
-                        side.synchronize()
-                    pre["codes"] = got if got is not None else self._label_codes(sample_labels)
+                    pre["codes"] = self._label_codes(sample_labels)
             except Exception:  # noqa: BLE001 - recomputed (and raised) by transform
                 pre.clear()
             self.timings_["labels_thread"] = time.perf_counter() - t_thr
@@ -599,7 +590,27 @@ class MELD(object):
         # None without CUDA: fit raises the engine's "no CPU fallback" error; the labels are still factorised on the host
         dev_index = _torch.cuda.current_device() if _torch.cuda.is_available() else None
         worker = threading.Thread(target=_prefetch, name="meld_b200-labels", daemon=True)
-        if os.environ.get("MELD_B200_NO_LABEL_THREAD"):
+        # Single GPU: the host factorisation (12-18 ms for 500k string labels) hides behind the ~30 ms build on a thread.
+        # Distributed: the build is only ~10 ms per rank and every rank waits for the slowest host, so the labels are
+        # factorised on the GPU first (~3 ms, _factorize_device).  (Running that on a side stream beside the build was
+        # measured too: the persistent search kernels hold every SM for milliseconds, the small kernels queue behind
+        # them -- 30 ms -- and the end-to-end step got slower and noisier.)
+        device_labels = (dev_index is not None and not os.environ.get("MELD_B200_HOST_LABELS")
+                         and (self.distributed or os.environ.get("MELD_B200_DEVICE_LABELS")))
+        if device_labels:
+            t_lab = time.perf_counter()
+            try:
+                flat = np.asarray(getattr(sample_labels, "values", sample_labels))
+                if flat.ndim == 1 or (flat.ndim == 2 and flat.shape[1] == 1):
+                    got = _factorize_device(_torch, flat.reshape(-1), _torch.device("cuda", dev_index))
+                    if got is not None:
+                        pre["codes"] = got
+            except Exception:  # noqa: BLE001 - the host path below (and transform) deal with it
+                pre.clear()
+            self.timings_["labels_device"] = time.perf_counter() - t_lab
+        if "codes" in pre:
+            pass
+        elif os.environ.get("MELD_B200_NO_LABEL_THREAD"):
             _prefetch()
         else:
             worker.start()

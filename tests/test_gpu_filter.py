@@ -552,7 +552,9 @@ def test_device_label_factorisation_equals_np_unique(mb, monkeypatch):
     assert _factorize_device(torch, np.array(["a", "b"] * 100), dev) is None  # short inputs stay on the host
     assert _factorize_device(torch, rng.normal(size=9000), dev) is None  # floats (NaN semantics) stay on the host
     X, labels = mb.synthetic.make_blobs(8000, 20, 5, 3, 6.0, seed=4)
+    monkeypatch.setenv("MELD_B200_DEVICE_LABELS", "1")  # single GPU defaults to the host thread
     a = mb.MELD(verbose=0, knn=7).fit_transform(X, labels)
+    monkeypatch.delenv("MELD_B200_DEVICE_LABELS")
     monkeypatch.setenv("MELD_B200_HOST_LABELS", "1")
     b = mb.MELD(verbose=0, knn=7).fit_transform(X, labels)
     assert list(a.columns) == list(b.columns) and np.array_equal(a.values, b.values)
