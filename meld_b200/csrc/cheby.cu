@@ -835,7 +835,7 @@ constexpr unsigned long long kFlagTimeoutNs = 4000000000ull;  // 4 s: a lost pee
 __device__ __forceinline__ void peer_wait(const unsigned long long *my_flags, int world, int rank,
                                           unsigned long long epoch, int *err_flag) {
   if (epoch == 0) return;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && *reinterpret_cast<volatile int *>(err_flag) == 0) {  // after a time-out: never wait again
     const unsigned long long t0 = global_timer_ns();
     for (int w = 0; w < world; ++w) {
       if (w == rank) continue;
