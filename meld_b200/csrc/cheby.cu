@@ -7,19 +7,20 @@
 //   estimate_lmax: 1.01 * largest eigenvalue of L.
 //
 // One launch per recurrence term; T_k is written over T_{k-2} (row i of T_{k-2} is only ever read by row i).
-// Three kernel families, selected by Tuning::x_mode (the graph remembers the mode it was finalised for):
-//   x_mode 2 (default)  cheby_flat_kernel / cheby_flat_pipe_kernel: no shared memory, no roles; 32 warps per SM
-//                       walk their own rows (G lanes per row), gather the neighbours' signal rows into registers
-//                       with 256-bit loads and stream values / columns with vectorised evict-first loads.  The
-//                       gather is bound by memory-level parallelism and the L1 tag stage (measured:
-//                       tools/microbench/gather_bench.cu), so staging buys nothing and occupancy everything.
-//   x_mode 0            cheby_step_kernel, dictionary-staged: a persistent 512-thread CTA per SM; warp 0 is a TMA
-//                       producer (cp.async.bulk of values, uint16 dictionary positions, row pointers, the block's
-//                       column dictionary and the rows' own T/R slices into an mbarrier ring), gather warps pull
-//                       the distinct signal rows with cp.async, compute teams multiply out of shared memory.
-//   x_mode 1            cheby_step_kernel with the matrix staged the same way but direct register gathers.
-// The staged kernels were the first design of the round (286 us per launch at 500k cells, the flat kernel 154);
-// they remain as cross-checked variants (tests/test_gpu_filter.py::test_filter_kernel_variants_agree).
+// Kernels (Tuning::x_mode; the graph remembers the mode it was finalised for):
+//   x_mode 2 (default)  cheby_flat2_kernel (round 2; cheby_flat_kernel / cheby_flat_pipe_kernel of round 1 remain for
+//                       very short / very long rows and as cross-checks): no shared memory, no roles; 32 warps per
+//                       SM walk their own rows (8 lanes per row), gather the neighbours' signal rows into registers
+//                       with 256-bit loads and stream values / columns with non-allocating vector loads.  Variants by
+//                       template: cache hints, entry layout, DOT (fused Lanczos dot product), PEER (row-partitioned
+//                       multi-GPU term: waits for the peers' flags, stores T_k into the peers' buffers over NVLink,
+//                       publishes its own flag).  The kernel is bound by the L1TEX data pipe: one slot per gathered
+//                       32-byte sector, whatever level serves it.
+//   x_mode 0 / 1        cheby_step_kernel: the first design of round 1 (TMA-staged row blocks, per-block column
+//                       dictionaries, cp.async gather warps; 286 us per launch at 500k cells against 152).  Kept only as
+//                       cross-checked variants (tests/test_gpu_filter.py::test_filter_kernel_variants_agree).
+// Also here: the Lanczos lmax estimate (single GPU and row-partitioned), the shared-basis sweep
+// (meld_b200_cheby_sweep), the row-partitioned filter (meld_b200_cheby_filter_dist) and the small signal helpers.
 #include "common.cuh"
 
 #include <math.h>
