@@ -22,6 +22,11 @@
 //      are appended to the other row;
 //   4. rows brought into column order by rank (merge_rows_kernel: own entries are already ascending, the
 //      few mirrored ones are placed by counting), then anisotropy + Laplacian in place.
+// Entry points: meld_b200_knn_graph_build (one GPU), meld_b200_dense_graph_build (thresh = 0: every pair is a
+// candidate, test scale), meld_b200_knn_candidates + meld_b200_graph_from_candidates (stage 1 sharded by query rows,
+// stage 2 replicated), meld_b200_stage2_begin / _records / _assemble / _finish (stage 2 row-partitioned as well: every
+// rank assembles only its rows; the caller runs two 8 N-byte all-gathers and one all-to-all-v of mirror records).
+// decay = 0 stands for the reference's decay=None (binary kNN kernel).
 #include "common.cuh"
 #include "knn_search.cuh"
 
