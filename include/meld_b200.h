@@ -53,10 +53,10 @@ int64_t meld_b200_sync_count(void);
 /* sm_count / cc_major / cc_minor of the current device (host pointers).        */
 int meld_b200_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
 
-/* Launch-configuration knobs of the Chebyshev kernel, for bench sweeps and tests
- * only (keys: blk_chunk, stage_cap, dict_cap, row_cap, n_stage, threads, gather_warps,
- * ctas_per_sm, group, use_dict, reorder, tc_multicast, prune, clusters, kmeans_iters,
- * reorder_min_n, prune_window, cluster_cells).  Takes effect for graphs created afterwards.                       */
+/* Launch-configuration knobs for bench sweeps and tests only (the defaults are the shipped configuration; the key
+ * list is in INTEGRATION.md: Chebyshev kernels blk_chunk, group, flat_*, pad_width, ctas_per_sm; graph build reorder,
+ * clusters, kmeans_iters, km_var_pct, prune*, tl_*, tc_multicast, ...).  Unknown keys are an error.  Takes effect
+ * for graphs created afterwards.                                                                                  */
 int meld_b200_set_tuning(const char *key, int value);
 
 /* ---- graph construction ------------------------------------------------------ */
@@ -166,8 +166,8 @@ int meld_b200_graph_export_knn_kernel(const meld_b200_graph_t *g, int64_t *indpt
                                       double *data, void *stream);
 /* Build statistics (host): [0] candidate-search passes run, [1] max candidates/row,
  * [2] candidate capacity used, [3] rows that overflowed on the first emit pass,
- * [4] search implementation (0 tcgen05, 1 SIMT), [5] sum of block dictionary sizes,
- * [6] row blocks on the direct path, [7] row blocks.                */
+ * [4] search implementation (0 tcgen05, 1 SIMT), [5], [6] reserved (0), [7] row blocks of the
+ * nonzero-balanced partition.                                        */
 int meld_b200_graph_build_stats(const meld_b200_graph_t *g, int64_t *stats8_host);
 /* CUDA-event timings of the last build (host): [0] ms of search pass 1, [1] ms of pass 2,
  * [2] flops issued by pass 2 and [3] by pass 1 (2 x 128 x 256 x K' per (row tile, column tile)

@@ -7,18 +7,16 @@
 //   estimate_lmax: 1.01 * largest eigenvalue of L.
 //
 // One launch per recurrence term; T_k is written over T_{k-2} (row i of T_{k-2} is only ever read by row i).
-// Kernels (Tuning::x_mode; the graph remembers the mode it was finalised for):
-//   x_mode 2 (default)  cheby_flat2_kernel (round 2; cheby_flat_kernel / cheby_flat_pipe_kernel of round 1 remain for
-//                       very short / very long rows and as cross-checks): no shared memory, no roles; 32 warps per
-//                       SM walk their own rows (8 lanes per row), gather the neighbours' signal rows into registers
-//                       with 256-bit loads and stream values / columns with non-allocating vector loads.  Variants by
-//                       template: cache hints, entry layout, DOT (fused Lanczos dot product), PEER (row-partitioned
-//                       multi-GPU term: waits for the peers' flags, stores T_k into the peers' buffers over NVLink,
-//                       publishes its own flag).  The kernel is bound by the L1TEX data pipe: one slot per gathered
-//                       32-byte sector, whatever level serves it.
-//   x_mode 0 / 1        cheby_step_kernel: the first design of round 1 (TMA-staged row blocks, per-block column
-//                       dictionaries, cp.async gather warps; 286 us per launch at 500k cells against 152).  Kept only as
-//                       cross-checked variants (tests/test_gpu_filter.py::test_filter_kernel_variants_agree).
+// Kernels: no shared-memory staging, no warp roles; 32 warps per SM walk their own rows, gather the neighbours' signal
+// rows into registers with 256-bit loads and stream values / columns with non-allocating vector loads.
+//   cheby_flat2_kernel   (default, 8 lanes per row)  variants by template: cache hints, entry layout, DOT (fused
+//                        Lanczos dot product), PEER (row-partitioned multi-GPU term: waits for the peers' flags,
+//                        stores T_k into the peers' buffers over NVLink, publishes its own flag).  Bound by the L1TEX
+//                        data pipe: one slot per gathered 32-byte sector, whatever level serves it.
+//   cheby_flat_kernel / cheby_flat_pipe_kernel  (round 1)  4 / 16 / 32 lanes per row for very short (<= 12 entries) or
+//                        very long (> 256) rows; also the cross-checks of tests/test_gpu_filter.py.
+// The first design of round 1 (TMA-staged row blocks with per-block column dictionaries and cp.async gather warps,
+// 286 us per launch at 500k cells against 152) was removed in round 2: it lost at every graph shape measured.
 // Also here: the Lanczos lmax estimate (single GPU and row-partitioned), the shared-basis sweep
 // (meld_b200_cheby_sweep), the row-partitioned filter (meld_b200_cheby_filter_dist) and the small signal helpers.
 #include "common.cuh"
@@ -29,62 +27,12 @@
 
 namespace meld {
 
-// ---- PTX helpers: mbarrier, 1-D TMA bulk copy, cp.async ---------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar), ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16_cg(void *dst, const void *src) {  // L2 only, no L1 allocation
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-// this thread's earlier cp.async copies count as one (pre-counted) arrival once they have landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 constexpr int kMaxPeers = 7;  // ranks of one NVSwitch box besides this one
 
 struct StepArgs {
   const int32_t *row_ptr;
   const int32_t *col;
   const double *val;
-  const uint16_t *lidx;
-  const int32_t *dict;
-  const int32_t *dcnt;
   const int32_t *blk;
   int32_t n_blk;
   int64_t row0;
@@ -94,18 +42,6 @@ struct StepArgs {
   double *R;
   double alpha, shift, gamma, c, c_cur;
   int r_acc;
-  int cap;         // CSR entries per stage
-  int ucap;        // dictionary entries (distinct columns) per stage
-  int rcap;        // row pointers per stage
-  int rows_cap;    // rows whose T/R slices are staged
-  int n_stage;     // pipeline depth
-  int gather_warps;
-  int x_mode;      // 0: dictionary + cp.async gathers; 1: staged (val, col) and direct register gathers
-  int team_warps;  // compute warps per team (one team per in-flight block)
-  int gather_rows; // dictionary rows fetched per warp-level cp.async instruction
-  int gather_cg;   // 1: cp.async.cg (bypass L1) for the gathers
-  int stage_epi;   // 1: the T/R arrays are library workspace (padded), slices may be bulk-copied
-  int stage_bytes;
   // flat kernel extras
   double *dot_partials;        // DOT variant (p = 1): per-CTA partial sums of T_cur[row] * y[row]
   // row-partitioned multi-GPU step (PEER variant): T_new is also stored into every peer's copy of the buffer
@@ -150,34 +86,6 @@ __device__ __forceinline__ void gather_row(const double *__restrict__ T, int32_t
     for (int k = 0; k < P; ++k) x[k] = __ldg(t + k);
   }
 }
-// The gathered rows are read back at random positions with 128-bit shared-memory loads, 8 lanes per
-// wavefront.  Chunk c of row t sits in 16-byte bank group (t * CH + c) mod 8, so for CH = 2 (p = 4) the
-// eight lanes of a wavefront can only hit four groups, for CH = 4 (p = 8) only two.  XOR-ing the chunk
-// index with a few higher bits of t spreads a wavefront over all eight groups.
-template <int P>
-__device__ __forceinline__ int chunk_swizzle(int t) {
-  if constexpr (P == 4) return (t >> 2) & 1;
-  if constexpr (P == 8) return (t >> 1) & 3;
-  return 0;
-}
-// Same row out of the stage's shared-memory copy.
-template <int P>
-__device__ __forceinline__ void smem_row(const double *xs, int li, double (&x)[P]) {
-  const double *t = xs + (size_t)li * P;
-  if constexpr (P % 2 == 0) {
-    const int sw = chunk_swizzle<P>(li);
-#pragma unroll
-    for (int k = 0; k < P; k += 2) {
-      const double2 v = *reinterpret_cast<const double2 *>(t + 2 * ((k >> 1) ^ sw));
-      x[k] = v.x;
-      x[k + 1] = v.y;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < P; ++k) x[k] = t[k];
-  }
-}
-
 __device__ __forceinline__ double ld_stream(const double *p) {  // read-once operand: do not keep in L1
   double v;
   asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -204,288 +112,7 @@ __device__ __forceinline__ double block_sum_fwd(double v, double *sh) {
   return sh[32];
 }
 
-constexpr int kUnroll = 4;  // independent entries in flight per lane
-
-// Where a block's operands live (shared-memory stage or global memory), already offset so that
-// CSR-entry / row indices are absolute.
-struct BlockView {
-  const double *vs;       // values, indexed by entry
-  const uint16_t *ls;     // dictionary positions, indexed by entry (staged blocks)
-  const int32_t *cs;      // columns, indexed by entry (direct blocks)
-  const int32_t *rp;      // row pointers, indexed by row
-  const double *xs;       // gathered T_cur rows of the dictionary (staged blocks)
-  const double *tc, *told, *rold;  // per-row slices indexed by (row * P + k), or nullptr -> global
-};
-
-template <int P, int G, int MODE>  // 0: all from global, 1: dictionary stage, 2: staged (val, col) + direct gathers
-__device__ __forceinline__ void process_rows(const StepArgs &a, const BlockView &bv, int r0, int r1, int gid, int gl,
-                                             int ngroups) {
-  for (int rb = r0; rb < r1; rb += ngroups) {  // uniform trip count for all compute warps (full-mask shuffles)
-    const int r = rb + gid;
-    const bool act = r < r1;
-    int eb = 0, ee = 0;
-    if (act) {
-      eb = bv.rp[r];
-      ee = bv.rp[r + 1];
-    }
-    const bool epi = act && gl < P;
-    const size_t li = (size_t)r * P + gl;
-    double tc = 0.0, told = 0.0, rold = 0.0;
-    if (epi) {  // requested first so their latency overlaps the row product
-      tc = bv.tc ? bv.tc[li] : __ldg(a.Tcur + (size_t)(a.row0 + r) * P + gl);
-      if (a.gamma != 0.0) told = bv.told ? bv.told[li] : ld_stream(a.Told + li);
-      if (a.R != nullptr && a.r_acc) rold = bv.rold ? bv.rold[li] : ld_stream(a.R + li);
-    }
-    double acc[P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) acc[k] = 0.0;
-    for (int e = eb + gl; e < ee; e += kUnroll * G) {
-      double v[kUnroll];
-      double x[kUnroll][P];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int eu = e + u * G;
-        if (eu < ee) {
-          v[u] = bv.vs[eu];
-          if constexpr (MODE == 1)
-            smem_row<P>(bv.xs, (int)bv.ls[eu], x[u]);
-          else
-            gather_row<P>(a.Tcur, bv.cs[eu], x[u]);
-        } else {
-          v[u] = 0.0;
-#pragma unroll
-          for (int k = 0; k < P; ++k) x[u][k] = 0.0;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-#pragma unroll
-        for (int k = 0; k < P; ++k) acc[k] = fma(v[u], x[u][k], acc[k]);
-      }
-    }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < P; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    }
-    if (epi) {
-      double y = acc[0];
-#pragma unroll
-      for (int k = 1; k < P; ++k)
-        if (gl == k) y = acc[k];
-      double tn = a.alpha * (y - a.shift * tc);
-      if (a.gamma != 0.0) tn -= a.gamma * told;
-      if (a.Tnew) a.Tnew[li] = tn;  // gathered by the next step: keep cacheable
-      if (a.R) {
-        double rv = a.c * tn + a.c_cur * tc;
-        if (a.r_acc) rv += rold;
-        st_stream(a.R + li, rv);
-      }
-    }
-  }
-}
-
-// Geometry of one block; every role recomputes it from the same two small arrays.
-struct BlockGeom {
-  int r0, r1, e0, e1;
-  int a0, nal;   // entry range aligned to 8 entries (16 B of uint16 indices)
-  int ra, nr;    // row-pointer range aligned to 4
-  int u;         // dictionary size, < 0: direct block
-  bool staged, epi_staged;
-  size_t sc0, sl0;  // aligned first element of the T_cur-own / local-row slices
-  int nc, nl;       // their lengths (even)
-};
-
-template <int P>
-__device__ __forceinline__ BlockGeom block_geom(const StepArgs &a, int b) {
-  BlockGeom g;
-  g.r0 = __ldg(a.blk + b);
-  g.r1 = __ldg(a.blk + b + 1);
-  g.e0 = __ldg(a.row_ptr + g.r0);
-  g.e1 = __ldg(a.row_ptr + g.r1);
-  g.a0 = g.e0 & ~7;
-  g.nal = ((g.e1 - g.a0) + 7) & ~7;
-  g.ra = g.r0 & ~3;
-  g.nr = ((g.r1 + 1 - g.ra) + 3) & ~3;
-  g.u = __ldg(a.dcnt + b);
-  g.staged = g.u >= 0 && g.nal <= a.cap && g.nr <= a.rcap && g.u <= a.ucap && g.e1 > g.e0;  // x_mode 1: u == 0
-  g.epi_staged = g.staged && a.stage_epi && (g.r1 - g.r0) <= a.rows_cap;
-  const size_t c0 = (size_t)(a.row0 + g.r0) * P, c1 = (size_t)(a.row0 + g.r1) * P;
-  const size_t l0 = (size_t)g.r0 * P, l1 = (size_t)g.r1 * P;
-  g.sc0 = c0 & ~(size_t)1;
-  g.sl0 = l0 & ~(size_t)1;
-  g.nc = (int)(((c1 - g.sc0) + 1) & ~(size_t)1);
-  g.nl = (int)(((l1 - g.sl0) + 1) & ~(size_t)1);
-  return g;
-}
-
-template <int P, int G>
-__global__ void __launch_bounds__(512, 1) cheby_step_kernel(const StepArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int ns = a.n_stage;
-  // stage layout (bytes): values | local indices | row pointers | dictionary | gathered rows | tc | told | rold
-  const int off_l = a.cap * 8;
-  const int off_r = off_l + a.cap * (a.x_mode == 1 ? 4 : 2);  // uint16 dictionary positions or int32 columns
-  const int off_d = off_r + a.rcap * 4;
-  const int off_x = off_d + a.ucap * 4;
-  const int epi_len = a.rows_cap * P + 2;
-  const int off_tc = off_x + a.ucap * P * 8;
-  const int off_to = off_tc + epi_len * 8;
-  const int off_ro = off_to + epi_len * 8;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ns * a.stage_bytes);
-  uint64_t *full_mat = bars, *full_x = bars + ns, *empty = bars + 2 * ns;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_compute_warps = (blockDim.x >> 5) - 1 - a.gather_warps;
-  const int stride = gridDim.x;
-
-  if (tid == 0) {
-    for (int s = 0; s < ns; ++s) {
-      mbar_init(&full_mat[s], 1);
-      mbar_init(&full_x[s], (uint32_t)a.gather_warps * 32u);
-      mbar_init(&empty[s], (uint32_t)a.team_warps);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0;
-      for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
-        const int s = it % ns;
-        const uint32_t ph = (uint32_t)(it / ns) & 1u;
-        unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
-        mbar_wait(&empty[s], ph ^ 1u);
-        const BlockGeom g = block_geom<P>(a, b);
-        if (!g.staged) {
-          mbar_arrive(&full_mat[s]);  // direct block: nothing staged, the phase still advances
-          continue;
-        }
-        const uint32_t ub = a.x_mode == 1 ? 0u : (uint32_t)((g.u + 3) & ~3) * 4u;
-        const uint32_t ib = (uint32_t)g.nal * (a.x_mode == 1 ? 4u : 2u);
-        uint32_t bytes = (uint32_t)g.nal * 8u + ib + (uint32_t)g.nr * 4u + ub;
-        if (g.epi_staged) {
-          bytes += (uint32_t)g.nc * 8u;
-          if (a.gamma != 0.0) bytes += (uint32_t)g.nl * 8u;
-          if (a.R != nullptr && a.r_acc) bytes += (uint32_t)g.nl * 8u;
-        }
-        mbar_arrive_expect_tx(&full_mat[s], bytes);
-        bulk_g2s(st, a.val + g.a0, (uint32_t)g.nal * 8u, &full_mat[s]);
-        if (a.x_mode == 1)
-          bulk_g2s(st + off_l, a.col + g.a0, ib, &full_mat[s]);
-        else
-          bulk_g2s(st + off_l, a.lidx + g.a0, ib, &full_mat[s]);
-        bulk_g2s(st + off_r, a.row_ptr + g.ra, (uint32_t)g.nr * 4u, &full_mat[s]);
-        if (ub) bulk_g2s(st + off_d, a.dict + (size_t)b * a.ucap, ub, &full_mat[s]);
-        if (g.epi_staged) {
-          bulk_g2s(st + off_tc, a.Tcur + g.sc0, (uint32_t)g.nc * 8u, &full_mat[s]);
-          if (a.gamma != 0.0) bulk_g2s(st + off_to, a.Told + g.sl0, (uint32_t)g.nl * 8u, &full_mat[s]);
-          if (a.R != nullptr && a.r_acc) bulk_g2s(st + off_ro, a.R + g.sl0, (uint32_t)g.nl * 8u, &full_mat[s]);
-        }
-      }
-    }
-  } else if (warp <= a.gather_warps) {
-    // ===== gather warps: dictionary -> cp.async of the T_cur rows into the stage =====
-    int it = 0;
-    for (int b = blockIdx.x; b < a.n_blk; b += stride, ++it) {
-      const int s = it % ns;
-      const uint32_t ph = (uint32_t)(it / ns) & 1u;
-      unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
-      mbar_wait(&full_mat[s], ph);
-      const BlockGeom g = block_geom<P>(a, b);
-      if (g.staged && a.x_mode == 0) {
-        const int32_t *sd = reinterpret_cast<const int32_t *>(st + off_d);
-        double *xs = reinterpret_cast<double *>(st + off_x);
-        // Consecutive lanes copy consecutive chunks of the same row.  Only the first gather_rows * CH lanes
-        // of a warp are active per instruction: every distinct 128-byte line inside ONE warp-level request
-        // is replayed at ~2 L1 cycles, while separate requests stream at ~1 cycle each, so few rows per
-        // instruction keep the L1 pipe (the real bound of this kernel) at its best rate.
-        constexpr int CH = (P % 2 == 0) ? P / 2 : P;   // chunks per row: 16 B (even P) or 8 B (odd P)
-        const int rpi = a.gather_rows > 0 ? min(a.gather_rows, 32 / CH) : 32 / CH;  // rows per warp instruction (0 = all lanes)
-        const int gw = warp - 1;
-        if (lane < rpi * CH) {
-          const int ch = lane % CH;
-          for (int t = gw * rpi + lane / CH; t < g.u; t += a.gather_warps * rpi) {
-            const double *src = a.Tcur + (size_t)sd[t] * P;
-            double *dst = xs + (size_t)t * P;
-            if constexpr (P % 2 == 0) {
-              double *d16 = dst + 2 * (ch ^ chunk_swizzle<P>(t));
-              if (a.gather_cg)
-                cp_async16_cg(d16, src + 2 * ch);
-              else
-                cp_async16(d16, src + 2 * ch);
-            } else {
-              cp_async8(dst + ch, src + ch);
-            }
-          }
-        }
-      }
-      cp_async_arrive_noinc(&full_x[s]);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  } else {
-    // ===== compute warps, in teams: team j owns blocks it = j, j + n_teams, ... so several stages are
-    // multiplied concurrently and a small block (a dozen rows) still keeps every lane of its team busy
-    const int cw = warp - 1 - a.gather_warps;
-    const int team = cw / a.team_warps, wit = cw % a.team_warps;
-    // never more teams than stages: a team waiting for use k of a stage must not be able to get a whole
-    // ring ahead of the slowest team (an mbarrier parity wait cannot tell "two phases behind" from "done")
-    const int n_teams = min(n_compute_warps / a.team_warps, ns);
-    const int ct = wit * 32 + lane;
-    const int ngroups = a.team_warps * 32 / G;
-    const int gid = ct / G, gl = ct % G;
-    if (team < n_teams) {
-      for (int it = team; blockIdx.x + (long long)it * stride < a.n_blk; it += n_teams) {
-        const int b = blockIdx.x + it * stride;
-        const int s = it % ns;
-        const uint32_t ph = (uint32_t)(it / ns) & 1u;
-        unsigned char *st = smem_raw + (size_t)s * a.stage_bytes;
-        const BlockGeom g = block_geom<P>(a, b);
-        // Teams consume stages out of order.  Before trusting a parity wait on use k of this stage, make
-        // sure use k-1 was released (then the "full" barriers really are in phase k, not still in k-1,
-        // where a wait for parity k would pass immediately and read the previous block's data).
-        if (it >= ns) mbar_wait(&empty[s], (uint32_t)(it / ns - 1) & 1u);
-        mbar_wait(&full_mat[s], ph);
-        mbar_wait(&full_x[s], ph);
-        BlockView bv;
-        if (g.staged) {
-          bv.vs = reinterpret_cast<const double *>(st) - g.a0;
-          bv.ls = reinterpret_cast<const uint16_t *>(st + off_l) - g.a0;
-          bv.cs = nullptr;
-          bv.rp = reinterpret_cast<const int32_t *>(st + off_r) - g.ra;
-          bv.xs = reinterpret_cast<const double *>(st + off_x);
-          if (g.epi_staged) {
-            bv.tc = reinterpret_cast<const double *>(st + off_tc) - g.sc0 + (size_t)a.row0 * P;  // indexed by local row
-            bv.told = (a.gamma != 0.0) ? reinterpret_cast<const double *>(st + off_to) - g.sl0 : nullptr;
-            bv.rold = (a.R != nullptr && a.r_acc) ? reinterpret_cast<const double *>(st + off_ro) - g.sl0 : nullptr;
-          } else {
-            bv.tc = bv.told = bv.rold = nullptr;
-          }
-          if (a.x_mode == 1) {
-            bv.cs = reinterpret_cast<const int32_t *>(st + off_l) - g.a0;
-            process_rows<P, G, 2>(a, bv, g.r0, g.r1, gid, gl, ngroups);
-          } else {
-            process_rows<P, G, 1>(a, bv, g.r0, g.r1, gid, gl, ngroups);
-          }
-        } else {
-          bv.vs = a.val;
-          bv.ls = nullptr;
-          bv.cs = a.col;
-          bv.rp = a.row_ptr;
-          bv.xs = nullptr;
-          bv.tc = bv.told = bv.rold = nullptr;
-          process_rows<P, G, 0>(a, bv, g.r0, g.r1, gid, gl, ngroups);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-      }
-    }
-  }
-}
-
-// ---- x_mode 2: the flat kernel ---------------------------------------------------------------------------
+// ---- the flat kernels ---------------------------------------------------------------------------------------
 // Measured on B200 (tools/microbench/gather_bench.cu): random 32-byte rows out of an L2-resident table arrive
 // at 0.55 / 0.70 / 0.79 rows per cycle per SM with 1024 / 2048 / 4096 LDG.256 in flight per SM, LDGSTS and
 // 32-byte TMA bulk copies are far slower (0.2 and 0.16 at best) -- the gather is bound by memory-level
@@ -1118,35 +745,6 @@ static FlatKernel pick_flat2_dot(int hint, bool peer) {
 static int auto_hint(int P, int hint) { return hint >= 0 ? hint : (P > 4 ? 2 : 1); }
 static int auto_layout(int P, int layout) { return layout >= 0 ? layout : (P > 4 ? 0 : 1); }
 
-typedef void (*StepKernel)(const StepArgs);
-
-template <int P>
-static StepKernel pick_group(int G) {
-  if constexpr (P <= 4) {
-    if (G == 4) return cheby_step_kernel<P, 4>;
-  }
-  switch (G) {
-    case 4:
-    case 8: return cheby_step_kernel<P, 8>;
-    case 16: return cheby_step_kernel<P, 16>;
-    default: return cheby_step_kernel<P, 32>;
-  }
-}
-
-static StepKernel pick_kernel(int P, int G) {
-  switch (P) {
-    case 1: return pick_group<1>(G);
-    case 2: return pick_group<2>(G);
-    case 3: return pick_group<3>(G);
-    case 4: return pick_group<4>(G);
-    case 5: return pick_group<5>(G);
-    case 6: return pick_group<6>(G);
-    case 7: return pick_group<7>(G);
-    case 8: return pick_group<8>(G);
-    default: return nullptr;
-  }
-}
-
 static int choose_group(const meld_b200_graph *g, int P) {
   int G = tuning().group;
   if (G != 4 && G != 8 && G != 16 && G != 32) {
@@ -1157,17 +755,14 @@ static int choose_group(const meld_b200_graph *g, int P) {
   return G;
 }
 
-// stage_epi: the T/R arrays come from library workspace (padded by two doubles), so the rows' own
-// slices may be bulk-copied with 16-byte aligned, even-length requests.
-static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_epi, cudaStream_t stream,
-                       int *grid_out = nullptr) {
+static int launch_step(const meld_b200_graph *g, StepArgs a, int P, cudaStream_t stream, int *grid_out = nullptr) {
   const Tuning &t = tuning();
   const int G = choose_group(g, P);
   const bool want_peer = a.n_peers > 0 || a.wait_epoch != 0 || a.post_epoch != 0;
   const bool want_dot = a.dot_partials != nullptr;
   // very short (<= 12 entries) or very long (> 256) rows keep the round-1 kernels with 4 / 32 lanes per row
   const bool g8 = (t.flat_group > 0 ? t.flat_group : G) == 8 || (t.flat_group <= 0 && G == 16);
-  if ((g->x_mode == 2 && t.flat_gen == 1 && g8) || want_peer || want_dot) {  // second-generation flat kernel (8 lanes per row)
+  if ((t.flat_gen == 1 && g8) || want_peer || want_dot) {  // second-generation flat kernel (8 lanes per row)
     const int hint = auto_hint(P, t.flat_hint), layout = auto_layout(P, t.flat_layout);
     FlatKernel fk = want_dot ? pick_flat2_dot(hint, want_peer)
                              : (want_peer ? pick_flat2_peer(P, hint) : pick_flat2(P, hint, layout));
@@ -1189,7 +784,7 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
     if (grid_out) *grid_out = grid;
     return 0;
   }
-  if (g->x_mode == 2) {  // flat kernel
+  {  // round-1 flat kernels (4 / 16 / 32 lanes per row, 768-thread and pipelined variants)
     int Gf = t.flat_group > 0 ? t.flat_group : G;
     if (Gf < P) Gf = 8;
     const bool wide = t.flat_threads != 768;
@@ -1218,53 +813,6 @@ static int launch_step(const meld_b200_graph *g, StepArgs a, int P, int stage_ep
     MELD_LAUNCH_CHECK();
     return 0;
   }
-  StepKernel k = pick_kernel(P, G);
-  MELD_REQUIRE(k != nullptr, "cheby_step: p=%d outside 1..8", P);
-  a.row_ptr = g->row_ptr.p;
-  a.col = g->col.p;
-  a.val = g->val.p;
-  a.lidx = g->lidx.p;
-  a.dict = g->dict.p;
-  a.dcnt = g->dcnt.p;
-  a.blk = g->blk.p;
-  a.n_blk = g->n_blk;
-  a.row0 = g->row0;
-  a.cap = g->stage_cap;
-  a.ucap = g->dict_cap;
-  a.rcap = g->row_cap + 8;
-  a.rows_cap = g->row_cap;
-  a.gather_warps = t.gather_warps;
-  a.team_warps = t.team_warps;
-  a.gather_rows = t.gather_rows;
-  a.gather_cg = t.gather_cg;
-  a.stage_epi = stage_epi;
-  const int threads = t.threads;
-  MELD_REQUIRE(threads % 32 == 0 && threads >= 96 && threads <= 512 && t.gather_warps >= 1 &&
-                   t.team_warps >= 1 && threads / 32 - 1 - t.gather_warps >= t.team_warps &&
-                   (t.gather_warps * 32) % 8 == 0,
-               "cheby_step: bad tuning (threads=%d gather_warps=%d)", threads, t.gather_warps);
-  const size_t epi_len = (size_t)a.rows_cap * P + 2;
-  a.x_mode = g->x_mode >= 1 ? 1 : 0;  // a flat-kernel graph whose rows are too long for it runs staged + direct gathers
-  if (a.x_mode == 1) a.ucap = 0;  // no dictionary / gathered-row area in the stage
-  size_t stage = (size_t)a.cap * (a.x_mode == 1 ? 12 : 10) + (size_t)a.rcap * 4 + (size_t)a.ucap * 4 +
-                 (size_t)a.ucap * P * 8 + 3 * epi_len * 8;
-  stage = (stage + 127) & ~(size_t)127;
-  const size_t budget = 227 * 1024 - 256;
-  int ns = t.n_stage > 0 ? t.n_stage : (int)(budget / stage);
-  if (ns > 8) ns = 8;
-  while (ns > 1 && (size_t)ns * stage + (size_t)ns * 24 > budget) --ns;
-  MELD_REQUIRE(ns >= 1 && (size_t)ns * stage + (size_t)ns * 24 <= budget, "cheby_step: a %zu-byte stage does not fit",
-               stage);
-  a.n_stage = ns;
-  a.stage_bytes = (int)stage;
-  const size_t smem = (size_t)ns * stage + (size_t)ns * 24;
-  MELD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = sm_count() * t.ctas_per_sm;
-  if (grid > g->n_blk) grid = g->n_blk;
-  if (grid < 1) grid = 1;
-  k<<<grid, threads, smem, stream>>>(a);
-  MELD_LAUNCH_CHECK();
-  return 0;
 }
 
 static int grid_for(int64_t n, int threads);
@@ -1592,7 +1140,7 @@ int meld_b200_cheby_step(meld_b200_graph_t *g, const double *T_cur, const double
   a.c = c;
   a.c_cur = c_cur;
   a.r_acc = r_accumulate;
-  return launch_step(g, a, p, /*stage_epi=*/0, (cudaStream_t)stream_);  // caller arrays: no padded bulk reads
+  return launch_step(g, a, p, (cudaStream_t)stream_);
 }
 
 int meld_b200_graph_permute_signal(const meld_b200_graph_t *g, const double *in, int p, int to_internal, double *out,
@@ -1617,8 +1165,7 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
   MELD_REQUIRE(g->row0 == 0 && g->n_rows == g->n_cols, "cheby_filter: needs the full operator (use cheby_step)");
   MELD_REQUIRE(S != R, "cheby_filter: R may not alias S");
   const int64_t n = g->n_rows;
-  // the staged kernels (x_mode 0 / 1) bulk-copy unpadded row slices; the flat kernels run on the padded width
-  const int pw = g->x_mode == 2 ? padded_width(p) : p;
+  const int pw = padded_width(p);
   // four padded work arrays (S and R in graph order, two recurrence buffers): even length + 2 so
   // the kernel's 16-byte aligned bulk copies of row slices stay inside the allocation
   const size_t len = ((size_t)n * pw + 2 + 3) & ~(size_t)3;  // multiple of 32 bytes: 256-bit gathers on the direct path
@@ -1640,7 +1187,7 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
   a.c = coeffs_host[1];
   a.c_cur = 0.5 * coeffs_host[0];
   a.r_acc = 0;
-  MELD_CHECK(launch_step(g, a, pw, 1, stream));
+  MELD_CHECK(launch_step(g, a, pw, stream));
   // k = 2 still reads T0 = S, so T2 goes to the second buffer; from k = 3 on T_k overwrites T_{k-2}.
   const double *cur = Ta, *old = Sp;
   for (int k = 2; k < n_coeffs; ++k) {
@@ -1653,7 +1200,7 @@ int meld_b200_cheby_filter(meld_b200_graph_t *g, double lmax, const double *coef
     a.c = coeffs_host[k];
     a.c_cur = 0.0;
     a.r_acc = 1;
-    MELD_CHECK(launch_step(g, a, pw, 1, stream));
+    MELD_CHECK(launch_step(g, a, pw, stream));
     old = cur;
     cur = nxt;
   }
@@ -1728,7 +1275,7 @@ int meld_b200_cheby_filter_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, doub
     a.wait_epoch = d->epoch;  // the peers' stores of term k-1 (or their release of the buffers) are visible
     a.post_epoch = ++d->epoch;
     if (nloc > 0) {
-      MELD_CHECK(launch_step(gs, a, pw, 0, stream));
+      MELD_CHECK(launch_step(gs, a, pw, stream));
     } else {  // a rank without rows still takes part in every phase
       dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, p, p, nullptr);
       MELD_LAUNCH_CHECK();
@@ -1758,7 +1305,7 @@ int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeff
   MELD_REQUIRE(g->row0 == 0 && g->n_rows == g->n_cols, "cheby_sweep: needs the full operator");
   const int64_t n = g->n_rows;
   // the whole basis T_0 .. T_m is kept (n_coeffs slots of the padded signal) + the coefficient table
-  const int pw = g->x_mode == 2 ? padded_width(p) : p;
+  const int pw = padded_width(p);
   const size_t len = ((size_t)n * pw + 2 + 3) & ~(size_t)3;
   const size_t ctab = ((size_t)n_filters * n_coeffs + 3) & ~(size_t)3;
   MELD_CHECK(ensure_work(g, (size_t)n_coeffs * len + ctab));
@@ -1785,7 +1332,7 @@ int meld_b200_cheby_sweep(meld_b200_graph_t *g, double lmax, const double *coeff
     a.alpha = (k == 1 ? 1.0 : 2.0) / a1;
     a.shift = a2;
     a.gamma = k >= 2 ? 1.0 : 0.0;
-    MELD_CHECK(launch_step(g, a, pw, 1, stream));
+    MELD_CHECK(launch_step(g, a, pw, stream));
   }
   constexpr int FC = 16;
   const size_t smem = (size_t)FC * n_coeffs * sizeof(double);
@@ -1840,7 +1387,7 @@ int meld_b200_estimate_lmax(meld_b200_graph_t *g, int max_iters, double rel_tol,
       a.Tnew = y;
       a.alpha = 1.0;
       a.dot_partials = pa;
-      MELD_CHECK(launch_step(g, a, 1, 1, stream));
+      MELD_CHECK(launch_step(g, a, 1, stream));
       lanczos_axpy_kernel<<<kRedBlocks, kRedThreads, 0, stream>>>(y, w_cur, w_prev, n, pa, pb + (j % 3) * kRedBlocks,
                                                                   pb + ((j + 2) % 3) * kRedBlocks, j, d_alpha, d_beta,
                                                                   pb + ((j + 1) % 3) * kRedBlocks);
@@ -1950,7 +1497,7 @@ int meld_b200_estimate_lmax_dist(meld_b200_graph_t *gs, meld_b200_dist_t *d, int
       a.post_epoch = ++d->epoch;
       const unsigned long long dot_epoch = a.post_epoch;
       if (nloc > 0) {
-        MELD_CHECK(launch_step(gs, a, 1, 0, stream));
+        MELD_CHECK(launch_step(gs, a, 1, stream));
       } else {
         a.n_scal_partials = 1;  // pa[0] = 0: an empty rank publishes a zero
         dist_unpermute_kernel<<<1, 256, 0, stream>>>(a, nullptr, nullptr, 0, 1, 1, nullptr);

@@ -59,35 +59,22 @@ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 
 int sm_count();
 
-// Launch configuration of the Chebyshev SpMM kernel (see cheby.cu).  The defaults are
-// the shipped configuration; meld_b200_set_tuning changes them for bench sweeps.
+// Launch configuration of the Chebyshev SpMM kernels (see cheby.cu) and of the graph build (knn.cu, knn_tc.cu).  The
+// defaults are the shipped configuration; meld_b200_set_tuning changes them for bench sweeps and tests.
 struct Tuning {
-  int blk_chunk = 768;    // target CSR entries per row block (C)
-  int stage_cap = 1024;   // CSR entries of shared memory per pipeline stage (multiple of 8, <= 2048)
-  int dict_cap = 768;     // distinct columns (dictionary entries) per stage (multiple of 4)
-  int row_cap = 64;       // rows per stage whose own T / R slices are staged (multiple of 8)
-  int n_stage = 0;        // TMA pipeline depth per CTA (0 = as many as fit in shared memory)
-  int threads = 512;      // threads per CTA: 1 producer warp + gather warps + compute warps
-  int gather_warps = 3;
-  int gather_rows = 0;    // dictionary rows per warp-level cp.async instruction (0 = as many as lanes allow)
-  int gather_cg = 0;      // 1: gathers bypass L1 (cp.async.cg)
-  int team_warps = 4;     // compute warps per team; teams take alternate blocks
-  int ctas_per_sm = 1;    // persistent CTAs per SM
+  int blk_chunk = 768;    // target CSR entries per row block (the nonzero-balanced row ranges of flat_sched = 1)
+  int ctas_per_sm = 1;    // persistent CTAs per SM (round-1 flat kernels)
   int group = 0;          // lanes per row (0 = choose from mean nnz/row)
-  int use_dict = 1;       // 0: every block takes the direct (global-memory) path
-  int x_mode = 2;         // 0: dictionary + cp.async gathers into the stage; 1: staged matrix, direct register gathers;
-                          // 2: flat kernel (no staging: every warp streams its rows and gathers into registers)
   int flat_threads = 1024;  // threads per CTA of the flat kernel (1024: <= 64 registers, 768: <= 80)
   int flat_pipe = 2;      // software-pipelined flat kernel (8 lanes per row): 0 never, 1 for P <= 4, 2 for P = 1 only
                           // (measured: 154 us either way at p = 4 -- L1-tag bound; Lanczos p = 1 gains 15 %)
   int flat_sched = 1;     // flat kernel: 1 = every CTA owns a contiguous, nonzero-balanced row range; 0 = round-robin
-  int flat_group = 0;     // lanes per row of the flat kernel (0 = like the staged kernel)
+  int flat_group = 0;     // lanes per row of the flat kernel (0 = `group`)
   int pad_width = 0;      // 1: signals of 3 / 5..7 columns run zero-padded to 4 / 8 (measured slower, see cheby.cu)
   int flat_gen = 1;       // 1: second-generation flat kernel (cheby_flat2_kernel), 0: the round-1 flat kernels
   int flat_hint = -1;     // cheby_flat2_kernel HINT (0..3, see cheby.cu); -1: chosen from the signal width
   int flat_layout = -1;   // cheby_flat2_kernel LAYOUT (0: 4 consecutive entries per lane, 1: lane-consecutive); -1: auto
   int reorder = 1;        // knn_graph_build orders cells along a Morton curve of the leading dims
-  int use_graph = 1;      // reserved
   int tc_multicast = 2;   // candidate search: CTA cluster size (1, 2, 4) sharing B tiles by TMA multicast
   int p1_segments = 0;    // candidate search pass 1 scans this many column segments per row (own first; 0 = all)
   int prune = 1;          // candidate search skips (row tile, column tile) pairs that bounding balls prove too far apart
@@ -183,8 +170,8 @@ struct DevBuf {
   DevBuf &operator=(const DevBuf &) = delete;
 };
 
-// Elements of padding appended to col/val so the 16-byte aligned TMA bulk copies of
-// a row block may start before / end after the block's own entries.
+// Elements of padding appended to col/val so the kernels' 16- / 32-byte vector loads of a row's entries may start
+// before / end after the row's own entries.
 constexpr int kCsrPad = 16;
 
 }  // namespace meld
@@ -196,18 +183,11 @@ struct meld_b200_graph {
   meld::DevBuf<int32_t> row_ptr{true};  // n_rows + 1
   meld::DevBuf<int32_t> col{true};      // nnz + kCsrPad
   meld::DevBuf<double> val{true};       // nnz + kCsrPad
-  // Row-block partition for the TMA-staged SpMM: block b = rows [blk[b], blk[b+1]).
+  // Row-block partition (blocks of ~blk_chunk entries): block b = rows [blk[b], blk[b+1]); the SpMM kernels cut their
+  // per-CTA row ranges at block boundaries so every CTA streams the same number of nonzeros.
   meld::DevBuf<int32_t> blk{true};  // n_blk + 1
   int32_t n_blk = 0;
   int32_t blk_chunk = 0;  // target nnz per block (C)
-  int32_t max_row_nnz = 0;
-  // Per-block column dictionaries: dict[b * dict_cap + t] = t-th distinct column of block b,
-  // dcnt[b] = their number (-1: block takes the direct path), lidx[e] = position of col[e].
-  meld::DevBuf<int32_t> dict{true};
-  meld::DevBuf<int32_t> dcnt{true};
-  meld::DevBuf<uint16_t> lidx{true};  // nnz + kCsrPad
-  int32_t stage_cap = 0, dict_cap = 0, row_cap = 0, x_mode = 0;
-  int64_t dict_total = 0, direct_blocks = 0;  // statistics
   // Cell order used internally (graph row a = caller's cell perm[a]); null = identity.
   meld::DevBuf<int32_t> perm{true};
   // Row slices of a partitioned operator: bit k of halo[i] = the k-th peer (ranks in order, this one skipped)
@@ -253,6 +233,6 @@ struct meld_b200_dist {
 };
 
 namespace meld {
-// Build the row-block partition (and max_row_nnz) of a graph whose row_ptr is final.
+// Build the row-block partition of a graph whose row_ptr is final.
 int graph_finalize(meld_b200_graph *g, cudaStream_t stream);
 }  // namespace meld

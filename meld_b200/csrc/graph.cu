@@ -166,166 +166,18 @@ __global__ void partition_rows_kernel(const int32_t *__restrict__ row_ptr, int64
   blk[b] = (int32_t)lo;
 }
 
-__global__ void max_row_nnz_kernel(const int32_t *__restrict__ row_ptr, int64_t n_rows, int32_t *out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int32_t m = 0;
-  for (; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) m = max(m, row_ptr[i + 1] - row_ptr[i]);
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
-}
-
-// One CTA per block: sort the block's columns, keep the distinct ones as the block dictionary and
-// rewrite every entry's column as its position in it.
-constexpr int kDictThreads = 256;
-constexpr int kDictMax = 2048;  // stage_cap limit
-
-__global__ void __launch_bounds__(kDictThreads) build_dict_kernel(const int32_t *__restrict__ row_ptr,
-                                                                 const int32_t *__restrict__ col,
-                                                                 const int32_t *__restrict__ blk, int cap, int ucap,
-                                                                 int rcap, int use_dict, int x_mode,
-                                                                 int32_t *__restrict__ dict,
-                                                                 int32_t *__restrict__ dcnt,
-                                                                 uint16_t *__restrict__ lidx) {
-  __shared__ int32_t keys[kDictMax];
-  __shared__ int32_t dist[kDictMax];
-  __shared__ int32_t scan[kDictThreads + 1];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int r0 = blk[b], r1 = blk[b + 1];
-  const int e0 = row_ptr[r0], e1 = row_ptr[r1];
-  const int n = e1 - e0;
-  const int a0 = e0 & ~7, nal = ((e1 - a0) + 7) & ~7;
-  const int ra = r0 & ~3, nr = ((r1 + 1 - ra) + 3) & ~3;
-  if (n == 0 || !use_dict || nal > cap || nr > rcap || n > kDictMax) {  // block-uniform
-    if (tid == 0) dcnt[b] = n == 0 ? 0 : -1;
-    return;
-  }
-  if (x_mode >= 1) {  // direct gathers (staged matrix or flat kernel): no dictionary
-    if (tid == 0) dcnt[b] = 0;
-    return;
-  }
-  int size = 1;
-  while (size < n) size <<= 1;
-  for (int i = tid; i < size; i += kDictThreads) keys[i] = i < n ? col[e0 + i] : 0x7fffffff;
-  __syncthreads();
-  for (int k = 2; k <= size; k <<= 1) {  // bitonic sort, ascending
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < size; i += kDictThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const int32_t x = keys[i], y = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) {
-            keys[i] = y;
-            keys[ixj] = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  // distinct values: each thread owns a contiguous slice of the sorted keys
-  const int per = (n + kDictThreads - 1) / kDictThreads;
-  const int lo = min(tid * per, n), hi = min(lo + per, n);
-  int heads = 0;
-  for (int i = lo; i < hi; ++i) heads += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-  scan[tid + 1] = heads;
-  if (tid == 0) scan[0] = 0;
-  __syncthreads();
-  if (tid == 0)
-    for (int i = 1; i <= kDictThreads; ++i) scan[i] += scan[i - 1];
-  __syncthreads();
-  const int u = scan[kDictThreads];
-  if (u > ucap) {
-    if (tid == 0) dcnt[b] = -1;
-    return;
-  }
-  int pos = scan[tid];
-  for (int i = lo; i < hi; ++i)
-    if (i == 0 || keys[i] != keys[i - 1]) dist[pos++] = keys[i];
-  __syncthreads();
-  for (int i = tid; i < u; i += kDictThreads) dict[(size_t)b * ucap + i] = dist[i];
-  if (tid == 0) dcnt[b] = u;
-  for (int i = tid; i < n; i += kDictThreads) {
-    const int32_t c = col[e0 + i];
-    int l = 0, h = u;  // lower_bound
-    while (l < h) {
-      const int m = (l + h) >> 1;
-      if (dist[m] < c)
-        l = m + 1;
-      else
-        h = m;
-    }
-    lidx[e0 + i] = (uint16_t)l;
-  }
-}
-
-__global__ void dict_stats_kernel(const int32_t *__restrict__ dcnt, int n_blk, unsigned long long *out2) {
-  unsigned long long tot = 0, direct = 0;
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_blk; b += gridDim.x * blockDim.x) {
-    const int u = dcnt[b];
-    if (u < 0)
-      ++direct;
-    else
-      tot += (unsigned long long)u;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    direct += __shfl_xor_sync(0xffffffffu, direct, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(out2, tot);
-    atomicAdd(out2 + 1, direct);
-  }
-}
-
 int graph_finalize(meld_b200_graph *g, cudaStream_t stream) {
-  const Tuning &t = tuning();
-  const int32_t chunk = t.blk_chunk;
-  MELD_REQUIRE(t.stage_cap % 8 == 0 && t.stage_cap <= kDictMax && t.stage_cap >= chunk && t.dict_cap % 4 == 0 &&
-                   t.dict_cap >= 4 && t.row_cap % 8 == 0 && t.row_cap >= 8,
-               "graph_finalize: bad tuning (stage_cap=%d dict_cap=%d row_cap=%d blk_chunk=%d)", t.stage_cap,
-               t.dict_cap, t.row_cap, chunk);
-  g->stage_cap = t.stage_cap;
-  g->dict_cap = t.dict_cap;
-  g->row_cap = t.row_cap;
-  g->x_mode = t.x_mode;
+  const int32_t chunk = tuning().blk_chunk;
+  MELD_REQUIRE(chunk >= 32, "graph_finalize: bad tuning (blk_chunk=%d)", chunk);
   g->blk_chunk = chunk;
   g->n_blk = (int32_t)(g->nnz > 0 ? ceil_div(g->nnz, chunk) : 1);
   MELD_CHECK(g->blk.alloc((size_t)g->n_blk + 1));
   partition_rows_kernel<<<(unsigned)ceil_div(g->n_blk + 1, 256), 256, 0, stream>>>(g->row_ptr.p, g->n_rows, chunk,
                                                                                   g->n_blk, g->blk.p);
   MELD_LAUNCH_CHECK();
-  DevBuf<int32_t> mx;
-  MELD_CHECK(mx.alloc(1));
-  MELD_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int32_t), stream));
-  if (g->n_rows > 0) {
-    int grid = (int)(ceil_div(g->n_rows, 256) < 1184 ? ceil_div(g->n_rows, 256) : 1184);
-    max_row_nnz_kernel<<<grid, 256, 0, stream>>>(g->row_ptr.p, g->n_rows, mx.p);
-    MELD_LAUNCH_CHECK();
-  }
-  MELD_CUDA(cudaMemcpyAsync(&g->max_row_nnz, mx.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  // block dictionaries
-  MELD_CHECK(g->dcnt.alloc((size_t)g->n_blk));
-  if (t.x_mode == 0) {  // only the dictionary-staged kernel reads these
-    MELD_CHECK(g->dict.alloc((size_t)g->n_blk * g->dict_cap));
-    MELD_CHECK(g->lidx.alloc((size_t)g->nnz + kCsrPad));
-    MELD_CUDA(cudaMemsetAsync(g->lidx.p, 0, ((size_t)g->nnz + kCsrPad) * sizeof(uint16_t), stream));
-  }
-  build_dict_kernel<<<g->n_blk, kDictThreads, 0, stream>>>(g->row_ptr.p, g->col.p, g->blk.p, g->stage_cap, g->dict_cap,
-                                                          g->row_cap + 8, t.use_dict, t.x_mode, g->dict.p, g->dcnt.p, g->lidx.p);
-  MELD_LAUNCH_CHECK();
-  DevBuf<unsigned long long> st2;
-  MELD_CHECK(st2.alloc(2));
-  MELD_CUDA(cudaMemsetAsync(st2.p, 0, 2 * sizeof(unsigned long long), stream));
-  dict_stats_kernel<<<64, 256, 0, stream>>>(g->dcnt.p, g->n_blk, st2.p);
-  MELD_LAUNCH_CHECK();
-  unsigned long long h2[2] = {0, 0};
-  MELD_CUDA(cudaMemcpyAsync(h2, st2.p, sizeof(h2), cudaMemcpyDeviceToHost, stream));
-  MELD_SYNC(stream);
-  g->dict_total = (int64_t)h2[0];
-  g->direct_blocks = (int64_t)h2[1];
-  g->stats[5] = g->dict_total;
-  g->stats[6] = g->direct_blocks;
+  MELD_SYNC(stream);  // builders return synchronised: the caller may free what it passed in
+  g->stats[5] = 0;
+  g->stats[6] = 0;
   g->stats[7] = g->n_blk;
   return 0;
 }
@@ -375,22 +227,10 @@ int meld_b200_set_tuning(const char *key, int value) {
   MELD_REQUIRE(key != nullptr, "set_tuning: NULL key");
   Tuning &t = tuning();
   if (!strcmp(key, "blk_chunk")) t.blk_chunk = value;
-  else if (!strcmp(key, "stage_cap")) t.stage_cap = value;
-  else if (!strcmp(key, "row_cap")) t.row_cap = value;
-  else if (!strcmp(key, "dict_cap")) t.dict_cap = value;
-  else if (!strcmp(key, "gather_warps")) t.gather_warps = value;
-  else if (!strcmp(key, "team_warps")) t.team_warps = value;
-  else if (!strcmp(key, "gather_rows")) t.gather_rows = value;
-  else if (!strcmp(key, "gather_cg")) t.gather_cg = value;
   else if (!strcmp(key, "p1_segments")) t.p1_segments = value;
-  else if (!strcmp(key, "use_dict")) t.use_dict = value;
-  else if (!strcmp(key, "x_mode")) t.x_mode = value;
   else if (!strcmp(key, "reorder")) t.reorder = value;
-  else if (!strcmp(key, "n_stage")) t.n_stage = value;
-  else if (!strcmp(key, "threads")) t.threads = value;
   else if (!strcmp(key, "ctas_per_sm")) t.ctas_per_sm = value;
   else if (!strcmp(key, "group")) t.group = value;
-  else if (!strcmp(key, "use_graph")) t.use_graph = value;
   else if (!strcmp(key, "tc_multicast")) t.tc_multicast = value;
   else if (!strcmp(key, "prune")) t.prune = value;
   else if (!strcmp(key, "clusters")) t.clusters = value;

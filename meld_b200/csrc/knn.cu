@@ -83,7 +83,7 @@ __global__ void row_norms_kernel(const double *__restrict__ X, const double *__r
 
 // ---- 0b. cell ordering along a Morton curve of the four highest-variance features ---------------
 // Neighbouring rows of the kNN graph then share most of their columns, which is what the Chebyshev
-// kernel's per-block column dictionaries (graph_finalize) and the L1/L2 caches feed on.
+// kernel's gathers (rows of T_k shared through L1 / L2 by neighbouring rows) feed on.
 __global__ void col_partial_sq_kernel(const double *__restrict__ X, const double *__restrict__ mu, int64_t n, int64_t d,
                                       double *partial) {
   for (int64_t k = threadIdx.x; k < d; k += blockDim.x) {
@@ -1276,7 +1276,7 @@ static int build_stage2(int64_t n, const int64_t *cptr, int32_t *cand, double *v
   }
   tm.lap("anisotropy + laplacian");
   MELD_CHECK(graph_finalize(g, stream));
-  tm.lap("finalize (block dictionaries)");
+  tm.lap("finalize (row-block partition)");
   if (perm.p) {  // the graph keeps its own copy (perm may live in the build arena)
     MELD_CHECK(g->perm.alloc(perm.n));
     MELD_CUDA(cudaMemcpyAsync(g->perm.p, perm.p, perm.n * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));

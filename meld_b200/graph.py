@@ -472,8 +472,8 @@ class DeviceGraph:
     def build_stats(self):
         arr = (C.c_int64 * 8)()
         nv.check(nv.lib().meld_b200_graph_build_stats(self._h, arr), "graph_build_stats")
-        keys = ["search_passes", "max_candidates", "candidate_cap", "overflow_rows", "search_impl", "dict_total",
-                "direct_blocks", "row_blocks"]
+        keys = ["search_passes", "max_candidates", "candidate_cap", "overflow_rows", "search_impl", "reserved5",
+                "reserved6", "row_blocks"]
         return {k: int(arr[i]) for i, k in enumerate(keys)}
 
     def build_times(self):

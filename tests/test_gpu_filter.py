@@ -11,8 +11,7 @@ from conftest import GOLDEN_CASES, density_parity, load_golden
 
 pytestmark = pytest.mark.gpu
 
-DEFAULT_X_MODE = 2  # the shipped kernel variant (common.cuh Tuning::x_mode)
-DEFAULT_FLAT_PIPE = 2
+DEFAULT_FLAT_PIPE = 2  # the shipped launch configuration (common.cuh Tuning)
 DEFAULT_FLAT_GEN = 1
 DEFAULT_FLAT_HINT = -1
 DEFAULT_FLAT_LAYOUT = -1
@@ -165,9 +164,9 @@ def test_row_partitioned_steps_match_full(mb):
     assert np.abs(out - ref).max() <= 1e-11 * np.abs(ref).max()
 
 
-def test_hub_row_longer_than_a_stage_and_empty_rows(mb):
-    """A star graph (hub degree >> stage capacity) takes the direct-from-global path; isolated
-    nodes with no stored entries are legal rows."""
+def test_hub_row_and_empty_rows(mb):
+    """A star graph (one row of ~9000 entries among rows of 2: one lane group walks the hub) and isolated nodes
+    with no stored entries are legal rows."""
     cheby, graph_o, _ = _oracle()
     n = 9000
     rows = np.concatenate([np.zeros(n - 11, dtype=int), np.arange(1, n - 10)])
@@ -227,24 +226,20 @@ def test_api_contract_on_device(mb):
 
 
 @pytest.mark.parametrize("tuning", [
-    dict(x_mode=1, gather_warps=1, team_warps=7),        # staged matrix + direct register gathers
-    dict(use_dict=0),                                      # every block on the direct global-memory path
-    dict(blk_chunk=256, stage_cap=512, dict_cap=256, row_cap=16),  # tiny stages: oversize / direct blocks mix in
-    dict(group=16), dict(group=4), dict(team_warps=6), dict(gather_rows=4, gather_warps=4),
-    dict(x_mode=2), dict(x_mode=2, flat_threads=768, flat_group=4), dict(x_mode=2, flat_group=16), dict(x_mode=2, flat_group=32),  # flat kernel
-    dict(x_mode=0),                                        # the dictionary-staged kernel
-    dict(flat_pipe=1), dict(flat_pipe=1, flat_threads=768), dict(flat_pipe=0),  # software-pipelined flat kernel
+    dict(blk_chunk=256), dict(flat_sched=0),               # smaller nonzero-balanced row ranges / round-robin rows
+    dict(group=16), dict(group=4), dict(group=32),          # lanes per row chosen by hand (round-1 kernels for 4 / 32)
+    dict(flat_threads=768, flat_group=4), dict(flat_group=16), dict(flat_group=32), dict(flat_gen=0, flat_sched=0),
+    dict(flat_gen=0, flat_pipe=1), dict(flat_gen=0, flat_pipe=1, flat_threads=768), dict(flat_gen=0, flat_pipe=0),
     dict(flat_gen=0), dict(flat_gen=1, flat_hint=0, flat_layout=0), dict(flat_gen=1, flat_hint=2, flat_layout=1),
-    dict(flat_gen=1, flat_hint=3, flat_layout=0),  # round-1 flat kernel / explicit variants of the second generation
+    dict(flat_gen=1, flat_hint=3, flat_layout=0),  # round-1 flat kernels / explicit variants of the second generation
 ])
 def test_filter_kernel_variants_agree(mb, tuning):
     """Every launch configuration of the Chebyshev kernel computes the same filter (1e-12)."""
     from meld_b200 import _native as nv
 
     cheby, _, _ = _oracle()
-    defaults = dict(blk_chunk=768, stage_cap=1024, dict_cap=768, row_cap=64, n_stage=0, threads=512, gather_warps=3,
-                    team_warps=4, gather_rows=0, ctas_per_sm=1, group=0, use_dict=1, x_mode=DEFAULT_X_MODE, flat_threads=1024,
-                    flat_group=0, flat_pipe=DEFAULT_FLAT_PIPE, flat_gen=DEFAULT_FLAT_GEN, flat_hint=DEFAULT_FLAT_HINT,
+    defaults = dict(blk_chunk=768, ctas_per_sm=1, group=0, flat_threads=1024, flat_group=0, flat_sched=1,
+                    flat_pipe=DEFAULT_FLAT_PIPE, flat_gen=DEFAULT_FLAT_GEN, flat_hint=DEFAULT_FLAT_HINT,
                     flat_layout=DEFAULT_FLAT_LAYOUT)
     g = load_golden("blobs2k5_wagner")
     S = np.random.default_rng(9).normal(size=(g["L"].shape[0], 4))

@@ -33,13 +33,17 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 
 def test_cuda_sass_is_sm100a_and_uses_tma(built_lib):
+    """The distance GEMM of the graph build is tcgen05 + TMA code, the Chebyshev SpMM gathers with 256-bit loads
+    (SASS mnemonics of /opt/skills/guides/B200_PROFILING.md)."""
     import subprocess
 
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
-    assert "cheby_step_kernel" in sass
-    assert "UBLKCP" in sass  # cp.async.bulk (1-D TMA) staging of the CSR row blocks
+    assert "cheby_flat2_kernel" in sass and "cheby_step_kernel" not in sass
+    assert "UTMALDG" in sass  # cp.async.bulk.tensor (TMA) operand tiles of the candidate search
+    assert "UTCHMMA" in sass or "UTCMMA" in sass  # tcgen05.mma
+    assert ".256" in sass  # 256-bit gathers of the signal rows
 
 
 def test_invalid_parameters_raise_reference_messages():
@@ -196,3 +200,44 @@ def test_fit_transform_prefetches_label_codes_on_a_thread(monkeypatch):
     monkeypatch.setattr(op, "fit", boom)
     with pytest.raises(RuntimeError, match="build failed"):
         op.fit_transform(np.zeros((8000, 3)), labels)
+
+
+def test_round2_host_logic_without_a_gpu():
+    """Row partitions, knn clamping, missing labels, filter kernels of the sweep -- everything that runs before the GPU."""
+    import warnings
+
+    import meld_b200
+    from meld_b200 import distributed as mdist
+    from meld_b200.graph import DeviceGraph, _clamp_knn
+
+    # 512-row tiles dealt to ranks in contiguous runs; the last rank takes the remainder
+    assert DeviceGraph.shard_bounds(6000, 3) == [0, 2048, 4096, 6000]
+    assert DeviceGraph.shard_bounds(500000, 8)[-1] == 500000
+    b = DeviceGraph.shard_bounds(500000, 8)
+    assert all(x % 512 == 0 for x in b[:-1]) and all(b[i] < b[i + 1] for i in range(8))
+    assert mdist.chunk_partition(500000, 8) == (62500, [62500 * r for r in range(9)])
+    # graphtools clamps knn > n - 2 with a warning instead of failing
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert _clamp_knn(50, 20) == 18
+        assert any("Cannot set knn" in str(x.message) for x in w)
+    assert _clamp_knn(5, 20) == 5
+    with pytest.raises(ValueError):
+        _clamp_knn(5, 2)
+    # NaN / None labels are refused, never merged into another label
+    op = meld_b200.MELD(verbose=0)
+    with pytest.raises(ValueError, match="missing values"):
+        op._label_codes(np.array(["a", None, "b", "a"], dtype=object))
+    # new constructor keywords are validated like the reference's
+    with pytest.raises(ValueError, match="dist_mode value bogus not recognized"):
+        meld_b200.MELD(verbose=0, dist_mode="bogus")
+    assert meld_b200.MELD(verbose=0, dist_mode="nccl").dist_build == "replicated"
+    assert meld_b200.MELD(verbose=0).dist_build == "rows"
+    assert meld_b200.MELD(verbose=0, decay=None).decay is None  # decay=None is the binary kNN kernel now
+
+
+def test_sharded_filter_rejects_bad_modes():
+    from meld_b200.distributed import ShardedFilter
+
+    with pytest.raises(ValueError, match="mode value tcp not recognized"):
+        ShardedFilter(None, mode="tcp")
