@@ -15,6 +15,7 @@ import numbers
 import os
 import threading
 import time
+import weakref
 
 import numpy as np
 import pandas as pd
@@ -373,7 +374,7 @@ class MELD(object):
         ind = np.zeros((len(codes), p), dtype=int)
         ind[np.arange(len(codes)), codes] = 1
         index = getattr(self, "_labels_index", None) if p == 2 else None
-        self._indicators = pd.DataFrame(ind, index=index, columns=self.samples)
+        self._indicators = pd.DataFrame(ind, index=index, columns=self.samples, copy=False)
         return self._indicators
 
     @property
@@ -385,7 +386,7 @@ class MELD(object):
             p = len(self.samples)
             ind = np.zeros((len(self._codes), p), dtype=int)
             ind[np.arange(len(self._codes)), self._codes] = 1
-            df = pd.DataFrame(ind, index=self._labels_index if p == 2 else None, columns=self.samples)
+            df = pd.DataFrame(ind, index=self._labels_index if p == 2 else None, columns=self.samples, copy=False)
             if self.sample_normalize:
                 df = df / df.sum(axis=0)
             self._indicators = df
@@ -438,15 +439,19 @@ class MELD(object):
         dev = self.graph.device
         d_codes = codes if isinstance(codes, torch.Tensor) else torch.from_numpy(codes).to(dev, non_blocking=True)
         densities = self.transform_device(d_codes, len(samples))
-        # Read-back through ONE persistent pinned staging buffer per size (a pageable 16 MB read-back costs ~3x as long;
-        # a fresh pinned allocation per call costs a cudaHostAlloc of milliseconds, because the DataFrame returned last
-        # time still owns the previous block), then a multi-threaded host copy into the array the DataFrame keeps.
-        staged = _pinned_staging(torch, densities)
-        staged.copy_(densities, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        host = torch.empty(densities.shape, dtype=densities.dtype).copy_(staged).numpy()
+        # Read-back into pinned host memory (a pageable 16 MB read-back costs ~3x as long).  The DataFrame is built
+        # straight on a block of a small pool of pinned buffers that is only reused once nothing refers to the array
+        # any more (_pinned_result); when the caller keeps more results than the pool holds, through one staging
+        # buffer and a host copy.  copy=False: pandas >= 3 otherwise copies (and transposes) the array, ~4 ms for 16 MB.
+        host = _pinned_result(torch, densities)
+        if host is None:
+            staged = _pinned_staging(torch, densities)
+            staged.copy_(densities, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            host = torch.empty(densities.shape, dtype=densities.dtype).copy_(staged).numpy()
         self.timings_["transform"] = time.perf_counter() - t0
-        self.sample_densities = pd.DataFrame(host, index=self._labels_index, columns=self.samples)
+        self.sample_densities = pd.DataFrame(host, index=self._labels_index, columns=self.samples, copy=False)
+        self.timings_["transform_total"] = time.perf_counter() - t0
         return self.sample_densities
 
     def transform_device(self, codes, n_samples):
@@ -561,7 +566,7 @@ class MELD(object):
         out, c0 = [], 0
         for samples, index in meta:
             pi = len(samples)
-            out.append([pd.DataFrame(host[f, :, c0:c0 + pi], index=index, columns=samples)
+            out.append([pd.DataFrame(host[f, :, c0:c0 + pi], index=index, columns=samples, copy=False)  # views of `host`
                         for f in range(len(settings))])
             c0 += pi
         return out[0] if single else out
@@ -636,6 +641,56 @@ def _pinned_staging(torch, like):
             _STAGING.clear()
         buf = _STAGING[key] = torch.empty(like.shape, dtype=like.dtype, device="cpu", pin_memory=True)
     return buf
+
+
+def _alloc_pinned(torch, shape, dtype):
+    return torch.empty(shape, dtype=dtype, device="cpu", pin_memory=True)
+
+
+def _sync_stream(torch, device):
+    torch.cuda.current_stream(device).synchronize()
+
+
+_RESULT_POOL = []  # [pinned tensor, weakref to the ndarray handed out last (None: never used)]
+_RESULT_POOL_MAX = 4
+_RESULT_POOL_BYTES = 1 << 28
+_RESULT_POOL_LOCK = threading.Lock()
+
+
+def _pinned_result(torch, dev_tensor):
+    """Copy a CUDA tensor into a pinned host block and return it as an ndarray WITHOUT a second host copy.
+
+    A block is handed out again only when the array made from it last time is gone (every view of that array -- the
+    DataFrame's blocks, ``df.values`` -- keeps it alive, so a live result is never overwritten).  At most
+    ``_RESULT_POOL_MAX`` blocks / ``_RESULT_POOL_BYTES`` stay pinned; a caller that holds more results than that, or
+    asks for a bigger one, gets None and the staged copy.  Allocating a pinned block costs milliseconds
+    (cudaHostAlloc), which is why they are kept."""
+    nbytes = dev_tensor.numel() * dev_tensor.element_size()
+    if nbytes == 0 or nbytes > _RESULT_POOL_BYTES:
+        return None
+    shape, dtype = tuple(dev_tensor.shape), dev_tensor.dtype
+
+    def is_free(e):
+        return e[1] is None or e[1]() is None
+
+    with _RESULT_POOL_LOCK:  # two threads must not pick the same free block
+        entry = next((e for e in _RESULT_POOL if is_free(e) and tuple(e[0].shape) == shape and e[0].dtype == dtype), None)
+        if entry is None:
+            busy = [e for e in _RESULT_POOL if not is_free(e)]
+            held = sum(e[0].numel() * e[0].element_size() for e in busy)
+            if len(busy) >= _RESULT_POOL_MAX or held + nbytes > _RESULT_POOL_BYTES:
+                return None  # the caller holds every block: do not pin more
+            _RESULT_POOL[:] = busy  # blocks of other shapes nobody refers to go
+            entry = [_alloc_pinned(torch, shape, dtype), None]
+            _RESULT_POOL.append(entry)
+        placeholder = np.empty(0)
+        entry[1] = weakref.ref(placeholder)  # taken: busy until the result array replaces this below
+    entry[0].copy_(dev_tensor, non_blocking=True)
+    _sync_stream(torch, dev_tensor.device)
+    host = entry[0].numpy()
+    entry[1] = weakref.ref(host)
+    del placeholder
+    return host
 
 
 _HASH_MULT = np.random.default_rng(0x5EED).integers(1, 2**63 - 1, size=64, dtype=np.int64).astype(np.uint64) | np.uint64(1)

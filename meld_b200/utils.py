@@ -46,7 +46,7 @@ def normalize_densities(sample_densities):
         return out
     norm = out.cpu().numpy()
     if is_df:
-        norm = pd.DataFrame(norm, index=index, columns=columns)
+        norm = pd.DataFrame(norm, index=index, columns=columns, copy=False)  # a fresh array: no second copy
     return norm
 
 

@@ -241,3 +241,50 @@ def test_sharded_filter_rejects_bad_modes():
 
     with pytest.raises(ValueError, match="mode value tcp not recognized"):
         ShardedFilter(None, mode="tcp")
+
+
+def test_pinned_result_pool_never_overwrites_a_live_result(monkeypatch):
+    """meld.py::_pinned_result hands a block out again only when nothing refers to the array made from it; a caller
+    that holds more results than the pool keeps gets None (the staged-copy path).  Pinned allocation and the stream
+    synchronisation are replaced by host stand-ins: the bookkeeping is what is tested here."""
+    import gc
+
+    import pandas as pd
+    import torch
+
+    from meld_b200 import meld as mm
+
+    allocs = []
+
+    def fake_alloc(torch_, shape, dtype):
+        allocs.append(shape)
+        return torch.empty(shape, dtype=dtype)
+
+    monkeypatch.setattr(mm, "_alloc_pinned", fake_alloc)
+    monkeypatch.setattr(mm, "_sync_stream", lambda torch_, device: None)
+    monkeypatch.setattr(mm, "_RESULT_POOL", [])
+    src = [torch.full((50, 3), float(i), dtype=torch.float64) for i in range(8)]
+    a = mm._pinned_result(torch, src[0])
+    df = pd.DataFrame(a, columns=list("xyz"), copy=False)
+    del a
+    b = mm._pinned_result(torch, src[1])  # `df` still views the first block: a second one is allocated
+    assert len(allocs) == 2 and float(df.values[0, 0]) == 0.0 and float(b[0, 0]) == 1.0
+    del df
+    gc.collect()
+    c = mm._pinned_result(torch, src[2])  # the first block is free again: no new allocation
+    assert len(allocs) == 2 and float(c[0, 0]) == 2.0 and float(b[0, 0]) == 1.0
+    held = [b, c]
+    while True:
+        got = mm._pinned_result(torch, src[len(held)])
+        if got is None:
+            break
+        held.append(got)
+    assert len(held) == mm._RESULT_POOL_MAX  # every block is referenced: the pool does not grow past its cap
+    assert [float(h[0, 0]) for h in held] == [1.0, 2.0, 2.0, 3.0]  # and none was overwritten
+    other = mm._pinned_result(torch, torch.zeros((7, 2), dtype=torch.float64))
+    assert other is None  # still capped, whatever the shape
+    del held, b, c, got
+    gc.collect()
+    other = mm._pinned_result(torch, torch.ones((7, 2), dtype=torch.float64))  # unreferenced blocks of another shape go
+    assert other is not None and other.shape == (7, 2) and len(mm._RESULT_POOL) == 1
+    assert mm._pinned_result(torch, torch.zeros((0, 2), dtype=torch.float64)) is None
