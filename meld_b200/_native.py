@@ -125,6 +125,20 @@ def current_stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def from_numpy_readonly(arr):
+    """``torch.from_numpy`` for arrays the engine only reads.  ``DataFrame.values`` is read-only under pandas'
+    copy-on-write and torch warns about tensors over non-writable memory; nothing here writes to its inputs."""
+    import warnings
+
+    import torch
+
+    if arr.flags.writeable:
+        return torch.from_numpy(arr)
+    with warnings.catch_warnings():
+        warnings.filterwarnings("ignore", message="The given NumPy array is not writable", category=UserWarning)
+        return torch.from_numpy(arr)
+
+
 def ptr(t):
     """Raw device pointer of a contiguous torch tensor (or None)."""
     if t is None:

@@ -556,7 +556,7 @@ def _as_device_f64(torch, x):
         arr = np.asarray(getattr(x, "values", x))
         if arr.dtype != np.float64 and arr.dtype != np.float32:
             arr = arr.astype(np.float64)
-        t = torch.from_numpy(np.ascontiguousarray(arr))
+        t = nv.from_numpy_readonly(np.ascontiguousarray(arr))
     if not t.is_cuda:
         if t.is_contiguous() and t.numel() * t.element_size() >= (64 << 20) and not t.is_pinned():
             t = _pageable_to_device(torch, t)

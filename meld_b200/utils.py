@@ -37,7 +37,7 @@ def normalize_densities(sample_densities):
         arr = np.ascontiguousarray(np.asarray(getattr(sample_densities, "values", sample_densities), dtype=np.float64))
         if arr.ndim != 2:
             raise ValueError("Expected 2D array, got {}D array instead".format(arr.ndim))
-        x = torch.from_numpy(arr).cuda()
+        x = nv.from_numpy_readonly(arr).cuda()
     n, p = x.shape
     out = torch.empty_like(x)
     nv.check(nv.lib().meld_b200_l1_normalize_rows(nv.ptr(x), n, p, nv.ptr(out), nv.current_stream_ptr()),

@@ -288,3 +288,20 @@ def test_pinned_result_pool_never_overwrites_a_live_result(monkeypatch):
     other = mm._pinned_result(torch, torch.ones((7, 2), dtype=torch.float64))  # unreferenced blocks of another shape go
     assert other is not None and other.shape == (7, 2) and len(mm._RESULT_POOL) == 1
     assert mm._pinned_result(torch, torch.zeros((0, 2), dtype=torch.float64)) is None
+
+
+def test_read_only_inputs_do_not_warn():
+    """DataFrame.values is read-only under pandas' copy-on-write; the engine only reads its inputs, so the torch view
+    of them is made without torch's non-writable warning (and without a copy)."""
+    import warnings
+
+    from meld_b200 import _native as nv
+
+    arr = np.arange(12.0).reshape(3, 4)
+    arr.setflags(write=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        t = nv.from_numpy_readonly(arr)
+    assert t.data_ptr() == arr.ctypes.data and tuple(t.shape) == (3, 4)
+    w = np.ones(3)
+    assert nv.from_numpy_readonly(w).data_ptr() == w.ctypes.data
