@@ -24,8 +24,6 @@ to rounding (tests/test_gpu_graph.py::test_device_pca_matches_sklearn), not mere
 
 from __future__ import annotations
 
-import numpy as np
-
 from . import _native as nv
 
 
